@@ -1,0 +1,207 @@
+/*
+ * mn_b200.h — C ABI of the B200-native Mega-NeRF rendering hot path (libmn_b200.so).
+ *
+ * The reference (cmusatyalab/mega-nerf @76d8d76b) is pure Python/PyTorch and has NO FFI / plugin
+ * boundary of its own; this header defines the boundary underneath the Python call
+ * surface it does have.  Each entry point cites the reference code it replaces (file:line, relative
+ * to the reference repository root).  The Python host mirror lives in mega_nerf_b200/*.py and binds
+ * these symbols with ctypes.
+ *
+ * Conventions
+ *  - every pointer named *_d is a DEVICE pointer to fp32 (or int32 where stated), row-major, borrowed
+ *    for the duration of the call; nothing is retained except by mn_model_set_weights (see there);
+ *  - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); all work is
+ *    enqueued on it, no entry point synchronises the host unless stated;
+ *  - every function returns MN_OK or an MN_ERR_* code; mn_last_error(ctx) gives the message.  Error
+ *    texts for the two reference exceptions are the reference's own (nerf.py:121-123,
+ *    rendering.py:412-414) so the Python shim can re-raise `Exception(msg)` verbatim;
+ *  - entry points are thread-safe per context, keep no hidden global state and spawn no threads.
+ */
+#ifndef MN_B200_H
+#define MN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MN_ABI_VERSION 1
+
+enum {
+    MN_OK = 0,
+    MN_ERR_INVALID = 1,    /* bad argument */
+    MN_ERR_CUDA = 2,       /* a CUDA runtime call or launch failed */
+    MN_ERR_SHAPE = 3,      /* "Unexpected input shape: ..."                (models/nerf.py:121-123) */
+    MN_ERR_SPHERE = 4,     /* "Not all your cameras are bounded by ..."    (rendering.py:412-414)  */
+    MN_ERR_WORKSPACE = 5,  /* workspace too small */
+    MN_ERR_UNSUPPORTED = 6 /* configuration outside what the kernels cover */
+};
+
+/* Arithmetic of the MLP stage. */
+enum {
+    MN_PREC_FP32 = 0,      /* CUDA-core fp32 FMA, parity mode (<= 1e-5 of the fp32 oracle)              */
+    MN_PREC_TC_F16 = 1,    /* tcgen05 kind::f16, fp16 operands, fp32 TMEM accumulate, 1 MMA pass        */
+    MN_PREC_TC_F16X3 = 2   /* tcgen05, hi/lo fp16 split of both operands, 3 MMA passes per algorithmic  */
+};
+
+typedef struct mn_ctx mn_ctx;
+typedef struct mn_model mn_model;
+
+/* ---- context --------------------------------------------------------------------------------- */
+int mn_abi_version(void);
+int mn_create(mn_ctx** out, int device);
+void mn_destroy(mn_ctx* ctx);
+const char* mn_last_error(const mn_ctx* ctx);
+/* Device-side status word written by kernels that detect reference exceptions (sphere check) or
+ * capacity overflow; mn_check_status copies it back (this one DOES synchronise `stream`) and maps it
+ * to MN_ERR_SPHERE / MN_ERR_WORKSPACE.  Call it where the reference has its own host sync
+ * (rendering.py:412 `.any()`).  */
+int mn_check_status(mn_ctx* ctx, void* stream);
+
+/* Measurement hooks used by bench.py: number of kernels launched through this context so far, and
+ * CUDA-event timing (on the launching stream) of the MLP-stage kernel launches. */
+long long mn_launch_count(const mn_ctx* ctx);
+int mn_profile_enable(mn_ctx* ctx, int on);
+int mn_profile_read(mn_ctx* ctx, double* total_ms, long long* n_launches);
+
+/* ---- ray generation --------------------------------------------------- mega_nerf/ray_utils.py */
+/* get_ray_directions (ray_utils.py:6-18): out_d [H*W*3]. */
+int mn_ray_directions(mn_ctx* ctx, int W, int H, float fx, float fy, float cx, float cy, int center_pixels,
+                      float* out_d, void* stream);
+/* get_rays / get_rays_batch / _get_rays_inner / _truncate_with_plane_intersection
+ * (ray_utils.py:21-84).  dirs_d [n_dirs_sets? P*3] with dirs_batched!=0 meaning [n,P,3];
+ * c2w_d [n,3,4]; out_d [n,P,8] = (o3,d3,near,far). */
+int mn_rays(mn_ctx* ctx, const float* dirs_d, int dirs_batched, const float* c2w_d, int n_poses, int64_t P,
+            float near, float far, int has_altitude, float alt_max, float alt_min, float* out_d, void* stream);
+
+/* ---- sampling --------------------------------------------------------- mega_nerf/rendering.py */
+/* Coarse depths + optional stratified jitter + points (rendering.py:82-87, 472-483).
+ *   rays_d [N,8]; z_steps_d [S] (torch.linspace(0,1,S) — passed in, never restated);
+ *   far_d optional [N] override of rays[:,7] (fg_far clamp, rendering.py:45);
+ *   rand_d optional [N,S] U[0,1) draws, used iff perturb>0;  z_out_d [N,S]; xyz_out_d [N,S,3]. */
+int mn_sample_coarse(mn_ctx* ctx, const float* rays_d, const float* far_d, const float* z_steps_d,
+                     const float* rand_d, float perturb, int64_t N, int S, float* z_out_d, float* xyz_out_d,
+                     void* stream);
+/* Stratified expansion of a shared 1-D depth vector (background path, rendering.py:47-50). */
+int mn_stratify(mn_ctx* ctx, const float* z_d, int64_t z_row_stride, const float* rand_d, float perturb, int64_t N,
+                int S, float* z_out_d, void* stream);
+/* xyz = o + d*z, separately rounded mul and add (rendering.py:100 lambda, :223). */
+int mn_points_from_z(mn_ctx* ctx, const float* rays_d, const float* z_d, int64_t N, int S, float* xyz_out_d,
+                     void* stream);
+/* _sample_pdf / _sample_cdf (rendering.py:486-536).  Exactly one of weights_d / cdf_d is given:
+ *   weights_d [N, w_stride] is the FULL coarse weight row; columns 1..S-2 are used (rendering.py:215);
+ *   cdf_d [N,S-2] is an externally supplied cdf (stage test: indices are bit-exact given cdf and u);
+ *   z_coarse_d [N,S] (bins are its midpoints, rendering.py:213);  u_d [F] (u_row_stride=0) or [N,F];
+ *   z_out_d [N,F]; inds_out_d optional int64 [N,F]; cdf_out_d optional [N,S-2]. */
+int mn_sample_pdf(mn_ctx* ctx, const float* z_coarse_d, const float* weights_d, int64_t w_stride,
+                  const float* cdf_d, const float* u_d, int64_t u_row_stride, int64_t N, int S, int F,
+                  float* z_out_d, int64_t* inds_out_d, float* cdf_out_d, void* stream);
+/* Per-ray sort of cat[a, b] (ascending, or descending) — cascade resample merge (rendering.py:219). */
+int mn_sort_cat(mn_ctx* ctx, const float* a_d, int na, const float* b_d, int nb, int64_t N, int descending,
+                float* out_d, void* stream);
+
+/* Volume rendering (rendering.py:336-393).  One warp per ray.
+ *   own samples: raw_d [N,S,4] = (r,g,b,sigma) and z_d [N,S] of THIS pass (already flipped if flip);
+ *   optional stored coarse samples to merge with (non-cascade fine pass, rendering.py:336-350):
+ *     raw2_d [N,S2,4], z2_d [N,S2] (and depth_real2_d) — sorted together by z, descending iff flip;
+ *   last_delta_d [N]: 1e10, or the sphere-exit depth for rays that continue into the background; when
+ *     < 1e10 the max of the pass's OWN z is subtracted first (rendering.py:191-193,224-225; quirk Q5);
+ *   depth_real_d optional [N,S]: background real depths used for the depth outputs.
+ *   outputs (any may be NULL): weights [N,S+S2] (merged order), rgb [N,3], depth [N], depth_var [N],
+ *   bg_lambda [N]. */
+int mn_composite(mn_ctx* ctx, const float* raw_d, const float* z_d, const float* depth_real_d, int S,
+                 const float* raw2_d, const float* z2_d, const float* depth_real2_d, int S2,
+                 const float* last_delta_d, int64_t N, int flip,
+                 float* weights_out_d, float* rgb_out_d, float* depth_out_d, float* depth_var_out_d,
+                 float* bg_lambda_out_d, void* stream);
+
+/* Background geometry (rendering.py:396-469).
+ * mn_intersect_sphere: fg_far [N]; raises the device status MN_ERR_SPHERE when a camera lies outside. */
+int mn_intersect_sphere(mn_ctx* ctx, const float* rays_d, const float* center3_d, const float* radius3_d, int64_t N,
+                        float* fg_far_out_d, void* stream);
+/* mn_points_outside: for rays selected by ray_ids_d (int64 [n], or NULL = all), inverse depths
+ * depth_d [n,S] -> pts [n,S,4] (or [n,S,7] with the real-xyz routing prefix) and depth_real [n,S]. */
+int mn_points_outside(mn_ctx* ctx, const float* rays_d, const int64_t* ray_ids_d, const float* depth_d,
+                      const float* center3_d, const float* radius3_d, int64_t n, int S, int include_xyz_real,
+                      int cluster_2d, float* pts_out_d, float* depth_real_out_d, void* stream);
+
+/* eval_sh + sigmoid (spherical_harmonics.py:55-106, rendering.py:301-306).
+ *   coef_d [B, coef_stride]: first 3*(deg+1)^2 columns are channel-major SH coefficients, column
+ *   3*(deg+1)^2 is sigma (copied through);  dirs_d [B/dir_div, 3];  out_d [B,4]. */
+int mn_sh_to_rgb(mn_ctx* ctx, int deg, const float* coef_d, int64_t coef_stride, const float* dirs_d,
+                 int64_t dir_stride, int dir_div, int64_t B, int apply_sigmoid, float* out_d, void* stream);
+/* Embedding.forward (models/nerf.py:8-25): x [B,dim] -> [B, dim*(1+2*n_freqs)]. */
+int mn_embed(mn_ctx* ctx, const float* x_d, int64_t B, int dim, int n_freqs, float* out_d, void* stream);
+
+/* ---- networks --------------------------------------------------------- mega_nerf/models/*.py */
+typedef struct {
+    int kind;              /* 0 = NeRF (nerf.py:45), 1 = Cascade (cascade.py:7; sub 0 coarse, 1 fine),
+                              2 = MegaNeRF (mega_nerf.py:7; n_sub sub-modules)                        */
+    int n_sub;
+    int pos_xyz_dim, pos_dir_dim, layers, layer_dim, appearance_dim, affine_appearance, appearance_count,
+        rgb_dim, xyz_dim, shifted_softplus;
+    int n_skip;
+    int skip_layers[8];
+    float boundary_margin; /* MegaNeRF only */
+    int xyz_real;          /* MegaNeRF only: first 3 input columns are routing-only (mega_nerf.py:36) */
+    int cluster_dim_start; /* MegaNeRF only: 1 if cluster_2d */
+} mn_model_desc;
+
+/* fp32 device tensors of one NeRF sub-module, in the reference state-dict layout ([out,in] row-major). */
+typedef struct {
+    const float* xyz_w[16];
+    const float* xyz_b[16];
+    const float *sigma_w, *sigma_b, *final_w, *final_b, *dir_a_w, *dir_a_b, *rgb_w, *rgb_b, *embedding_a,
+        *affine_w, *affine_b;
+} mn_nerf_weights;
+
+int mn_model_create(mn_ctx* ctx, const mn_model_desc* desc, mn_model** out);
+void mn_model_destroy(mn_model* m);
+/* centroids [n_sub,3] device fp32; copied. */
+int mn_model_set_centroids(mn_model* m, const float* centroids_d, void* stream);
+/* (Re)pack one sub-module: transposes / pads / splits the weights into model-owned device buffers
+ * (the only persistent allocation the library makes).  Call again whenever the parameters change. */
+int mn_model_set_weights(mn_model* m, int sub, const mn_nerf_weights* w, void* stream);
+
+/* Where the per-row model inputs come from.  Mirrors the two ways the reference builds rows:
+ *   mode 0 — an explicit row matrix x [B, cols] as handed to nn.Module.__call__ (nerf.py:115);
+ *   mode 1 — ray-structured: xyz [B, xyz_cols] plus per-ray directions / image indices that the
+ *            reference would broadcast with repeat+cat (rendering.py:275-292,311-319): row b belongs
+ *            to ray b / samples_per_ray. */
+typedef struct {
+    int mode;
+    const float* x_d;       /* mode 0: [B, cols]; mode 1: xyz [B, xyz_cols]                          */
+    int cols;               /* mode 0: cols; mode 1: xyz_cols (3, 4, or 7 with the real-xyz prefix)  */
+    const float* dirs_d;    /* mode 1: [n_rays, dir_stride], NULL if the model takes no dirs          */
+    int64_t dir_stride;
+    const float* idx_d;     /* mode 1: [n_rays] image indices as fp32, NULL if no appearance          */
+    int samples_per_ray;    /* mode 1 */
+} mn_rows;
+
+/* Slot capacity per row reserved for blended routing (boundary_margin > 1): a row within the margin
+ * of more sub-modules than this raises MN_ERR_WORKSPACE at the next mn_check_status.  Default
+ * min(n_sub, 4); hard routing always uses 1. */
+int mn_model_set_max_multiplicity(mn_model* m, int max_multiplicity);
+
+size_t mn_model_workspace_bytes(const mn_model* m, int64_t B, int precision);
+/* nn.Module.__call__(x, sigma_only, sigma_noise) for NeRF / Cascade(use_coarse) / MegaNeRF
+ * (nerf.py:115-160, cascade.py:13-18, mega_nerf.py:19-61).  out_d [B, out_cols] with
+ * out_cols = 1 if sigma_only else rgb_dim+1.  sigma_noise_d optional [B].  Returns MN_ERR_SHAPE with
+ * the reference's message on a bad column count. */
+int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int use_coarse, int sigma_only,
+                     const float* sigma_noise_d, int precision, float* out_d, void* workspace_d,
+                     size_t workspace_bytes, void* stream);
+/* Routing only (mega_nerf.py:21-30), for the stage tests: assign_out_d int32 [B] (margin==1) or
+ * weights_out_d [B,n_sub] (margin>1). */
+int mn_model_route(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int32_t* assign_out_d,
+                   float* weights_out_d, void* stream);
+/* Counters of the last mn_model_forward on this model, read back lazily (synchronises `stream`):
+ * slots = routed (row, sub-module) pairs, tiles = 128-row MLP tiles. */
+int mn_model_last_stats(mn_ctx* ctx, mn_model* m, int64_t* slots, int64_t* tiles, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MN_B200_H */

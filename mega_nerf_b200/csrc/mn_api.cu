@@ -1,0 +1,375 @@
+// Context / model management and the nn.Module-level forward entry point of the C ABI.
+#include <vector>
+
+#include "mn_model.cuh"
+
+namespace {
+
+__global__ void transpose_kernel(const float* __restrict__ src, int N, int K, float* __restrict__ dst) {
+    // src [N][K] (nn.Linear weight, [out,in]) -> dst [K][N]
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * K) return;
+    const int k = (int)(i / N), n = (int)(i % N);
+    dst[i] = src[(int64_t)n * K + k];
+}
+
+int pack_T(mn_ctx* ctx, const float* src, int N, int K, float* dst, cudaStream_t st) {
+    const int64_t n = (int64_t)N * K;
+    transpose_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(src, N, K, dst);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}
+
+int al4(int x) { return (x + 3) / 4 * 4; }
+
+void build_layout(mn_model* m) {
+    const mn_model_desc& d = m->d;
+    NetDims& nd = m->nd;
+    nd.layers = d.layers;
+    nd.L = d.layer_dim;
+    nd.xyz_dim = d.xyz_dim;
+    nd.nf_xyz = d.pos_xyz_dim;
+    nd.nf_dir = d.pos_dir_dim;
+    nd.in_xyz = d.xyz_dim + d.xyz_dim * d.pos_xyz_dim * 2;
+    nd.in_dir = d.pos_dir_dim > 0 ? 3 + 3 * d.pos_dir_dim * 2 : 0;
+    nd.app = d.appearance_dim;
+    nd.affine = d.affine_appearance;
+    nd.app_in_dira = (d.appearance_dim > 0 && !d.affine_appearance) ? 1 : 0;
+    nd.aux = nd.in_dir + (nd.app_in_dira ? nd.app : 0);
+    nd.has_dir_a = (d.pos_dir_dim > 0 || nd.app_in_dira) ? 1 : 0;
+    nd.rgb_dim = d.rgb_dim;
+    nd.rgb_in = nd.has_dir_a ? nd.L / 2 : nd.L;
+    nd.softplus = d.shifted_softplus;
+    nd.app_count = d.appearance_count;
+    nd.skip_mask = 0;
+    for (int i = 0; i < d.n_skip; ++i)
+        if (d.skip_layers[i] > 0 && d.skip_layers[i] < 32) nd.skip_mask |= 1 << d.skip_layers[i];
+
+    PackedLayout& l = m->lay;
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += al4(n); return o; };
+    for (int i = 0; i < nd.layers; ++i) {
+        l.kin[i] = (i == 0) ? nd.in_xyz : (((nd.skip_mask >> i) & 1) ? nd.in_xyz + nd.L : nd.L);
+        l.w[i] = take(l.kin[i] * nd.L);
+        l.b[i] = take(nd.L);
+    }
+    l.sigma_w = take(nd.L);
+    l.sigma_b = take(1);
+    l.final_w = take(nd.has_dir_a ? nd.L * nd.L : 0);
+    l.final_b = take(nd.has_dir_a ? nd.L : 0);
+    l.dira_w = take(nd.has_dir_a ? (nd.L + nd.aux) * (nd.L / 2) : 0);
+    l.dira_b = take(nd.has_dir_a ? nd.L / 2 : 0);
+    l.rgb_w = take(nd.rgb_in * nd.rgb_dim);
+    l.rgb_b = take(nd.rgb_dim);
+    l.emb = take(nd.app > 0 ? nd.app_count * nd.app : 0);
+    l.aff_w = take(nd.affine ? nd.app * 12 : 0);
+    l.aff_b = take(nd.affine ? 12 : 0);
+    l.total = off;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mn_abi_version(void) { return MN_ABI_VERSION; }
+
+int mn_create(mn_ctx** out, int device) {
+    if (!out) return MN_ERR_INVALID;
+    mn_ctx* c = new mn_ctx();
+    c->device = device;
+    *out = c;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        c->err = "cudaSetDevice failed (no CUDA device: this library has no CPU fallback)";
+        return MN_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    MN_CUDA(c, cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        c->err = std::string("libmn_b200 is built for sm_100a only; found ") + prop.name;
+        return MN_ERR_UNSUPPORTED;
+    }
+    MN_CUDA(c, cudaMalloc(&c->status_d, sizeof(unsigned int)));
+    MN_CUDA(c, cudaMemset(c->status_d, 0, sizeof(unsigned int)));
+    return MN_OK;
+}
+
+void mn_destroy(mn_ctx* ctx) {
+    if (!ctx) return;
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    if (ctx->status_d) cudaFree(ctx->status_d);
+    delete ctx;
+}
+
+const char* mn_last_error(const mn_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mn_check_status(mn_ctx* ctx, void* stream) {
+    if (!ctx) return MN_ERR_INVALID;
+    unsigned int h = 0;
+    MN_CUDA(ctx, cudaMemcpyAsync(&h, ctx->status_d, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MN_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    if (h) MN_CUDA(ctx, cudaMemsetAsync(ctx->status_d, 0, sizeof(h), (cudaStream_t)stream));
+    if (h & MN_STATUS_SPHERE)
+        return mn_fail(ctx, MN_ERR_SPHERE,
+                       "Not all your cameras are bounded by the unit sphere; please make sure the cameras are "
+                       "normalized properly!");
+    if (h & MN_STATUS_OVERFLOW)
+        return mn_fail(ctx, MN_ERR_WORKSPACE, "routing slot capacity exceeded (raise max multiplicity)");
+    return MN_OK;
+}
+
+long long mn_launch_count(const mn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mn_profile_enable(mn_ctx* ctx, int on) {
+    if (!ctx) return MN_ERR_INVALID;
+    ctx->prof_on = on;
+    ctx->prof_used = 0;
+    return MN_OK;
+}
+
+int mn_profile_read(mn_ctx* ctx, double* total_ms, long long* n_launches) {
+    if (!ctx) return MN_ERR_INVALID;
+    double tot = 0;
+    for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+        MN_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[i + 1]));
+        float ms = 0;
+        MN_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (n_launches) *n_launches = (long long)(ctx->prof_used / 2);
+    ctx->prof_used = 0;
+    return MN_OK;
+}
+
+int mn_model_create(mn_ctx* ctx, const mn_model_desc* desc, mn_model** out) {
+    if (!ctx || !desc || !out) return MN_ERR_INVALID;
+    const mn_model_desc& d = *desc;
+    if (d.kind < 0 || d.kind > 2 || d.n_sub < 1 || d.n_sub > MN_MAX_SUB)
+        return mn_fail(ctx, MN_ERR_INVALID, "mn_model_create: kind / n_sub out of range (n_sub <= 64)");
+    if (d.layers < 1 || d.layers > MN_MAX_LAYERS || d.xyz_dim < 3 || d.xyz_dim > 4 || d.n_skip < 0 || d.n_skip > 8)
+        return mn_fail(ctx, MN_ERR_INVALID, "mn_model_create: layers / xyz_dim / skip_layers out of range");
+    if (d.rgb_dim > 3 && d.pos_dir_dim != 0)
+        return mn_fail(ctx, MN_ERR_INVALID, "rgb_dim > 3 requires pos_dir_dim == 0 (models/nerf.py:52-53)");
+    if (d.kind == 1 && d.n_sub != 2) return mn_fail(ctx, MN_ERR_INVALID, "Cascade needs exactly 2 sub-modules");
+    if (d.kind == 2 && d.boundary_margin < 1.0f)
+        return mn_fail(ctx, MN_ERR_INVALID, "boundary_margin must be >= 1 (models/mega_nerf.py:11)");
+    mn_model* m = new mn_model();
+    m->ctx = ctx;
+    m->d = d;
+    build_layout(m);
+    m->max_multiplicity = d.kind == 2 ? (d.boundary_margin > 1.0f ? (d.n_sub < 4 ? d.n_sub : 4) : 1) : 1;
+    *out = m;
+    MN_CUDA(ctx, cudaMalloc(&m->packed, (size_t)d.n_sub * m->lay.total * sizeof(float)));
+    MN_CUDA(ctx, cudaMemset(m->packed, 0, (size_t)d.n_sub * m->lay.total * sizeof(float)));
+    MN_CUDA(ctx, cudaMalloc(&m->centroids_d, (size_t)MN_MAX_SUB * 3 * sizeof(float)));
+    MN_CUDA(ctx, cudaMalloc(&m->counters_d, CNT_TOTAL * sizeof(int)));
+    MN_CUDA(ctx, cudaMemset(m->counters_d, 0, CNT_TOTAL * sizeof(int)));
+    return MN_OK;
+}
+
+void mn_model_destroy(mn_model* m) {
+    if (!m) return;
+    if (m->packed) cudaFree(m->packed);
+    if (m->centroids_d) cudaFree(m->centroids_d);
+    if (m->counters_d) cudaFree(m->counters_d);
+    if (m->tc_packed) cudaFree(m->tc_packed);
+    delete m;
+}
+
+int mn_model_set_max_multiplicity(mn_model* m, int mult) {
+    if (!m || mult < 1) return MN_ERR_INVALID;
+    m->max_multiplicity = mult > m->d.n_sub ? m->d.n_sub : mult;
+    return MN_OK;
+}
+
+int mn_model_set_centroids(mn_model* m, const float* centroids_d, void* stream) {
+    if (!m || !centroids_d) return MN_ERR_INVALID;
+    mn_ctx* ctx = m->ctx;
+    MN_CUDA(ctx, cudaMemcpyAsync(m->centroids_d, centroids_d, (size_t)m->d.n_sub * 3 * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return MN_OK;
+}
+
+int mn_model_set_weights(mn_model* m, int sub, const mn_nerf_weights* w, void* stream) {
+    if (!m || !w || sub < 0 || sub >= m->d.n_sub) return MN_ERR_INVALID;
+    mn_ctx* ctx = m->ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    const NetDims& nd = m->nd;
+    const PackedLayout& l = m->lay;
+    float* P = m->packed + (size_t)sub * l.total;
+    auto copy = [&](float* dst, const float* src, size_t n) -> int {
+        if (!src) return mn_fail(ctx, MN_ERR_INVALID, "mn_model_set_weights: missing tensor");
+        MN_CUDA(ctx, cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return MN_OK;
+    };
+    int rc;
+    for (int i = 0; i < nd.layers; ++i) {
+        if (!w->xyz_w[i] || !w->xyz_b[i]) return mn_fail(ctx, MN_ERR_INVALID, "mn_model_set_weights: missing trunk layer");
+        if ((rc = pack_T(ctx, w->xyz_w[i], nd.L, l.kin[i], P + l.w[i], st))) return rc;
+        if ((rc = copy(P + l.b[i], w->xyz_b[i], nd.L))) return rc;
+    }
+    if ((rc = copy(P + l.sigma_w, w->sigma_w, nd.L))) return rc;
+    if ((rc = copy(P + l.sigma_b, w->sigma_b, 1))) return rc;
+    if (nd.has_dir_a) {
+        if (!w->final_w || !w->dir_a_w) return mn_fail(ctx, MN_ERR_INVALID, "mn_model_set_weights: missing head");
+        if ((rc = pack_T(ctx, w->final_w, nd.L, nd.L, P + l.final_w, st))) return rc;
+        if ((rc = copy(P + l.final_b, w->final_b, nd.L))) return rc;
+        if ((rc = pack_T(ctx, w->dir_a_w, nd.L / 2, nd.L + nd.aux, P + l.dira_w, st))) return rc;
+        if ((rc = copy(P + l.dira_b, w->dir_a_b, nd.L / 2))) return rc;
+    }
+    if (!w->rgb_w) return mn_fail(ctx, MN_ERR_INVALID, "mn_model_set_weights: missing rgb head");
+    if ((rc = pack_T(ctx, w->rgb_w, nd.rgb_dim, nd.rgb_in, P + l.rgb_w, st))) return rc;
+    if ((rc = copy(P + l.rgb_b, w->rgb_b, nd.rgb_dim))) return rc;
+    if (nd.app > 0)
+        if ((rc = copy(P + l.emb, w->embedding_a, (size_t)nd.app_count * nd.app))) return rc;
+    if (nd.affine) {
+        if (!w->affine_w) return mn_fail(ctx, MN_ERR_INVALID, "mn_model_set_weights: missing affine");
+        if ((rc = pack_T(ctx, w->affine_w, 12, nd.app, P + l.aff_w, st))) return rc;
+        if ((rc = copy(P + l.aff_b, w->affine_b, 12))) return rc;
+    }
+    return mn_mlp_tc_pack(ctx, m, sub, st);
+}
+
+static int64_t slot_capacity(const mn_model* m, int64_t B) {
+    if (m->d.kind != 2) return mn_cdiv(B, MN_TILE) * MN_TILE;
+    return mn_cdiv(B * m->max_multiplicity, MN_TILE) * MN_TILE + (int64_t)m->d.n_sub * MN_TILE;
+}
+
+size_t mn_model_workspace_bytes(const mn_model* m, int64_t B, int precision) {
+    if (!m) return 0;
+    const int64_t cap = slot_capacity(m, B);
+    size_t bytes = 256;
+    if (m->d.kind == 2) {
+        bytes += mn_align((size_t)cap * sizeof(int));                                       // slot_row
+        if (m->d.boundary_margin > 1.0f) {
+            bytes += mn_align((size_t)cap * sizeof(float));                                 // slot_w
+            bytes += mn_align((size_t)B * m->d.n_sub * sizeof(int));                        // row_slots
+            bytes += mn_align((size_t)cap * (m->d.rgb_dim + 1) * sizeof(float));            // slot_out
+        }
+    }
+    if (precision != MN_PREC_FP32) bytes += mn_mlp_tc_workspace(m, cap / MN_TILE, precision);
+    return bytes;
+}
+
+int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int use_coarse, int sigma_only,
+                     const float* sigma_noise_d, int precision, float* out_d, void* workspace_d,
+                     size_t workspace_bytes, void* stream) {
+    if (!ctx || !m || !rows || B < 0) return MN_ERR_INVALID;
+    const mn_model_desc& d = m->d;
+    const NetDims& nd = m->nd;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int has_dir = (!sigma_only && d.pos_dir_dim > 0) ? 1 : 0;
+    const int has_idx = (!sigma_only && d.appearance_dim > 0) ? 1 : 0;
+    const int prefix = (d.kind == 2 && d.xyz_real) ? 3 : 0;
+
+    RowSrc src{};
+    src.xyz_dim = d.xyz_dim;
+    src.net_off = prefix;
+    if (rows->mode == 0) {
+        const int expected = d.xyz_dim + 3 * has_dir + has_idx;
+        if (rows->cols - prefix != expected) {
+            char buf[256];
+            // the child module is what raises (models/nerf.py:121-123); it sees the row matrix minus the
+            // routing prefix, so report that shape.
+            snprintf(buf, sizeof(buf), "Unexpected input shape: torch.Size([%lld, %d]) (expected: %d, xyz_dim: %d)",
+                     (long long)B, rows->cols - prefix, expected, d.xyz_dim);
+            return mn_fail(ctx, MN_ERR_SHAPE, buf);
+        }
+        src.x = rows->x_d;
+        src.cols = rows->cols;
+        src.div = 1;
+        // nerf.py:146 reads directions as x[:, -4:-1]; :149 the index as x[:, -1]
+        src.dirs = rows->x_d + rows->cols - 4;
+        src.dir_stride = rows->cols;
+        src.idx = rows->x_d + rows->cols - 1;
+        src.idx_stride = rows->cols;
+        src.dir_quirk = 0;  // the pointer arithmetic above already reproduces the slice
+    } else {
+        if (rows->cols - prefix != d.xyz_dim) {
+            char buf[256];
+            snprintf(buf, sizeof(buf), "Unexpected input shape: torch.Size([%lld, %d]) (expected: %d, xyz_dim: %d)",
+                     (long long)B, rows->cols - prefix + 3 * (rows->dirs_d ? 1 : 0) + (rows->idx_d ? 1 : 0),
+                     d.xyz_dim + 3 * has_dir + has_idx, d.xyz_dim);
+            return mn_fail(ctx, MN_ERR_SHAPE, buf);
+        }
+        if ((has_dir && !rows->dirs_d) || (has_idx && !rows->idx_d) || rows->samples_per_ray < 1)
+            return mn_fail(ctx, MN_ERR_INVALID, "mn_model_forward: ray-structured rows lack dirs / indices");
+        src.x = rows->x_d;
+        src.cols = rows->cols;
+        src.div = rows->samples_per_ray;
+        src.dirs = rows->dirs_d;
+        src.dir_stride = rows->dir_stride;
+        src.idx = rows->idx_d;
+        src.idx_stride = 1;
+        src.dir_quirk = (has_dir && !has_idx) ? 1 : 0;  // [xyz, dir] rows: x[:, -4:-1] = (z, dx, dy)
+    }
+    if (B == 0) return MN_OK;
+
+    MlpArgs a{};
+    a.nd = nd;
+    a.lay = m->lay;
+    a.packed = m->packed;
+    a.src = src;
+    a.n_sub = d.n_sub;
+    a.B = B;
+    a.sigma_only = sigma_only;
+    a.sigma_noise = sigma_noise_d;
+    a.out = out_d;
+    a.out_cols = sigma_only ? 1 : nd.rgb_dim + 1;
+
+    const int64_t cap = slot_capacity(m, B);
+    const size_t need = mn_model_workspace_bytes(m, B, precision);
+    if (need > 256 && (!workspace_d || workspace_bytes < need))
+        return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_model_forward: workspace too small");
+    char* ws = (char*)workspace_d;
+    auto carve = [&](size_t n) { char* p = ws; ws += mn_align(n); return p; };
+
+    int rc;
+    int* row_slots = nullptr;
+    float* slot_out = nullptr;
+    if (d.kind == 2) {
+        int* slot_row = (int*)carve((size_t)cap * sizeof(int));
+        float* slot_w = nullptr;
+        const bool blend = d.boundary_margin > 1.0f;
+        if (blend) {
+            slot_w = (float*)carve((size_t)cap * sizeof(float));
+            row_slots = (int*)carve((size_t)B * d.n_sub * sizeof(int));
+            slot_out = (float*)carve((size_t)cap * a.out_cols * sizeof(float));
+        }
+        if ((rc = mn_route_build(ctx, m, src, B, cap, slot_row, slot_w, row_slots, st))) return rc;
+        a.slot_row = slot_row;
+        a.slot_w = slot_w;
+        a.counters = m->counters_d;
+        a.B = cap;
+        a.scatter = blend ? 0 : 1;
+        if (blend) a.out = slot_out;
+    } else {
+        a.fixed_sub = (d.kind == 1) ? (use_coarse ? 0 : 1) : 0;
+        a.scatter = 1;
+    }
+
+    const int64_t n_tiles = cap / MN_TILE;
+    mn_prof_begin(ctx, st);
+    if (precision == MN_PREC_FP32)
+        rc = mn_mlp_simt_launch(ctx, a, n_tiles, st);
+    else
+        rc = mn_mlp_tc_launch(ctx, m, a, n_tiles, precision, ws, workspace_bytes - (size_t)(ws - (char*)workspace_d), st);
+    mn_prof_end(ctx, st);
+    if (rc) return rc;
+    if (row_slots) return mn_route_combine(ctx, m, B, row_slots, slot_out, a.out_cols, out_d, st);
+    return MN_OK;
+}
+
+int mn_model_last_stats(mn_ctx* ctx, mn_model* m, int64_t* slots, int64_t* tiles, void* stream) {
+    if (!ctx || !m) return MN_ERR_INVALID;
+    int h[2] = {0, 0};
+    MN_CUDA(ctx, cudaMemcpyAsync(h, m->counters_d + CNT_NSLOTS, 2 * sizeof(int), cudaMemcpyDeviceToHost,
+                                 (cudaStream_t)stream));
+    MN_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    if (slots) *slots = h[1];
+    if (tiles) *tiles = h[0] / MN_TILE;
+    return MN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// Shared host/device definitions for libmn_b200.so.  The whole library is compiled with
+// -fmad=false: every multiply-add that the fp32 oracle performs as two separately rounded torch ops
+// stays two roundings here; fused multiply-adds appear only where written explicitly as fmaf().
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/mn_b200.h"
+
+// device status bits (mn_ctx::status_d)
+#define MN_STATUS_SPHERE 1u
+#define MN_STATUS_OVERFLOW 2u
+
+#include <vector>
+
+struct mn_ctx {
+    int device = 0;
+    int sm_count = 148;
+    std::string err;
+    unsigned int* status_d = nullptr;
+    long long launches = 0;             // kernels launched through this context (bench: gpu_launches)
+    // optional CUDA-event timing of the MLP kernel launches (bench: roofline.achieved)
+    int prof_on = 0;
+    std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
+    size_t prof_used = 0;
+};
+
+static inline void mn_prof_begin(mn_ctx* ctx, cudaStream_t st) {
+    if (!ctx->prof_on) return;
+    if (ctx->prof_used + 2 > ctx->prof_ev.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        ctx->prof_ev.push_back(a);
+        ctx->prof_ev.push_back(b);
+    }
+    cudaEventRecord(ctx->prof_ev[ctx->prof_used], st);
+}
+static inline void mn_prof_end(mn_ctx* ctx, cudaStream_t st) {
+    if (!ctx->prof_on) return;
+    cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], st);
+    ctx->prof_used += 2;
+}
+
+static inline int mn_fail(mn_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define MN_CUDA(ctx, expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            return mn_fail(ctx, MN_ERR_CUDA,                                                        \
+                           std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ +   \
+                               ":" + std::to_string(__LINE__) + ")");                               \
+        }                                                                                           \
+    } while (0)
+
+#define MN_LAUNCH_CHECK(ctx)               \
+    do {                                   \
+        (ctx)->launches++;                 \
+        MN_CUDA(ctx, cudaGetLastError());  \
+    } while (0)
+
+static inline int64_t mn_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t mn_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// Where per-row network inputs come from (device-side view of mn_rows).
+// ------------------------------------------------------------------------------------------------
+struct RowSrc {
+    const float* x;      // mode 0: [B, cols];  mode 1: xyz [B, cols]
+    int cols;            // row stride of x
+    int net_off;         // first network column inside x (3 when a real-xyz routing prefix is present)
+    const float* dirs;   // per-ray (mode 1) or inside x (mode 0)
+    int64_t dir_stride;
+    const float* idx;
+    int64_t idx_stride;
+    int div;             // row -> ray divisor (1 in mode 0)
+    int dir_quirk;       // models/nerf.py:146 x[:, -4:-1] with no index column: dir := (xyz_z, d_x, d_y)
+    int xyz_dim;
+
+    __device__ __forceinline__ float xyz(int64_t row, int j) const { return x[row * cols + net_off + j]; }
+    __device__ __forceinline__ float route_xyz(int64_t row, int j) const { return x[row * cols + j]; }
+    __device__ __forceinline__ float dir(int64_t row, int j) const {
+        if (dir_quirk) {
+            // columns [-4:-1] of [xyz(3), dir(3)] are (z, d_x, d_y)
+            if (j == 0) return x[row * cols + net_off + 2];
+            return dirs[(row / div) * dir_stride + (j - 1)];
+        }
+        return dirs[(row / div) * dir_stride + j];
+    }
+    __device__ __forceinline__ float index(int64_t row) const { return idx[(row / div) * idx_stride]; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mn_pow2f(int k) { return __int_as_float((127 + k) << 23); }
+
+// sin / cos of (2^k * x) exactly as the oracle evaluates them: the product is exact (power of two),
+// then a full-range accurate sincos (no fast-math intrinsics).
+__device__ __forceinline__ void mn_pe_sincos(float x, int k, float* s, float* c) {
+    sincosf(x * mn_pow2f(k), s, c);
+}
+
+__device__ __forceinline__ float mn_softplus_shifted(float x) {
+    // F.softplus(x - 1, beta=1, threshold=20)   (models/nerf.py:38-39)
+    float y = x - 1.0f;
+    return y > 20.0f ? y : log1pf(expf(y));
+}
+
+__device__ __forceinline__ float mn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ double mn_shfl_up_d(double v, int delta) {
+    return __shfl_up_sync(0xffffffffu, v, delta);
+}

@@ -1,0 +1,72 @@
+// Internal model representation shared by the packer, the router and the MLP kernels.
+#pragma once
+#include "mn_common.cuh"
+
+#define MN_MAX_LAYERS 16
+#define MN_MAX_SUB 64
+#define MN_TILE 128   // slot-space bucket alignment == rows of one tensor-core MLP tile
+
+// Offsets (in floats) of each packed tensor inside one sub-module's fp32 buffer.  All matrices are
+// stored K-major ("transposed": Wt[k][n] = W[n][k]) so that consecutive output channels are contiguous.
+struct PackedLayout {
+    int w[MN_MAX_LAYERS], b[MN_MAX_LAYERS], kin[MN_MAX_LAYERS];
+    int sigma_w, sigma_b, final_w, final_b, dira_w, dira_b, rgb_w, rgb_b, emb, aff_w, aff_b;
+    int total;
+};
+
+struct NetDims {
+    int layers, L, in_xyz, in_dir, app, aux, rgb_dim, rgb_in, xyz_dim, nf_xyz, nf_dir, has_dir_a, affine,
+        softplus, skip_mask, app_count, app_in_dira;
+};
+
+struct mn_model {
+    mn_ctx* ctx = nullptr;
+    mn_model_desc d{};
+    NetDims nd{};
+    PackedLayout lay{};
+    float* packed = nullptr;          // [n_sub * lay.total] fp32
+    float* centroids_d = nullptr;     // [n_sub, 3]
+    int* counters_d = nullptr;        // routing scratch: see mn_route.cu
+    int max_multiplicity = 0;         // slot capacity per row for blended routing
+    // tensor-core packed weights (fp16 hi / lo images), see mn_mlp_tc.cu
+    void* tc_packed = nullptr;
+    size_t tc_sub_bytes = 0;
+    int tc_ready = 0;
+};
+
+// counters_d layout (ints)
+#define CNT_COUNT 0                        // [MN_MAX_SUB]   rows routed to each sub-module
+#define CNT_START (MN_MAX_SUB)             // [MN_MAX_SUB+1] tile-aligned slot offsets
+#define CNT_CURSOR (2 * MN_MAX_SUB + 1)    // [MN_MAX_SUB]
+#define CNT_NSLOTS (3 * MN_MAX_SUB + 1)    // [1] padded slot count (end of last bucket)
+#define CNT_NPAIRS (3 * MN_MAX_SUB + 2)    // [1] routed (row, sub) pairs
+#define CNT_TOTAL (3 * MN_MAX_SUB + 4)
+
+// Arguments common to both MLP kernels.
+struct MlpArgs {
+    NetDims nd;
+    PackedLayout lay;
+    const float* packed;      // fp32 packed weights, sub s at packed + s * lay.total
+    RowSrc src;
+    const int* slot_row;      // slot -> row, -1 = padding; NULL = identity
+    const float* slot_w;      // slot -> blend weight; NULL = 1
+    const int* counters;      // routing counters (bucket starts, n_slots) or NULL
+    int n_sub;
+    int fixed_sub;            // used when counters == NULL
+    int64_t B;                // rows (identity mode) / slot capacity (routed mode)
+    int sigma_only;
+    const float* sigma_noise; // [rows] or NULL
+    float* out;               // [*, out_cols]
+    int out_cols;
+    int scatter;              // 1: out index = row, 0: out index = slot
+};
+
+int mn_route_build(mn_ctx* ctx, mn_model* m, const RowSrc& src, int64_t B, int64_t cap, int* slot_row, float* slot_w,
+                   int* row_slots, cudaStream_t st);
+int mn_route_combine(mn_ctx* ctx, mn_model* m, int64_t B, const int* row_slots, const float* slot_out, int out_cols,
+                     float* out, cudaStream_t st);
+int mn_mlp_simt_launch(mn_ctx* ctx, const MlpArgs& a, int64_t n_tiles128, cudaStream_t st);
+int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles128, int precision, void* ws,
+                     size_t ws_bytes, cudaStream_t st);
+size_t mn_mlp_tc_workspace(const mn_model* m, int64_t n_tiles128, int precision);
+int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st);

@@ -1,0 +1,216 @@
+// Spatial routing of sample rows to sub-modules (models/mega_nerf.py:21-49), bucketed into
+// MN_TILE-aligned slot ranges so that every MLP tile belongs to exactly one sub-module, plus the
+// ascending-sub-module blend that replaces `results[mask] += sub_result * weights`.
+//
+// Distances restate torch.cdist's matmul path bit for bit:
+//   x_ = [-2x, |x|^2, 1],  c_ = [c, 1, |c|^2],  d^2 = FMA chain over k ascending from an accumulator
+//   of 0, clamp_min(0), sqrt.  Batches with <= 25 rows AND <= 25 centroids take cdist's direct path
+//   sqrt(fma-accumulated sum (x-c)^2) instead, as torch does.
+#include "mn_model.cuh"
+
+namespace {
+
+__device__ __forceinline__ void distances(const RowSrc& src, int64_t row, const float* __restrict__ cent, int K,
+                                          int s, bool direct, float* d) {
+    float x[3];
+    for (int j = s; j < 3; ++j) x[j] = src.route_xyz(row, j);
+    if (direct) {
+        for (int k = 0; k < K; ++k) {
+            float acc = 0.0f;
+            for (int j = s; j < 3; ++j) {
+                const float t = x[j] - cent[k * 3 + j];
+                acc = fmaf(t, t, acc);  // torch's direct cdist kernel contracts this (probe: 100% bitwise)
+            }
+            d[k] = sqrtf(acc);
+        }
+        return;
+    }
+    float xn = x[s] * x[s];
+    for (int j = s + 1; j < 3; ++j) xn = xn + x[j] * x[j];
+    for (int k = 0; k < K; ++k) {
+        float cn = cent[k * 3 + s] * cent[k * 3 + s];
+        for (int j = s + 1; j < 3; ++j) cn = cn + cent[k * 3 + j] * cent[k * 3 + j];
+        float acc = 0.0f;
+        for (int j = s; j < 3; ++j) acc = fmaf(-2.0f * x[j], cent[k * 3 + j], acc);
+        acc = fmaf(xn, 1.0f, acc);
+        acc = fmaf(1.0f, cn, acc);
+        d[k] = sqrtf(fmaxf(acc, 0.0f));
+    }
+}
+
+// -> number of active sub-modules; mask bits; for margin > 1 the normalised weights in w[]
+__device__ __forceinline__ uint64_t route_row(const float* d, int K, float margin, float* w) {
+    float dmin = d[0];
+    int amin = 0;
+    for (int k = 1; k < K; ++k)
+        if (d[k] < dmin) { dmin = d[k]; amin = k; }
+    if (!(margin > 1.0f)) return 1ull << amin;
+    uint64_t mask = 0;
+    float sum = 0.0f;
+    const float thr = margin * dmin;
+    for (int k = 0; k < K; ++k) {
+        float inv = 1.0f / (d[k] + 1e-8f);
+        if (d[k] > thr) inv = 0.0f;
+        w[k] = inv;
+        sum = sum + inv;
+    }
+    for (int k = 0; k < K; ++k) {
+        w[k] = w[k] / sum;
+        if (w[k] > 0.0f) mask |= 1ull << k;
+    }
+    return mask;
+}
+
+__global__ void route_count_kernel(RowSrc src, int64_t B, const float* __restrict__ cent, int K, int s, float margin,
+                                   int direct, int* counters) {
+    __shared__ int hist[MN_MAX_SUB];
+    __shared__ float sc[MN_MAX_SUB * 3];
+    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) sc[i] = cent[i];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t mask = 0;
+    if (row < B) {
+        float d[MN_MAX_SUB], w[MN_MAX_SUB];
+        distances(src, row, sc, K, s, direct, d);
+        mask = route_row(d, K, margin, w);
+    }
+    for (int k = 0; k < K; ++k) {
+        const unsigned b = __ballot_sync(0xffffffffu, (mask >> k) & 1);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(&hist[k], __popc(b));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x)
+        if (hist[i]) atomicAdd(&counters[CNT_COUNT + i], hist[i]);
+}
+
+__global__ void route_scan_kernel(int* counters, int K) {
+    if (threadIdx.x == 0) {
+        int off = 0, pairs = 0;
+        for (int k = 0; k < K; ++k) {
+            counters[CNT_START + k] = off;
+            const int c = counters[CNT_COUNT + k];
+            pairs += c;
+            off += (c + MN_TILE - 1) / MN_TILE * MN_TILE;
+            counters[CNT_CURSOR + k] = 0;
+        }
+        counters[CNT_START + K] = off;
+        counters[CNT_NSLOTS] = off;
+        counters[CNT_NPAIRS] = pairs;
+    }
+}
+
+__global__ void route_scatter_kernel(RowSrc src, int64_t B, const float* __restrict__ cent, int K, int s, float margin,
+                                     int direct, int* counters, int64_t cap, int* slot_row, float* slot_w,
+                                     int* row_slots, unsigned int* status) {
+    __shared__ float sc[MN_MAX_SUB * 3];
+    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) sc[i] = cent[i];
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint64_t mask = 0;
+    float w[MN_MAX_SUB];
+    if (row < B) {
+        float d[MN_MAX_SUB];
+        distances(src, row, sc, K, s, direct, d);
+        mask = route_row(d, K, margin, w);
+    }
+    for (int k = 0; k < K; ++k) {
+        const bool on = (mask >> k) & 1;
+        const unsigned b = __ballot_sync(0xffffffffu, on);
+        if (!b) {
+            if (row < B && row_slots) row_slots[row * K + k] = -1;
+            continue;
+        }
+        int base = 0;
+        const int leader = __ffs(b) - 1;
+        if (lane == leader) base = atomicAdd(&counters[CNT_CURSOR + k], __popc(b));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        int slot = -1;
+        if (on) {
+            slot = counters[CNT_START + k] + base + __popc(b & ((1u << lane) - 1));
+            if (slot >= cap) {
+                atomicOr(status, MN_STATUS_OVERFLOW);
+                slot = -1;
+            } else {
+                slot_row[slot] = (int)row;
+                if (slot_w) slot_w[slot] = w[k];
+            }
+        }
+        if (row < B && row_slots) row_slots[row * K + k] = slot;
+    }
+}
+
+__global__ void combine_kernel(int64_t B, int K, const int* __restrict__ row_slots, const float* __restrict__ slot_out,
+                               int out_cols, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * out_cols) return;
+    const int64_t row = i / out_cols;
+    const int c = (int)(i % out_cols);
+    float acc = 0.0f;
+    for (int k = 0; k < K; ++k) {  // ascending sub-module order (mega_nerf.py:34,49)
+        const int slot = row_slots[row * K + k];
+        if (slot >= 0) acc = acc + slot_out[(int64_t)slot * out_cols + c];
+    }
+    out[i] = acc;
+}
+
+__global__ void route_only_kernel(RowSrc src, int64_t B, const float* __restrict__ cent, int K, int s, float margin,
+                                  int direct, int* assign, float* weights) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= B) return;
+    float d[MN_MAX_SUB], w[MN_MAX_SUB];
+    distances(src, row, cent, K, s, direct, d);
+    const uint64_t mask = route_row(d, K, margin, w);
+    if (margin > 1.0f) {
+        for (int k = 0; k < K; ++k) weights[row * K + k] = w[k];
+    } else {
+        assign[row] = __ffsll((long long)mask) - 1;
+    }
+}
+
+}  // namespace
+
+int mn_route_build(mn_ctx* ctx, mn_model* m, const RowSrc& src, int64_t B, int64_t cap, int* slot_row, float* slot_w,
+                   int* row_slots, cudaStream_t st) {
+    const int K = m->d.n_sub;
+    const int direct = (B <= 25 && K <= 25) ? 1 : 0;
+    MN_CUDA(ctx, cudaMemsetAsync(m->counters_d, 0, CNT_TOTAL * sizeof(int), st));
+    MN_CUDA(ctx, cudaMemsetAsync(slot_row, 0xFF, (size_t)cap * sizeof(int), st));
+    const unsigned blocks = (unsigned)mn_cdiv(B, 256);
+    route_count_kernel<<<blocks, 256, 0, st>>>(src, B, m->centroids_d, K, m->d.cluster_dim_start, m->d.boundary_margin,
+                                               direct, m->counters_d);
+    MN_LAUNCH_CHECK(ctx);
+    route_scan_kernel<<<1, 32, 0, st>>>(m->counters_d, K);
+    MN_LAUNCH_CHECK(ctx);
+    route_scatter_kernel<<<blocks, 256, 0, st>>>(src, B, m->centroids_d, K, m->d.cluster_dim_start,
+                                                 m->d.boundary_margin, direct, m->counters_d, cap, slot_row, slot_w,
+                                                 row_slots, ctx->status_d);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}
+
+int mn_route_combine(mn_ctx* ctx, mn_model* m, int64_t B, const int* row_slots, const float* slot_out, int out_cols,
+                     float* out, cudaStream_t st) {
+    const int64_t n = B * out_cols;
+    combine_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(B, m->d.n_sub, row_slots, slot_out, out_cols, out);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}
+
+extern "C" int mn_model_route(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int32_t* assign_out_d,
+                              float* weights_out_d, void* stream) {
+    if (!ctx || !m || !rows) return MN_ERR_INVALID;
+    if (m->d.kind != 2) return mn_fail(ctx, MN_ERR_INVALID, "mn_model_route: not a MegaNeRF model");
+    RowSrc src{};
+    src.x = rows->x_d;
+    src.cols = rows->cols;
+    src.div = 1;
+    const int K = m->d.n_sub;
+    const int direct = (B <= 25 && K <= 25) ? 1 : 0;
+    if (B == 0) return MN_OK;
+    route_only_kernel<<<(unsigned)mn_cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(
+        src, B, m->centroids_d, K, m->d.cluster_dim_start, m->d.boundary_margin, direct, assign_out_d, weights_out_d);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}

@@ -1,0 +1,299 @@
+"""render_rays() with the reference's signature and result dictionary (mega_nerf/rendering.py:15-173),
+orchestrating the sm_100a kernels of libmn_b200.so.  Host syncs happen only where the reference has
+them too (sphere check :412, background ray selection :37).
+
+Forward only in this round; results carry no autograd graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from argparse import Namespace
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _cabi as K
+from .modules import NeRF, MegaNeRF, Cascade
+
+TO_COMPOSITE = ('rgb', 'depth')
+
+
+def _unwrap(m: Optional[nn.Module]):
+    if m is None:
+        return None
+    return m.module if hasattr(m, 'module') and not isinstance(m, (NeRF, MegaNeRF, Cascade)) else m
+
+
+class _Stage:
+    """Thin typed wrappers over the stage entry points, bound to one device/stream."""
+
+    def __init__(self, device: torch.device):
+        self.dev = device
+        self.L = K.lib()
+        self.h = K.ctx(device)
+
+    @property
+    def st(self):
+        return K.stream_of(self.dev)
+
+    def new(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, device=self.dev, dtype=dtype)
+
+    def sample_coarse(self, rays, far, steps, rand, perturb, N, S):
+        z, xyz = self.new(N, S), self.new(N, S, 3)
+        K.check(self.L.mn_sample_coarse(self.h, K.ptr(rays), K.ptr(far), K.ptr(steps), K.ptr(rand), float(perturb), N, S,
+                                        K.ptr(z), K.ptr(xyz), self.st), self.h)
+        return z, xyz
+
+    def stratify(self, z1d, rand, perturb, N, S):
+        out = self.new(N, S)
+        K.check(self.L.mn_stratify(self.h, K.ptr(z1d), 0, K.ptr(rand), float(perturb), N, S, K.ptr(out), self.st), self.h)
+        return out
+
+    def points_from_z(self, rays, z):
+        N, S = z.shape
+        xyz = self.new(N, S, 3)
+        K.check(self.L.mn_points_from_z(self.h, K.ptr(rays), K.ptr(z), N, S, K.ptr(xyz), self.st), self.h)
+        return xyz
+
+    def sample_pdf(self, z_coarse, weights, u, F):
+        N, S = z_coarse.shape
+        out = self.new(N, F)
+        ustride = 0 if u.dim() == 1 else F
+        K.check(self.L.mn_sample_pdf(self.h, K.ptr(z_coarse), K.ptr(weights), weights.shape[1], None, K.ptr(u), ustride,
+                                     N, S, F, K.ptr(out), None, None, self.st), self.h)
+        return out
+
+    def sort_cat(self, a, b, descending=False):
+        N = a.shape[0]
+        out = self.new(N, a.shape[1] + b.shape[1])
+        K.check(self.L.mn_sort_cat(self.h, K.ptr(a), a.shape[1], K.ptr(b), b.shape[1], N, int(descending), K.ptr(out),
+                                   self.st), self.h)
+        return out
+
+    def composite(self, raw, z, dreal, raw2, z2, dreal2, last_delta, flip, want_w, want_rgb, want_depth, want_var,
+                  want_lambda):
+        N, S = z.shape
+        S2 = 0 if z2 is None else z2.shape[1]
+        w = self.new(N, S + S2) if want_w else None
+        rgb = self.new(N, 3) if want_rgb else None
+        depth = self.new(N) if want_depth else None
+        var = self.new(N) if want_var else None
+        lam = self.new(N) if want_lambda else None
+        K.check(self.L.mn_composite(self.h, K.ptr(raw), K.ptr(z), K.ptr(dreal), S, K.ptr(raw2), K.ptr(z2), K.ptr(dreal2), S2,
+                                    K.ptr(last_delta), N, int(flip), K.ptr(w), K.ptr(rgb), K.ptr(depth), K.ptr(var),
+                                    K.ptr(lam), self.st), self.h)
+        return w, rgb, depth, var, lam
+
+    def intersect_sphere(self, rays, center, radius):
+        N = rays.shape[0]
+        out = self.new(N)
+        K.check(self.L.mn_intersect_sphere(self.h, K.ptr(rays), K.ptr(center), K.ptr(radius), N, K.ptr(out), self.st), self.h)
+        # the reference raises from a host-side `.any()` here (rendering.py:412-414)
+        K.check(self.L.mn_check_status(self.h, self.st), self.h)
+        return out
+
+    def points_outside(self, rays, ids, depth, center, radius, real, c2d):
+        n, S = depth.shape
+        pts = self.new(n, S, 7 if real else 4)
+        dreal = self.new(n, S)
+        K.check(self.L.mn_points_outside(self.h, K.ptr(rays), K.ptr(ids), K.ptr(depth), K.ptr(center), K.ptr(radius), n, S,
+                                         int(real), int(c2d), K.ptr(pts), K.ptr(dreal), self.st), self.h)
+        return pts, dreal
+
+    def sh_to_rgb(self, deg, coef, dirs, S):
+        B = coef.shape[0]
+        out = self.new(B, 4)
+        K.check(self.L.mn_sh_to_rgb(self.h, deg, K.ptr(coef), coef.shape[1], K.ptr(dirs), dirs.stride(0), S, B, 1,
+                                    K.ptr(out), self.st), self.h)
+        return out
+
+
+def _query(sg: _Stage, net: nn.Module, hparams: Namespace, typ: str, xyz: torch.Tensor, dirs: torch.Tensor,
+           idx: Optional[torch.Tensor]) -> torch.Tensor:
+    """Model query for [n,S,C] points -> raw [n,S,4] = (rgb, sigma).  rendering.py:275-334."""
+    n, S, Cc = xyz.shape
+    B = n * S
+    native = net._native()
+    first = native.subs[0]
+    rows = K.Rows()
+    rows.mode = 1
+    rows.x_d = xyz.data_ptr()
+    rows.cols = Cc
+    rows.samples_per_ray = S
+    use_dirs = hparams.pos_dir_dim != 0
+    if use_dirs:
+        rows.dirs_d = dirs.data_ptr()
+        rows.dir_stride = dirs.stride(0)
+    if idx is not None:
+        rows.idx_d = idx.data_ptr()
+    noise = None
+    if net.training:
+        # same draw order / shapes as the reference's per-chunk torch.rand (rendering.py:294,321)
+        ch = hparams.model_chunk_size
+        noise = torch.cat([torch.rand(min(ch, B - a), 1, device=xyz.device) for a in range(0, B, ch)], 0)
+    out = native.forward(rows, B, xyz.device, typ == 'coarse', False, noise, first.rgb_dim + 1)
+    if hparams.pos_dir_dim == 0 and hparams.sh_deg is not None:
+        out = sg.sh_to_rgb(hparams.sh_deg, out, dirs, S)
+    return out.view(n, S, 4)
+
+
+def _two_pass(sg: _Stage, net: nn.Module, hparams: Namespace, dirs: torch.Tensor, idx: Optional[torch.Tensor],
+              xyz_coarse: torch.Tensor, z: torch.Tensor, last_delta: torch.Tensor, get_depth: bool,
+              get_depth_variance: bool, get_bg_lambda: bool, flip: bool, depth_real: Optional[torch.Tensor],
+              xyz_fine_fn: Callable) -> Dict[str, torch.Tensor]:
+    """coarse -> resample -> fine  (rendering.py:176-248 with _inference :251-393 inlined)."""
+    res: Dict[str, torch.Tensor] = {}
+    fine = hparams.fine_samples > 0
+    cascade = hparams.use_cascade
+    training = net.training
+
+    # ---- coarse pass
+    xyz_c, z_c = xyz_coarse, z
+    if flip:
+        xyz_c = torch.flip(xyz_coarse, dims=[-2]).contiguous()
+        z_c = torch.flip(z, dims=[-1]).contiguous()
+    raw_c = _query(sg, net, hparams, 'coarse', xyz_c, dirs, idx)
+    w, rgb, depth, var, lam = sg.composite(raw_c, z_c, depth_real, None, None, None, last_delta, flip,
+                                           want_w=fine, want_rgb=cascade,
+                                           want_depth=(not fine) and (get_depth or get_depth_variance),
+                                           want_var=(not fine) and get_depth_variance,
+                                           want_lambda=get_bg_lambda and cascade)
+    if lam is not None:
+        res['bg_lambda_coarse'] = lam
+    if rgb is not None:
+        res['rgb_coarse'] = rgb
+    if (not fine) and get_depth:
+        res['depth_coarse'] = depth
+    if var is not None:
+        res['depth_variance_coarse'] = var
+    if not fine:
+        return res
+
+    # ---- resample (bins from the unflipped depths, weights as computed: quirk Q7)
+    perturb = hparams.perturb if training else 0
+    F = hparams.fine_samples // 2 if flip else hparams.fine_samples
+    n = z.shape[0]
+    if perturb == 0:
+        u = torch.linspace(0, 1, F, device=z.device)
+    else:
+        u = torch.rand(n, F, device=z.device)
+    z_f = sg.sample_pdf(z, w, u, F)
+    if cascade:
+        z_f = sg.sort_cat(z, z_f)
+    xyz_f, dreal_f = xyz_fine_fn(z_f)
+
+    # ---- fine pass
+    if cascade:
+        if flip:
+            xyz_f = torch.flip(xyz_f, dims=[-2]).contiguous()
+            z_f = torch.flip(z_f, dims=[-1]).contiguous()
+        raw_f = _query(sg, net, hparams, 'fine', xyz_f, dirs, idx)
+        _, rgb, depth, var, lam = sg.composite(raw_f, z_f, dreal_f, None, None, None, last_delta, flip, False, True,
+                                               get_depth or get_depth_variance, get_depth_variance, get_bg_lambda)
+    else:
+        raw_f = _query(sg, net, hparams, 'fine', xyz_f, dirs, idx)
+        _, rgb, depth, var, lam = sg.composite(raw_f, z_f, dreal_f, raw_c, z_c, depth_real if dreal_f is not None else None,
+                                               last_delta, flip, False, True, get_depth or get_depth_variance,
+                                               get_depth_variance, get_bg_lambda)
+    res['rgb_fine'] = rgb
+    if lam is not None:
+        res['bg_lambda_fine'] = lam
+    if get_depth:
+        res['depth_fine'] = depth
+    if var is not None:
+        res['depth_variance_fine'] = var
+    return res
+
+
+def render_rays(nerf: nn.Module,
+                bg_nerf: Optional[nn.Module],
+                rays: torch.Tensor,
+                image_indices: Optional[torch.Tensor],
+                hparams: Namespace,
+                sphere_center: Optional[torch.Tensor],
+                sphere_radius: Optional[torch.Tensor],
+                get_depth: bool,
+                get_depth_variance: bool,
+                get_bg_fg_rgb: bool) -> Tuple[Dict[str, torch.Tensor], bool]:
+    net = _unwrap(nerf)
+    bg = _unwrap(bg_nerf)
+    if not isinstance(net, (NeRF, MegaNeRF, Cascade)) or (bg is not None and not isinstance(bg, (NeRF, MegaNeRF, Cascade))):
+        raise TypeError('mega_nerf_b200.render_rays needs mega_nerf_b200 modules (use get_nerf / install())')
+    with torch.no_grad():
+        return _render(net, bg, rays, image_indices, hparams, sphere_center, sphere_radius, get_depth,
+                       get_depth_variance, get_bg_fg_rgb)
+
+
+def _render(net, bg, rays, image_indices, hparams, sphere_center, sphere_radius, get_depth, get_depth_variance,
+            get_bg_fg_rgb):
+    dev = rays.device
+    sg = _Stage(dev)
+    rays = K.f32c(rays)
+    N = rays.shape[0]
+    idx = None
+    if image_indices is not None:
+        idx = K.f32c(image_indices.to(dev)).view(-1)        # int32 in training, float in eval (runner.py:246,554)
+    dirs = rays[:, 3:6]                                      # strided view, [N,3] with row stride 8
+    perturb = hparams.perturb if net.training else 0
+    S = hparams.coarse_samples
+    last_delta = torch.full((N,), 1e10, device=dev, dtype=torch.float32)
+    far_override = None
+    with_bg = None
+    bg_res = None
+    center = K.f32c(sphere_center.to(dev)) if sphere_center is not None else None
+    radius = K.f32c(sphere_radius.to(dev)) if sphere_radius is not None else None
+
+    if bg is not None:
+        fg_far = sg.intersect_sphere(rays, center, radius)
+        fg_far = torch.maximum(fg_far, rays[:, 6])
+        with_bg = torch.arange(N, device=dev)[rays[:, 7] > fg_far]          # host sync, as in the reference (:37)
+        nb = with_bg.shape[0]
+        if nb > 0:
+            last_delta[with_bg] = fg_far[with_bg]
+            far_override = torch.minimum(rays[:, 7], fg_far)
+            half = S // 2
+            bz1 = torch.linspace(0, 1, half, device=dev)
+            rnd = torch.rand(nb, half, device=dev) if perturb > 0 else None
+            bz = sg.stratify(bz1, rnd, perturb, nb, half)
+            real = hparams.container_path is not None or hparams.train_mega_nerf is not None
+            c2d = real and net.cluster_dim_start == 1
+            mk = lambda zz: sg.points_outside(rays, with_bg, zz, center, radius, real, c2d)
+            bpts, breal = mk(bz)
+            bg_dirs = rays[with_bg][:, 3:6]
+            bg_idx = idx[with_bg].contiguous() if idx is not None else None
+            bg_res = _two_pass(sg, bg, hparams, bg_dirs, bg_idx, bpts, bz,
+                               torch.full((nb,), 1e10, device=dev, dtype=torch.float32), get_depth,
+                               get_depth_variance, False, True, breal, mk)
+
+    steps = torch.linspace(0, 1, S, device=dev)
+    rnd = torch.rand(N, S, device=dev) if perturb > 0 else None
+    z, xyz = sg.sample_coarse(rays, far_override, steps, rnd, perturb, N, S)
+    res = _two_pass(sg, net, hparams, dirs, idx, xyz, z, last_delta, get_depth, get_depth_variance, bg is not None,
+                    False, None, lambda zz: (sg.points_from_z(rays, zz), None))
+
+    if bg is not None:
+        types = ['fine' if hparams.fine_samples > 0 else 'coarse']
+        if hparams.use_cascade and hparams.fine_samples > 0:
+            types.append('coarse')
+        for typ in types:
+            for key in TO_COMPOSITE:
+                name = f'{key}_{typ}'
+                if name not in res:
+                    continue
+                val = res[name]
+                if with_bg.shape[0] > 0:
+                    lam = res[f'bg_lambda_{typ}'][with_bg]
+                    add = torch.zeros_like(val)
+                    add[with_bg] = bg_res[name] * (lam.unsqueeze(-1) if val.dim() > 1 else lam)
+                    if get_bg_fg_rgb:
+                        res[f'fg_{name}'] = val
+                        res[f'bg_{name}'] = add
+                    res[name] = val + add
+                elif get_bg_fg_rgb:
+                    res[f'fg_{name}'] = val
+                    res[f'bg_{name}'] = torch.zeros_like(val)
+    present = bool(bg is not None and with_bg.shape[0] > 0)
+    return res, present
