@@ -1,8 +1,681 @@
-// tcgen05 / TMEM MLP path (placeholder until the kernel lands).
+// MN_PREC_TC_F16 / MN_PREC_TC_F16X3: the NeRF MLP (models/nerf.py:115-160) on the 5th-gen tensor cores.
+//
+//   tc_encode_kernel   sample rows -> fp16 feature tiles (positional encodings of xyz / dir, appearance
+//                      embedding) written in the exact shared-memory operand image, one 128-row tile
+//                      per CTA, coalesced 16-byte stores.
+//   tc_mlp_kernel      persistent, warp-specialised: warp 0 = TMA producer (cp.async.bulk of weight
+//                      K-slabs through an mbarrier ring and of the feature tiles), warp 1 = single-thread
+//                      tcgen05.mma issuer (accumulators in TMEM), warps 2-5 = epilogue (tcgen05.ld ->
+//                      bias/ReLU -> fp16 -> next layer's A operand in shared memory; heads -> HBM).
+//                      Activations never leave the SM between layers.
+//
+// Operand layout (both A tiles and packed weights): K-major, no swizzle, "interleaved" core matrices:
+//   element (row r, col k) of an R-row operand lives at byte (k/8)*(R*16) + r*16 + (k%8)*2,
+// i.e. [K/8][R][8] fp16.  UMMA descriptor: LBO = R*16 (next 8-column chunk), SBO = 128 (next 8-row group).
+// The epilogue's per-row 16-byte stores and the packer's images are contiguous in this layout, any K that
+// is a multiple of 16 works, and no TMA tensor map is needed (plain 1-D bulk copies).
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
 #include "mn_model.cuh"
 
-size_t mn_mlp_tc_workspace(const mn_model*, int64_t, int) { return 0; }
-int mn_mlp_tc_pack(mn_ctx*, mn_model*, int, cudaStream_t) { return MN_OK; }
-int mn_mlp_tc_launch(mn_ctx* ctx, mn_model*, const MlpArgs&, int64_t, int, void*, size_t, cudaStream_t) {
-    return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core MLP path not built yet");
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kStageBytes = 32 * 1024;  // one weight ring stage: up to 64 K-columns x 256 rows x 2 B
+constexpr int kStages = 3;
+constexpr int kSlabCols = 64;
+constexpr int kMaxGemm = 16;
+constexpr int kThreads = 192;
+
+enum { SRC_H = 0, SRC_XPE = 1, SRC_XAUX = 2 };
+enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
+
+struct TcGemm {
+    int n;           // MMA N
+    int nseg;
+    int src[2];
+    int k[2];        // padded K columns per segment (multiple of 16)
+    int w_off;       // byte offset of the weight image inside one precision plane of a sub-module
+    int bias_off;    // float offset inside the sub-module's fp32 block
+    int epi;
+};
+
+struct TcPlan {
+    int n_gemm, n_trunk;
+    TcGemm g[kMaxGemm];
+    int kpe, kaux;         // padded feature-tile widths
+    int plane_bytes;       // bytes of all weight images of one sub-module (one precision plane)
+    int f32_floats;        // fp32 block: biases per GEMM (256 each) + sigma_w[L] + sigma_b
+    int sigma_w_off;       // float offset of sigma_w in the fp32 block
+    int sub_bytes;         // total bytes per sub-module: planes (hi[,lo]) + fp32 block
+    int x_tile_bytes;      // bytes of one feature tile image (one plane)
+    int L;
+};
+
+int pad16(int x) { return (x + 15) / 16 * 16; }
+
+bool build_plan(const NetDims& nd, TcPlan* p) {
+    if (nd.L % 32 != 0 || nd.L > 256 || nd.L < 32 || nd.rgb_dim > 32 || nd.affine || nd.layers > 12) return false;
+    TcPlan& P = *p;
+    P = TcPlan{};
+    P.L = nd.L;
+    P.kpe = pad16(nd.in_xyz);
+    P.kaux = nd.aux > 0 ? pad16(nd.aux) : 0;
+    int woff = 0, ng = 0;
+    auto add = [&](int n, int s0, int k0, int s1, int k1, int epi) {
+        TcGemm& g = P.g[ng];
+        g.n = n;
+        g.nseg = k1 > 0 ? 2 : 1;
+        g.src[0] = s0; g.k[0] = k0; g.src[1] = s1; g.k[1] = k1;
+        g.w_off = woff;
+        g.bias_off = ng * 256;
+        g.epi = epi;
+        woff += (k0 + k1) * n * 2;
+        ++ng;
+    };
+    for (int i = 0; i < nd.layers; ++i) {
+        const int epi = (i == nd.layers - 1) ? EPI_RELU_SIGMA : EPI_RELU;
+        if (i == 0) add(nd.L, SRC_XPE, P.kpe, 0, 0, epi);
+        else if ((nd.skip_mask >> i) & 1) add(nd.L, SRC_XPE, P.kpe, SRC_H, nd.L, epi);
+        else add(nd.L, SRC_H, nd.L, 0, 0, epi);
+    }
+    P.n_trunk = ng;
+    if (nd.has_dir_a) {
+        add(nd.L, SRC_H, nd.L, 0, 0, EPI_LINEAR);
+        add(nd.L / 2, SRC_H, nd.L, SRC_XAUX, P.kaux, EPI_RELU);
+        add(32, SRC_H, nd.L / 2, 0, 0, EPI_RGB);
+    } else {
+        add(32, SRC_H, nd.L, 0, 0, EPI_RGB);
+    }
+    P.n_gemm = ng;
+    P.plane_bytes = woff;
+    P.sigma_w_off = ng * 256;
+    P.f32_floats = ng * 256 + nd.L + 4;
+    P.x_tile_bytes = (P.kpe + P.kaux) * kTileM * 2;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (launch failure) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("mn_mlp_tc: mbarrier timeout block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    // kind::f16: D=f32 (bit 4), A=B=f16 (0), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: nn.Linear weight [N_src][K_src] fp32 -> image [K/8][N][8] fp16 (hi) and the residual (lo)
+// ------------------------------------------------------------------------------------------------
+__global__ void tc_pack_kernel(const float* __restrict__ wt /* packed fp32, K-major Wt[k][n_src] */, int n_src, int k_src,
+                               int N, int K, int k_real0, int k_pad0, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * K) return;
+    // i enumerates the image linearly: ((k/8)*N + n)*8 + k%8
+    const int k8 = (int)(i % 8);
+    const int n = (int)((i / 8) % N);
+    const int kc = (int)(i / (8 * (int64_t)N));
+    const int k = kc * 8 + k8;
+    int ks;
+    if (k < k_pad0) ks = k < k_real0 ? k : -1;
+    else ks = k_real0 + (k - k_pad0);
+    float v = 0.0f;
+    if (ks >= 0 && ks < k_src && n < n_src) v = wt[(int64_t)ks * n_src + n];
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+__global__ void tc_pack_f32_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_dst) dst[i] = i < n ? src[i] : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// feature tiles
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileM) tc_encode_kernel(const MlpArgs a, int kpe, int kaux, int split,
+                                                           __half* __restrict__ ximg, int64_t plane_stride_halves) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    __half* img = reinterpret_cast<__half*>(sm_raw);                  // hi image, then lo image
+    const int ktot = kpe + kaux;
+    const NetDims& nd = a.nd;
+    const int t = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t slot0 = tile * kTileM;
+    const int64_t n_slots = a.counters ? a.counters[CNT_NSLOTS] : a.B;
+    if (slot0 >= n_slots) return;
+    const int64_t slot = slot0 + t;
+    int64_t row = -1;
+    if (slot < n_slots) row = a.slot_row ? (int64_t)a.slot_row[slot] : slot;
+    __half* lo_img = img + (size_t)ktot * kTileM;
+    auto put = [&](int col, float v) {
+        const int o = (col >> 3) * (kTileM * 8) + t * 8 + (col & 7);
+        const __half h = __float2half_rn(v);
+        img[o] = h;
+        if (split) lo_img[o] = __float2half_rn(v - __half2float(h));
+    };
+    int sub = a.fixed_sub;
+    if (a.counters) {
+        sub = 0;
+        while (sub + 1 < a.n_sub && slot0 >= a.counters[CNT_START + sub + 1]) ++sub;
+    }
+    if (row < 0) {
+        for (int c = 0; c < ktot; ++c) put(c, 0.0f);
+    } else {
+        float x[4];
+        for (int j = 0; j < nd.xyz_dim; ++j) { x[j] = a.src.xyz(row, j); put(j, x[j]); }
+        for (int k = 0; k < nd.nf_xyz; ++k)
+            for (int j = 0; j < nd.xyz_dim; ++j) {
+                float s, c;
+                mn_pe_sincos(x[j], k, &s, &c);
+                const int base = nd.xyz_dim + k * 2 * nd.xyz_dim;
+                put(base + j, s);
+                put(base + nd.xyz_dim + j, c);
+            }
+        for (int c = nd.in_xyz; c < kpe; ++c) put(c, 0.0f);
+        if (kaux > 0) {
+            int col = kpe;
+            if (!a.sigma_only) {
+                if (nd.nf_dir > 0) {
+                    float d[3];
+                    for (int j = 0; j < 3; ++j) { d[j] = a.src.dir(row, j); put(col + j, d[j]); }
+                    for (int k = 0; k < nd.nf_dir; ++k)
+                        for (int j = 0; j < 3; ++j) {
+                            float s, c;
+                            mn_pe_sincos(d[j], k, &s, &c);
+                            put(col + 3 + k * 6 + j, s);
+                            put(col + 3 + k * 6 + 3 + j, c);
+                        }
+                    col += nd.in_dir;
+                }
+                if (nd.app_in_dira) {
+                    const float* emb = a.packed + (size_t)sub * a.lay.total + a.lay.emb;
+                    int id = (int)a.src.index(row);
+                    id = min(max(id, 0), nd.app_count - 1);
+                    for (int j = 0; j < nd.app; ++j) put(col + j, emb[(size_t)id * nd.app + j]);
+                    col += nd.app;
+                }
+            }
+            for (int c = col; c < ktot; ++c) put(c, 0.0f);
+        }
+    }
+    __syncthreads();
+    const int nvec = ktot * kTileM * 2 / 16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(img);
+    uint4* d4 = reinterpret_cast<uint4*>(ximg + tile * (int64_t)ktot * kTileM);
+    for (int i = t; i < nvec; i += kTileM) d4[i] = s4[i];
+    if (split) {
+        const uint4* s4l = reinterpret_cast<const uint4*>(lo_img);
+        uint4* d4l = reinterpret_cast<uint4*>(ximg + plane_stride_halves + tile * (int64_t)ktot * kTileM);
+        for (int i = t; i < nvec; i += kTileM) d4l[i] = s4l[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the MLP kernel
+// ------------------------------------------------------------------------------------------------
+struct TcArgs {
+    MlpArgs m;
+    TcPlan plan;
+    const unsigned char* wpack;   // per sub-module: [hi plane][lo plane?][fp32 block]
+    const __half* ximg;           // feature tiles (hi plane; lo plane at +x_plane_halves)
+    int64_t x_plane_halves;
+    int split;                    // 1: three MMA passes (hi*hi + hi*lo + lo*hi)
+    int desc_swap;                // debug: swap LBO / SBO roles
+    int64_t n_tiles_cap;
+};
+
+struct SmemLayout {
+    // byte offsets inside dynamic shared memory
+    int ring, h, xa, f32, bars, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(const TcPlan& p) {
+    SmemLayout s;
+    s.ring = 0;
+    s.h = s.ring + kStages * kStageBytes;
+    s.xa = s.h + p.L * kTileM * 2;
+    const int kx = p.kpe > p.kaux ? p.kpe : p.kaux;
+    s.f32 = s.xa + kx * kTileM * 2;
+    s.bars = s.f32 + ((p.f32_floats * 4 + 15) / 16) * 16;
+    s.total = s.bars + 256;
+    return s;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TcPlan& P = A.plan;
+    const SmemLayout SL = smem_layout(P);
+    unsigned char* ring = smem + SL.ring;
+    unsigned char* Hs = smem + SL.h;
+    unsigned char* XA = smem + SL.xa;
+    float* F32 = reinterpret_cast<float*>(smem + SL.f32);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bars);
+    uint64_t* full = bars;                  // [kStages]
+    uint64_t* empty = bars + kStages;       // [kStages]
+    uint64_t* xa_full = bars + 2 * kStages;
+    uint64_t* xa_empty = xa_full + 1;
+    uint64_t* acc_full = xa_full + 2;
+    uint64_t* epi_done = xa_full + 3;
+    uint64_t* f32_full = xa_full + 4;
+    uint64_t* f32_empty = xa_full + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xa_full + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_slots = A.m.counters ? A.m.counters[CNT_NSLOTS] : A.m.B;
+    const int64_t n_tiles = (n_slots + kTileM - 1) / kTileM;
+    const int n_gemm = A.m.sigma_only ? P.n_trunk : P.n_gemm;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(xa_full, 1);
+        mbar_init(xa_empty, 1);
+        mbar_init(acc_full, 1);
+        mbar_init(epi_done, 128);
+        mbar_init(f32_full, 1);
+        mbar_init(f32_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto sub_of = [&](int64_t tile) -> int {
+        int sub = A.m.fixed_sub;
+        if (A.m.counters) {
+            sub = 0;
+            const int64_t s0 = tile * kTileM;
+            while (sub + 1 < A.m.n_sub && s0 >= A.m.counters[CNT_START + sub + 1]) ++sub;
+        }
+        return sub;
+    };
+    const int npass = A.split ? 3 : 1;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, xphase = 0, fphase = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int sub = sub_of(tile);
+                const unsigned char* wsub = A.wpack + (size_t)sub * P.sub_bytes;
+                const size_t f32_off = (size_t)P.plane_bytes * 2;   // both planes are always packed
+                // biases + sigma weights of this tile's sub-module
+                mbar_wait(f32_empty, fphase ^ 1);
+                mbar_expect_tx(f32_full, (uint32_t)(((P.f32_floats * 4 + 15) / 16) * 16));
+                bulk_g2s(F32, wsub + f32_off, (uint32_t)(((P.f32_floats * 4 + 15) / 16) * 16), f32_full);
+                fphase ^= 1;
+                for (int gi = 0; gi < n_gemm; ++gi) {
+                    const TcGemm& g = P.g[gi];
+                    for (int pass = 0; pass < npass; ++pass) {
+                        // pass 0: A_hi * W_hi, pass 1: A_hi * W_lo, pass 2: A_lo * W_hi
+                        const unsigned char* wimg = wsub + (pass == 1 ? (size_t)P.plane_bytes : 0) + g.w_off;
+                        int kbase = 0;
+                        for (int sgi = 0; sgi < g.nseg; ++sgi) {
+                            const int kseg = g.k[sgi];
+                            if (g.src[sgi] != SRC_H) {
+                                const __half* xt = A.ximg + (pass == 2 ? A.x_plane_halves : 0) +
+                                                   tile * (int64_t)(P.kpe + P.kaux) * kTileM +
+                                                   (g.src[sgi] == SRC_XAUX ? (int64_t)P.kpe * kTileM : 0);
+                                mbar_wait(xa_empty, xphase ^ 1);
+                                mbar_expect_tx(xa_full, (uint32_t)(kseg * kTileM * 2));
+                                bulk_g2s(XA, xt, (uint32_t)(kseg * kTileM * 2), xa_full);
+                                xphase ^= 1;
+                            }
+                            for (int k0 = 0; k0 < kseg; k0 += kSlabCols) {
+                                const int kc = min(kSlabCols, kseg - k0);
+                                const uint32_t bytes = (uint32_t)(kc * g.n * 2);
+                                mbar_wait(&empty[stage], phase ^ 1);
+                                mbar_expect_tx(&full[stage], bytes);
+                                bulk_g2s(ring + (size_t)stage * kStageBytes, wimg + (size_t)(kbase + k0) * g.n * 2, bytes,
+                                         &full[stage]);
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            }
+                            kbase += kseg;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, xphase = 0, n_epi_waits = 0;
+            bool first = true;
+            const uint32_t h_base = smem_u32(Hs), xa_base = smem_u32(XA), ring_base = smem_u32(ring);
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int gi = 0; gi < n_gemm; ++gi) {
+                    const TcGemm& g = P.g[gi];
+                    const uint32_t idesc = make_idesc(g.n);
+                    if (!first) {
+                        // previous GEMM's accumulator drained and its activations written (and fenced)
+                        mbar_wait(epi_done, n_epi_waits & 1);
+                        ++n_epi_waits;
+                        tc_fence_after();
+                    }
+                    first = false;
+                    uint32_t accum = 0;
+                    for (int pass = 0; pass < npass; ++pass) {
+                        for (int sgi = 0; sgi < g.nseg; ++sgi) {
+                            const int kseg = g.k[sgi];
+                            const bool from_x = g.src[sgi] != SRC_H;
+                            // lo plane of H lives right after the hi plane in the H buffer (split mode)
+                            uint32_t a_base = from_x ? xa_base : h_base + (pass == 2 ? (uint32_t)(P.L * kTileM * 2) : 0u);
+                            if (from_x) {
+                                mbar_wait(xa_full, xphase);
+                                xphase ^= 1;
+                                tc_fence_after();
+                            }
+                            for (int k0 = 0; k0 < kseg; k0 += kSlabCols) {
+                                const int kc = min(kSlabCols, kseg - k0);
+                                mbar_wait(&full[stage], phase);
+                                tc_fence_after();
+                                const uint32_t b_base = ring_base + stage * kStageBytes;
+                                for (int kk = 0; kk < kc; kk += 16) {
+                                    const uint32_t a_addr = a_base + (uint32_t)((k0 + kk) / 8) * (kTileM * 16);
+                                    const uint32_t b_addr = b_base + (uint32_t)(kk / 8) * (uint32_t)(g.n * 16);
+                                    uint64_t ad, bd;
+                                    if (!A.desc_swap) {
+                                        ad = make_desc(a_addr, kTileM * 16, 128);
+                                        bd = make_desc(b_addr, (uint32_t)g.n * 16, 128);
+                                    } else {
+                                        ad = make_desc(a_addr, 128, kTileM * 16);
+                                        bd = make_desc(b_addr, 128, (uint32_t)g.n * 16);
+                                    }
+                                    tc_mma_f16(tmem_base, ad, bd, idesc, accum);
+                                    accum = 1;
+                                }
+                                tc_commit(&empty[stage]);   // frees the ring stage when these MMAs retire
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            }
+                            if (from_x) tc_commit(xa_empty);
+                        }
+                    }
+                    tc_commit(acc_full);
+                }
+            }
+        }
+    } else {
+        // =========================== epilogue (4 warps, one TMEM lane quarter each) ===========================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                 // row of the tile == TMEM lane
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t acc_phase = 0, fphase = 0;
+        const int L = P.L;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t slot = tile * kTileM + r;
+            int64_t row = -1;
+            if (slot < n_slots) row = A.m.slot_row ? (int64_t)A.m.slot_row[slot] : slot;
+            mbar_wait(f32_full, fphase);
+            fphase ^= 1;
+            float sigma = 0.0f;
+            for (int gi = 0; gi < n_gemm; ++gi) {
+                const TcGemm& g = P.g[gi];
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                const float* bias = F32 + g.bias_off;
+                if (g.epi == EPI_RGB) {
+                    uint32_t v[32];
+                    tmem_ld32(t_lane, v);
+                    tmem_ld_wait();
+                    if (row >= 0) {
+                        const NetDims& nd = A.m.nd;
+                        const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
+                        const float w = A.m.slot_w ? A.m.slot_w[slot] : 1.0f;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            if (c < nd.rgb_dim) {
+                                float x = __uint_as_float(v[c]) + bias[c];
+                                if (nd.rgb_dim == 3) x = mn_sigmoid(x);
+                                A.m.out[o + c] = A.m.slot_w ? x * w : x;
+                            }
+                        }
+                        A.m.out[o + nd.rgb_dim] = A.m.slot_w ? sigma * w : sigma;
+                    }
+                } else {
+                    const bool relu = g.epi != EPI_LINEAR;
+                    const bool want_sigma = g.epi == EPI_RELU_SIGMA;
+                    const float* sw = F32 + P.sigma_w_off;
+                    float sacc = 0.0f;
+                    for (int c0 = 0; c0 < g.n; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float x = __uint_as_float(v[j]) + bias[c0 + j];
+                            if (relu) x = fmaxf(x, 0.0f);
+                            f[j] = x;
+                        }
+                        if (want_sigma) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) sacc = fmaf(f[j], sw[c0 + j], sacc);
+                        }
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float x0 = f[j8 * 8 + 2 * e], x1 = f[j8 * 8 + 2 * e + 1];
+                                const __half2 h2 = __floats2half2_rn(x0, x1);
+                                hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                                if (A.split) {
+                                    const float2 back = __half22float2(h2);
+                                    const __half2 l2 = __floats2half2_rn(x0 - back.x, x1 - back.y);
+                                    lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                                }
+                            }
+                            const int chunk = (c0 >> 3) + j8;
+                            unsigned char* dst = Hs + (size_t)chunk * (kTileM * 16) + (size_t)r * 16;
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            if (A.split)
+                                *reinterpret_cast<uint4*>(dst + (size_t)L * kTileM * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                    }
+                    if (want_sigma) {
+                        float s = sacc + sw[L];   // sigma bias stored right after sigma_w
+                        if (A.m.sigma_noise && row >= 0) s = s + A.m.sigma_noise[row];
+                        sigma = A.m.nd.softplus ? mn_softplus_shifted(s) : fmaxf(s, 0.0f);
+                        if (A.m.sigma_only && row >= 0) {
+                            const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
+                            A.m.out[o] = A.m.slot_w ? sigma * A.m.slot_w[slot] : sigma;
+                        }
+                    }
+                    fence_proxy_async();   // generic-proxy stores to H -> visible to the tensor core (async proxy)
+                }
+                tc_fence_before();
+                mbar_arrive(epi_done);
+            }
+            mbar_arrive(f32_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+size_t mn_mlp_tc_workspace(const mn_model* m, int64_t n_tiles128, int precision) {
+    TcPlan P;
+    if (!build_plan(m->nd, &P)) return 0;
+    const size_t planes = precision == MN_PREC_TC_F16X3 ? 2 : 1;
+    return mn_align((size_t)n_tiles128 * P.x_tile_bytes * planes, 1024) + 1024;
+}
+
+int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
+    TcPlan P;
+    if (!build_plan(m->nd, &P)) {
+        m->tc_ready = 0;
+        return MN_OK;  // configuration only served by the fp32 kernel
+    }
+    const NetDims& nd = m->nd;
+    const size_t sub_bytes = mn_align((size_t)P.plane_bytes * 2 + (size_t)P.f32_floats * 4, 256);
+    if (!m->tc_packed) {
+        MN_CUDA(ctx, cudaMalloc(&m->tc_packed, sub_bytes * m->d.n_sub));
+        MN_CUDA(ctx, cudaMemsetAsync(m->tc_packed, 0, sub_bytes * m->d.n_sub, st));
+        m->tc_sub_bytes = sub_bytes;
+    }
+    unsigned char* base = (unsigned char*)m->tc_packed + (size_t)sub * sub_bytes;
+    const float* Pk = m->packed + (size_t)sub * m->lay.total;
+    float* f32 = reinterpret_cast<float*>(base + (size_t)P.plane_bytes * 2);
+    auto pack = [&](const TcGemm& g, const float* wt, int n_src, int k_src, int k_real0, int k_pad0, const float* bias,
+                    int n_bias) -> int {
+        const int K = g.k[0] + (g.nseg > 1 ? g.k[1] : 0);
+        const int64_t n = (int64_t)g.n * K;
+        __half* hi = reinterpret_cast<__half*>(base + g.w_off);
+        __half* lo = reinterpret_cast<__half*>(base + P.plane_bytes + g.w_off);
+        tc_pack_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, k_real0, k_pad0, hi, lo);
+        MN_LAUNCH_CHECK(ctx);
+        tc_pack_f32_kernel<<<1, 256, 0, st>>>(bias, n_bias, f32 + g.bias_off, 256);
+        MN_LAUNCH_CHECK(ctx);
+        return MN_OK;
+    };
+    int rc, gi = 0;
+    for (int i = 0; i < nd.layers; ++i, ++gi) {
+        const bool has_pe = (i == 0) || ((nd.skip_mask >> i) & 1);
+        if ((rc = pack(P.g[gi], Pk + m->lay.w[i], nd.L, m->lay.kin[i], has_pe ? nd.in_xyz : 0, has_pe ? P.kpe : 0,
+                       Pk + m->lay.b[i], nd.L)))
+            return rc;
+    }
+    if (nd.has_dir_a) {
+        if ((rc = pack(P.g[gi++], Pk + m->lay.final_w, nd.L, nd.L, 0, 0, Pk + m->lay.final_b, nd.L))) return rc;
+        if ((rc = pack(P.g[gi++], Pk + m->lay.dira_w, nd.L / 2, nd.L + nd.aux, 0, 0, Pk + m->lay.dira_b, nd.L / 2))) return rc;
+    }
+    if ((rc = pack(P.g[gi++], Pk + m->lay.rgb_w, nd.rgb_dim, nd.rgb_in, 0, 0, Pk + m->lay.rgb_b, nd.rgb_dim))) return rc;
+    // sigma_w [L] + sigma_b
+    tc_pack_f32_kernel<<<(unsigned)mn_cdiv(nd.L + 4, 256), 256, 0, st>>>(Pk + m->lay.sigma_w, nd.L, f32 + P.sigma_w_off, nd.L);
+    MN_LAUNCH_CHECK(ctx);
+    tc_pack_f32_kernel<<<1, 32, 0, st>>>(Pk + m->lay.sigma_b, 1, f32 + P.sigma_w_off + nd.L, 4);
+    MN_LAUNCH_CHECK(ctx);
+    m->tc_ready = 1;
+    return MN_OK;
+}
+
+int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles128, int precision, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+    TcArgs A{};
+    if (!build_plan(a.nd, &A.plan) || !m->tc_ready)
+        return mn_fail(ctx, MN_ERR_UNSUPPORTED,
+                       "tensor-core MLP path covers layer_dim <= 256 (multiple of 32), rgb_dim <= 32, no affine appearance; "
+                       "use precision 'fp32' for this model");
+    if (n_tiles128 <= 0) return MN_OK;
+    TcPlan& P = A.plan;
+    const int split = precision == MN_PREC_TC_F16X3 ? 1 : 0;
+    P.sub_bytes = (int)m->tc_sub_bytes;
+    // the packed layout always holds both planes; tell the kernel where the fp32 block is
+    A.m = a;
+    A.wpack = (const unsigned char*)m->tc_packed;
+    A.split = split;
+    static int desc_swap = -1;
+    if (desc_swap < 0) {
+        const char* e = getenv("MN_TC_DESC_SWAP");
+        desc_swap = (e && e[0] == '1') ? 1 : 0;
+    }
+    A.desc_swap = desc_swap;
+    A.n_tiles_cap = n_tiles128;
+    const size_t need = mn_mlp_tc_workspace(m, n_tiles128, precision);
+    if (ws_bytes < need || !ws) return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_mlp_tc_launch: workspace too small");
+    uintptr_t wp = ((uintptr_t)ws + 1023) / 1024 * 1024;
+    __half* ximg = reinterpret_cast<__half*>(wp);
+    A.ximg = ximg;
+    A.x_plane_halves = (int64_t)n_tiles128 * (P.kpe + P.kaux) * kTileM;
+
+    const size_t enc_sm = (size_t)P.x_tile_bytes * (split ? 2 : 1);
+    MN_CUDA(ctx, cudaFuncSetAttribute(tc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_sm));
+    tc_encode_kernel<<<(unsigned)n_tiles128, kTileM, enc_sm, st>>>(a, P.kpe, P.kaux, split, ximg, A.x_plane_halves);
+    MN_LAUNCH_CHECK(ctx);
+
+    SmemLayout SL = smem_layout(P);
+    int total = SL.total + (split ? P.L * kTileM * 2 : 0);   // lo plane of H
+    if (split) {
+        // lo plane sits between H-hi and XA: shift the later regions
+        return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tc_f16x3 kernel variant not enabled yet");
+    }
+    MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
+    const unsigned grid = (unsigned)(n_tiles128 < ctx->sm_count ? n_tiles128 : ctx->sm_count);
+    tc_mlp_kernel<<<grid, kThreads, total, st>>>(A);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
 }

@@ -17,7 +17,9 @@ pytestmark = pytest.mark.gpu
 
 DEV = torch.device('cuda:0')
 MLP_TOL = {'fp32': 1e-5, 'tc_f16': 1e-4, 'tc_f16x3': 1e-5}
-PRECS = ['fp32']
+PRECS = ['fp32', 'tc_f16']
+TC_UNSUPPORTED_NERF = {'fg512', 'affine'}      # served by the fp32 kernel only
+TC_UNSUPPORTED_RENDER = {'c4_mega25_512'}
 
 
 def M():
@@ -88,6 +90,10 @@ def test_nerf_variants(golden, vname, prec):
     assert C.net_checksum(net) == gd['wsum']
     p = product_net(net)
     tol = MLP_TOL[prec]
+    if prec != 'fp32' and vname in TC_UNSUPPORTED_NERF:
+        with pytest.raises(RuntimeError, match="use precision 'fp32'"):
+            p(x.to(DEV))
+        return
     assert relerr(p(x.to(DEV)), gd['out']) <= tol
     xs = C.nerf_rows(spec, 160, 31, sigma_only=True)
     assert relerr(p(xs.to(DEV), sigma_only=True), gd['sigma_only']) <= tol
@@ -258,7 +264,9 @@ def test_resample_indices_bit_exact(golden):
     u = torch.linspace(0, 1, 128, device=DEV)
     K.check(K.lib().mn_sample_pdf(sg.h, K.ptr(zj), K.ptr(w), s, None, K.ptr(u), 0, n, s, 128, K.ptr(out), None, K.ptr(cdf_out),
                                   sg.st), sg.h)
-    assert float((cdf_out.cpu() - gd['cdf']).abs().max()) <= 1.2e-7
+    # the pdf normaliser is summed in fp64 here and by torch's vectorised fp32 reduction in the oracle:
+    # a 1-ulp difference of the sum moves every cdf entry by up to ~2 ulp of 1.0
+    assert float((cdf_out.cpu() - gd['cdf']).abs().max()) <= 2.5e-7
     frac_same = float((out.cpu() == gd['z']).float().mean())
     assert frac_same > 0.9 and relerr(out, gd['z']) <= 1e-4, frac_same
 
@@ -314,6 +322,8 @@ def test_render_rays(golden, rname, prec):
     from argparse import Namespace
     m = M()
     m.set_precision(prec)
+    if prec != 'fp32' and rname in TC_UNSUPPORTED_RENDER:
+        pytest.skip('512-wide sub-modules run on the fp32 kernel in this round')
     net, bg_net, rays, idx, opts, center, radius = C.render_case(rname)
     gd = golden[f'render_{rname}']
     assert C.net_checksum(net) + (C.net_checksum(bg_net) if bg_net else 0.0) == gd['wsum']
