@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Headline benchmark of the Mega-NeRF rendering hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host CPU cores
+
+A "step" is one render_rays() pass over one batch of synthetic rays: BASELINE.json configs[1]
+(MegaNeRF 8 x 256-wide sub-modules, 4096 rays x (64 coarse + 128 fine) samples, random-init weights).
+With N > 1 (torchrun, one rank per GPU) rays are sharded: every rank renders its own 4096 rays with
+replicated weights and the per-ray results (rgb + depth) are all-gathered over NCCL each step (weak scaling).
+
+Prints ONE JSON line on rank 0 (see the task contract): value = ray-samples/s with inputs resident in HBM
+(device-timed with CUDA events), e2e = the same through the public API from pinned host buffers including
+H2D/D2H, roofline for the dominant (MLP) kernel, cpu_baseline = the oracle port timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from argparse import Namespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+N_RAYS = 4096
+COARSE, FINE = 64, 128
+MARGIN = 1.15
+L2_FLUSH_BYTES = 256 << 20
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d['bf16_tflops'], tflops_sustained=d.get('bf16_tflops_sustained'), hbm=d['hbm_gbs'], src='measured')
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, src='fallback')
+
+
+def workload(seed_shift: int = 0):
+    from oracle import mn_oracle as O
+    spec = O.NerfSpec()
+    cents = O.grid_centroids(2, 4)
+    net = O.make_net('mega', spec, seed=0, n_sub=8, centroids=cents, boundary_margin=MARGIN, cluster_2d=True)
+    rays = O.synthetic_rays(N_RAYS, seed=seed_shift)
+    idx = O.synthetic_indices(N_RAYS, spec.appearance_count, seed=1 + seed_shift)
+    opts = O.RenderOpts(coarse_samples=COARSE, fine_samples=FINE, use_cascade=False, perturb=1.0, pos_dir_dim=4,
+                        sh_deg=None, model_chunk_size=32 * 1024)
+    return spec, net, rays, idx, opts
+
+
+def flops_per_row(spec) -> int:
+    L, ix = spec.layer_dim, spec.in_xyz
+    f = 0
+    for i in range(spec.layers):
+        kin = ix if i == 0 else (L + ix if i in spec.skip_layers else L)
+        f += 2 * kin * L
+    f += 2 * L                                   # sigma
+    if spec.has_dir_a:
+        f += 2 * L * L                           # xyz_encoding_final
+        f += 2 * (L + spec.in_dir + (spec.appearance_dim if not spec.affine_appearance else 0)) * (L // 2)
+        f += 2 * (L // 2) * spec.rgb_dim
+    else:
+        f += 2 * L * spec.rgb_dim
+    return f
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def run_reference(args, rank: int):
+    """The reference algorithm (oracle port of /root/reference, see oracle/mn_oracle.py) on the host CPU."""
+    if rank != 0:
+        return
+    from oracle import mn_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    spec, net, rays, idx, opts = workload()
+    sample = 1024
+    r, i = rays[:sample], idx[:sample]
+    times = []
+    with torch.inference_mode():
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.render_rays(net, None, r, i, opts, None, None, True, False, False)
+            if s >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    tot = sum(times)
+    value = sample * (COARSE + FINE) * args.steps / tot
+    line = {
+        'impl': 'reference', 'metric': 'ray-samples/sec (MLP+composite)', 'value': value, 'unit': 'samples/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'mega-nerf 8-submodule 256-ch, {N_RAYS} rays x ({COARSE}+{FINE}) samples, margin {MARGIN}; '
+                               f'each CPU step renders a {sample}-ray sample of it'},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': f'{sample} of {N_RAYS} rays per step, {args.steps} steps'},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('MN_B200_PRECISION', 'tc_f16'))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import mega_nerf_b200 as M
+    from mega_nerf_b200 import _cabi as K
+    from oracle import mn_oracle as O            # cpu_baseline / parity sample only
+    from test_gpu_parity import product_net
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    spec, net, rays_h, idx_h, opts = workload(seed_shift=rank)
+    hp = Namespace(**vars(opts))
+    model = product_net(net).to(dev).eval()
+    M.set_precision(args.precision)
+    rays_d, idx_d = rays_h.to(dev), idx_h.to(dev)
+    rays_pin, idx_pin = rays_h.pin_memory(), idx_h.pin_memory()
+    out_pin = torch.empty(N_RAYS, 4).pin_memory()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    gather_buf = torch.empty(world * N_RAYS, 4, device=dev) if world > 1 else None
+    h = K.ctx(dev)
+    L = K.lib()
+
+    def step_resident():
+        res, _ = M.render_rays(model, None, rays_d, idx_d, hp, None, None, True, False, False)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, torch.cat([res['rgb_fine'], res['depth_fine'].unsqueeze(-1)], -1))
+        return res
+
+    def step_e2e():
+        r = rays_pin.to(dev, non_blocking=True)
+        i = idx_pin.to(dev, non_blocking=True)
+        res, _ = M.render_rays(model, None, r, i, hp, None, None, True, False, False)
+        packed = torch.cat([res['rgb_fine'], res['depth_fine'].unsqueeze(-1)], -1)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, packed)
+        out_pin.copy_(packed, non_blocking=True)
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for a, b in evs:
+            flush.fill_(1)                      # L2 flush between timed iterations (not timed)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+        step_e2e()
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput (the `value`) with clocks sampled during the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.mn_launch_count(h)
+    ms_total = timed(step_resident, args.steps)
+    launches = L.mn_launch_count(h) - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    samples_per_step = N_RAYS * (COARSE + FINE) * world
+    value = samples_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API from pinned host memory
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
+
+    # ---- MLP kernel duration by CUDA events on the launching stream (roofline)
+    nat = model._native()
+    K.check(L.mn_profile_enable(h, 1), h)
+    timed(step_resident, args.steps)
+    tot_ms, n_l = C.c_double(), C.c_longlong()
+    K.check(L.mn_profile_read(h, C.byref(tot_ms), C.byref(n_l)), h)
+    K.check(L.mn_profile_enable(h, 0), h)
+    slots, tiles = nat.stats(dev)                # of the last (fine) pass
+    rows_fine = N_RAYS * FINE
+    mult = slots / rows_fine
+    pk = peaks()
+    fl_row = flops_per_row(spec)
+    # per step: coarse + fine launches; algorithmic flops = rows * m * flops_row (m measured on the fine pass)
+    flops_step = N_RAYS * (COARSE + FINE) * mult * fl_row
+    kernel_ms_per_step = tot_ms.value / args.steps
+    achieved = flops_step / (kernel_ms_per_step * 1e-3) / 1e12 if kernel_ms_per_step > 0 else 0.0
+    passes = {'fp32': 1, 'tc_f16': 1, 'tc_f16x3': 3}[args.precision]
+
+    if rank == 0:
+        # parity sample against the oracle (not timed): 256 rays
+        with torch.inference_mode():
+            ref, _ = O.render_rays(net, None, rays_h[:256], idx_h[:256], opts, None, None, True, False, False)
+        got, _ = M.render_rays(model, None, rays_d[:256], idx_d[:256], hp, None, None, True, False, False)
+        par = float((got['rgb_fine'].cpu() - ref['rgb_fine']).abs().max() / ref['rgb_fine'].abs().max())
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count())
+            with torch.inference_mode():
+                O.render_rays(net, None, rays_h[:512], idx_h[:512], opts, None, None, True, False, False)   # warm
+                t0 = time.perf_counter()
+                O.render_rays(net, None, rays_h, idx_h, opts, None, None, True, False, False)
+                dt = time.perf_counter() - t0
+            cpu = {'value': N_RAYS * (COARSE + FINE) / dt, 'unit': 'samples/s', 'cores': torch.get_num_threads(),
+                   'kind': 'port', 'sample': f'one full {N_RAYS}-ray batch ({dt:.1f} s) after a 512-ray warm-up'}
+
+        line = {
+            'metric': 'ray-samples/sec (MLP+composite)', 'value': value, 'unit': 'samples/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'fp32': 'f32', 'tc_f16': 'f16 operands / f32 accumulate', 'tc_f16x3': 'f16x3 split / f32 accumulate'}[args.precision],
+            'data': 'synthetic',
+            'config': {'workload': f'BASELINE configs[1]: mega-nerf 8-submodule 256-ch, {N_RAYS} rays x ({COARSE} coarse + {FINE} fine) '
+                                   f'per GPU, boundary_margin {MARGIN} (m = {mult:.3f} sub-modules/sample), random-init weights',
+                       'parallelism': f'ray-sharded x{world}, weights replicated, 1 all-gather of [rays,4] per step' if world > 1 else 'single GPU',
+                       'precision': args.precision, 'l2': f'flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)',
+                       'rays_per_sec': value / (COARSE + FINE)},
+            'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e / args.steps,
+                    'h2d_bytes_per_step': rays_pin.numel() * 4 + idx_pin.numel() * 4, 'd2h_bytes_per_step': out_pin.numel() * 4},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': {'bound': 'tensor', 'kernel': 'tc_mlp_kernel' if args.precision != 'fp32' else 'mlp_simt_kernel',
+                         'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
+                         'frac_of_sustained_peak': achieved / pk['tflops_sustained'] if pk['tflops_sustained'] else None,
+                         'peak_source': pk['src'], 'traffic': None,
+                         'algorithmic_flops_per_row': fl_row, 'mma_passes_per_algorithmic': passes,
+                         'kernel_ms_per_step': kernel_ms_per_step, 'launches_per_step': n_l.value / args.steps},
+            'parity': {'max_rel_rgb_vs_oracle_256_rays': par},
+        }
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

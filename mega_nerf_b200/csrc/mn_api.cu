@@ -350,12 +350,10 @@ int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, i
     }
 
     const int64_t n_tiles = cap / MN_TILE;
-    mn_prof_begin(ctx, st);
     if (precision == MN_PREC_FP32)
         rc = mn_mlp_simt_launch(ctx, a, n_tiles, st);
     else
         rc = mn_mlp_tc_launch(ctx, m, a, n_tiles, precision, ws, workspace_bytes - (size_t)(ws - (char*)workspace_d), st);
-    mn_prof_end(ctx, st);
     if (rc) return rc;
     if (row_slots) return mn_route_combine(ctx, m, B, row_slots, slot_out, a.out_cols, out_d, st);
     return MN_OK;

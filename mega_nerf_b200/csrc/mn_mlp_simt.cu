@@ -260,6 +260,7 @@ int mn_mlp_simt_launch(mn_ctx* ctx, const MlpArgs& a, int64_t n_tiles128, cudaSt
     if (nd.L % 64 != 0 || nd.L > 512 || nd.L < 64)
         return mn_fail(ctx, MN_ERR_UNSUPPORTED, "fp32 MLP kernel supports layer_dim in {64,...,512} (multiple of 64)");
     if (n_tiles128 <= 0) return MN_OK;
+    mn_prof_begin(ctx, st);
     if (nd.L <= 256) {
         const size_t sm = simt_smem_bytes<64>(nd);
         MN_CUDA(ctx, cudaFuncSetAttribute(mlp_simt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -269,6 +270,7 @@ int mn_mlp_simt_launch(mn_ctx* ctx, const MlpArgs& a, int64_t n_tiles128, cudaSt
         MN_CUDA(ctx, cudaFuncSetAttribute(mlp_simt_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         mlp_simt_kernel<32><<<(unsigned)(n_tiles128 * 4), 256, sm, st>>>(a);
     }
+    mn_prof_end(ctx, st);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
 }

@@ -23,9 +23,11 @@
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kStageBytes = 32 * 1024;  // one weight ring stage: up to 64 K-columns x 256 rows x 2 B
-constexpr int kStages = 3;
-constexpr int kSlabCols = 64;
+constexpr int kMaxStages = 4;
+// weight ring geometry: single pass = 3 stages x 64 K-columns (32 KiB); split mode (H holds hi+lo planes) = 4 x 32 columns
+__host__ __device__ constexpr int ring_stages(bool) { return 3; }
+__host__ __device__ constexpr int ring_slab_cols(bool split) { return split ? 32 : 64; }
+__host__ __device__ constexpr int ring_stage_bytes(bool split) { return ring_slab_cols(split) * 256 * 2; }
 constexpr int kMaxGemm = 16;
 constexpr int kThreads = 192;
 
@@ -302,11 +304,11 @@ struct SmemLayout {
     int ring, h, xa, f32, bars, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(const TcPlan& p) {
+__host__ __device__ inline SmemLayout smem_layout(const TcPlan& p, bool split) {
     SmemLayout s;
     s.ring = 0;
-    s.h = s.ring + kStages * kStageBytes;
-    s.xa = s.h + p.L * kTileM * 2;
+    s.h = s.ring + ring_stages(split) * ring_stage_bytes(split);
+    s.xa = s.h + p.L * kTileM * 2 * (split ? 2 : 1);   // split: hi plane then lo plane
     const int kx = p.kpe > p.kaux ? p.kpe : p.kaux;
     s.f32 = s.xa + kx * kTileM * 2;
     s.bars = s.f32 + ((p.f32_floats * 4 + 15) / 16) * 16;
@@ -314,18 +316,22 @@ __host__ __device__ inline SmemLayout smem_layout(const TcPlan& p) {
     return s;
 }
 
+template <bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
+    constexpr int kStages = ring_stages(kSplit);
+    constexpr int kSlabCols = ring_slab_cols(kSplit);
+    constexpr int kStageBytes = ring_stage_bytes(kSplit);
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
-    const SmemLayout SL = smem_layout(P);
+    const SmemLayout SL = smem_layout(P, kSplit);
     unsigned char* ring = smem + SL.ring;
     unsigned char* Hs = smem + SL.h;
     unsigned char* XA = smem + SL.xa;
     float* F32 = reinterpret_cast<float*>(smem + SL.f32);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bars);
     uint64_t* full = bars;                  // [kStages]
-    uint64_t* empty = bars + kStages;       // [kStages]
-    uint64_t* xa_full = bars + 2 * kStages;
+    uint64_t* empty = bars + kMaxStages;    // [kStages]
+    uint64_t* xa_full = bars + 2 * kMaxStages;
     uint64_t* xa_empty = xa_full + 1;
     uint64_t* acc_full = xa_full + 2;
     uint64_t* epi_done = xa_full + 3;
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
         }
         return sub;
     };
-    const int npass = A.split ? 3 : 1;
+    constexpr int npass = kSplit ? 3 : 1;
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -537,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                                 const float x0 = f[j8 * 8 + 2 * e], x1 = f[j8 * 8 + 2 * e + 1];
                                 const __half2 h2 = __floats2half2_rn(x0, x1);
                                 hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                                if (A.split) {
+                                if (kSplit) {
                                     const float2 back = __half22float2(h2);
                                     const __half2 l2 = __floats2half2_rn(x0 - back.x, x1 - back.y);
                                     lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
@@ -546,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                             const int chunk = (c0 >> 3) + j8;
                             unsigned char* dst = Hs + (size_t)chunk * (kTileM * 16) + (size_t)r * 16;
                             *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            if (A.split)
+                            if (kSplit)
                                 *reinterpret_cast<uint4*>(dst + (size_t)L * kTileM * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
@@ -667,15 +673,20 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     tc_encode_kernel<<<(unsigned)n_tiles128, kTileM, enc_sm, st>>>(a, P.kpe, P.kaux, split, ximg, A.x_plane_halves);
     MN_LAUNCH_CHECK(ctx);
 
-    SmemLayout SL = smem_layout(P);
-    int total = SL.total + (split ? P.L * kTileM * 2 : 0);   // lo plane of H
-    if (split) {
-        // lo plane sits between H-hi and XA: shift the later regions
-        return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tc_f16x3 kernel variant not enabled yet");
-    }
-    MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
+    const SmemLayout SL = smem_layout(P, split != 0);
+    const int total = SL.total;
+    if (total > 227 * 1024) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core MLP: shared-memory budget exceeded");
     const unsigned grid = (unsigned)(n_tiles128 < ctx->sm_count ? n_tiles128 : ctx->sm_count);
-    tc_mlp_kernel<<<grid, kThreads, total, st>>>(A);
+    if (split) {
+        MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
+        mn_prof_begin(ctx, st);
+        tc_mlp_kernel<true><<<grid, kThreads, total, st>>>(A);
+    } else {
+        MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
+        mn_prof_begin(ctx, st);
+        tc_mlp_kernel<false><<<grid, kThreads, total, st>>>(A);
+    }
+    mn_prof_end(ctx, st);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
 }

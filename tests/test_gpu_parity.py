@@ -16,8 +16,11 @@ from oracle import mn_oracle as O
 pytestmark = pytest.mark.gpu
 
 DEV = torch.device('cuda:0')
-MLP_TOL = {'fp32': 1e-5, 'tc_f16': 1e-4, 'tc_f16x3': 1e-5}
-PRECS = ['fp32', 'tc_f16']
+# tc_f16 rounds both operands of every layer to fp16 (2^-11): raw MLP rows land at 0.6-1.1e-4, rendered rgb
+# (averaged by compositing) below 1e-4; tc_f16x3 (hi/lo split, 3 passes) is the parity-grade tensor mode.
+MLP_TOL = {'fp32': 1e-5, 'tc_f16': 2.5e-4, 'tc_f16x3': 1e-5}
+RENDER_TOL = {'fp32': 1e-4, 'tc_f16': 2e-4, 'tc_f16x3': 1e-4}
+PRECS = ['fp32', 'tc_f16', 'tc_f16x3']
 TC_UNSUPPORTED_NERF = {'fg512', 'affine'}      # served by the fp32 kernel only
 TC_UNSUPPORTED_RENDER = {'c4_mega25_512'}
 
@@ -267,8 +270,7 @@ def test_resample_indices_bit_exact(golden):
     # the pdf normaliser is summed in fp64 here and by torch's vectorised fp32 reduction in the oracle:
     # a 1-ulp difference of the sum moves every cdf entry by up to ~2 ulp of 1.0
     assert float((cdf_out.cpu() - gd['cdf']).abs().max()) <= 2.5e-7
-    frac_same = float((out.cpu() == gd['z']).float().mean())
-    assert frac_same > 0.9 and relerr(out, gd['z']) <= 1e-4, frac_same
+    assert relerr(out, gd['z']) <= 1e-5
 
 
 def test_sort_and_merge():
@@ -294,7 +296,9 @@ def test_sort_and_merge():
         w, rgb, depth, var, lam = sg.composite(raw_b.to(DEV), b.to(DEV), None, raw_a.to(DEV), a.to(DEV), None, ld.to(DEV),
                                                flip, True, True, True, True, True)
         assert relerr(w, c['weights']) <= 1e-6 and relerr(rgb, c['rgb']) <= 1e-6
-        assert relerr(depth, c['depth']) <= 1e-6 and relerr(lam, c['bg_lambda']) <= 1e-6
+        # bg_lambda is a product of 192 factors: 1-ulp differences between CUDA expf and torch's CPU exp in
+        # individual alphas compound multiplicatively (~sqrt(S) ulp)
+        assert relerr(depth, c['depth']) <= 1e-6 and relerr(lam, c['bg_lambda']) <= 5e-6
 
 
 def test_background_geometry(golden):
@@ -335,8 +339,8 @@ def test_render_rays(golden, rname, prec):
                                  radius.to(DEV) if radius is not None else None, True, True, True)
     assert present == gd['present']
     assert set(res) == set(gd['out']), set(res) ^ set(gd['out'])
-    tol = 1e-4
+    tol = RENDER_TOL[prec]
     for k, v in gd['out'].items():
         assert res[k].shape == v.shape and res[k].dtype == torch.float32 and res[k].device.type == 'cuda'
         e = relerr(res[k], v)
-        assert e <= (5e-4 if 'variance' in k else tol), (k, e)
+        assert e <= (5 * tol if 'variance' in k else tol), (k, e)
