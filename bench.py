@@ -108,14 +108,37 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def usable_cpus() -> int:
+    """Host threads this process can really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q, p = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, n)
+
+
+def cpu_rays_per_sec(O, net, rays, idx, opts, n_probe: int = 64) -> float:
+    """Quick probe of the oracle's speed on this host, used to bound the timed CPU samples."""
+    with torch.inference_mode():
+        O.render_rays(net, None, rays[:n_probe], idx[:n_probe], opts, None, None, True, False, False)
+        t0 = time.perf_counter()
+        O.render_rays(net, None, rays[:n_probe], idx[:n_probe], opts, None, None, True, False, False)
+        return n_probe / (time.perf_counter() - t0)
+
+
 def run_reference(args, rank: int):
     """The reference algorithm (oracle port of /root/reference, see oracle/mn_oracle.py) on the host CPU."""
     if rank != 0:
         return
     from oracle import mn_oracle as O
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(usable_cpus())
     spec, net, rays, idx, opts = workload()
-    sample = 1024
+    rate = cpu_rays_per_sec(O, net, rays, idx, opts)
+    # bounded sample: the whole --steps/--warmup run should take about two minutes of CPU time
+    sample = int(min(N_RAYS, max(64, rate * 120.0 / (args.steps + args.warmup)))) // 64 * 64
     r, i = rays[:sample], idx[:sample]
     times = []
     with torch.inference_mode():
@@ -140,7 +163,14 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+def log(msg):
+    if os.environ.get('MN_BENCH_VERBOSE', '1') == '1':
+        print(f'[bench {time.strftime("%H:%M:%S")}] {msg}', file=sys.stderr, flush=True)
+
+
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(240, repeat=True, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -216,10 +246,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    log('workload built; warm-up')
     for _ in range(args.warmup):
         step_resident()
         step_e2e()
     torch.cuda.synchronize()
+    log('warm-up done')
 
     # ---- device-resident throughput (the `value`) with clocks sampled during the timed region
     sampler = ClockSampler(local_rank)
@@ -232,10 +264,12 @@ def main():
     samples_per_step = N_RAYS * (COARSE + FINE) * world
     value = samples_per_step * args.steps / (ms_total * 1e-3)
 
+    log(f'resident: {ms_total / args.steps:.3f} ms/step')
     # ---- end to end through the public API from pinned host memory
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
 
+    log(f'e2e: {ms_e2e / args.steps:.3f} ms/step')
     # ---- MLP kernel duration by CUDA events on the launching stream (roofline)
     nat = model._native()
     K.check(L.mn_profile_enable(h, 1), h)
@@ -254,23 +288,28 @@ def main():
     achieved = flops_step / (kernel_ms_per_step * 1e-3) / 1e12 if kernel_ms_per_step > 0 else 0.0
     passes = {'fp32': 1, 'tc_f16': 1, 'tc_f16x3': 3}[args.precision]
 
+    log(f'mlp kernel: {kernel_ms_per_step:.3f} ms/step, m={mult:.3f}')
     if rank == 0:
         # parity sample against the oracle (not timed): 256 rays
+        torch.set_num_threads(usable_cpus())
         with torch.inference_mode():
             ref, _ = O.render_rays(net, None, rays_h[:256], idx_h[:256], opts, None, None, True, False, False)
         got, _ = M.render_rays(model, None, rays_d[:256], idx_d[:256], hp, None, None, True, False, False)
         par = float((got['rgb_fine'].cpu() - ref['rgb_fine']).abs().max() / ref['rgb_fine'].abs().max())
 
+        log(f'parity sample done: {par:.2e}')
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            torch.set_num_threads(os.cpu_count())
+            torch.set_num_threads(usable_cpus())
+            rate = cpu_rays_per_sec(O, net, rays_h, idx_h, opts)
+            n_cpu = int(min(N_RAYS, max(64, rate * 15.0))) // 64 * 64         # ~15 s of CPU work
             with torch.inference_mode():
-                O.render_rays(net, None, rays_h[:512], idx_h[:512], opts, None, None, True, False, False)   # warm
                 t0 = time.perf_counter()
-                O.render_rays(net, None, rays_h, idx_h, opts, None, None, True, False, False)
+                O.render_rays(net, None, rays_h[:n_cpu], idx_h[:n_cpu], opts, None, None, True, False, False)
                 dt = time.perf_counter() - t0
-            cpu = {'value': N_RAYS * (COARSE + FINE) / dt, 'unit': 'samples/s', 'cores': torch.get_num_threads(),
-                   'kind': 'port', 'sample': f'one full {N_RAYS}-ray batch ({dt:.1f} s) after a 512-ray warm-up'}
+            cpu = {'value': n_cpu * (COARSE + FINE) / dt, 'unit': 'samples/s', 'cores': torch.get_num_threads(),
+                   'kind': 'port', 'sample': f'first {n_cpu} of the {N_RAYS} rays of the same batch ({dt:.1f} s), after a 64-ray probe'}
+            log(f'cpu baseline: {cpu["value"]:.3e} samples/s on {cpu["cores"]} threads')
 
         line = {
             'metric': 'ray-samples/sec (MLP+composite)', 'value': value, 'unit': 'samples/s',
