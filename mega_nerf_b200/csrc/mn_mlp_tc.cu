@@ -25,11 +25,10 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 4;
 // weight ring geometry: single pass = 3 stages x 64 K-columns (32 KiB); split mode (H holds hi+lo planes) = 4 x 32 columns
-__host__ __device__ constexpr int ring_stages(bool) { return 3; }
 __host__ __device__ constexpr int ring_slab_cols(bool split) { return split ? 32 : 64; }
 __host__ __device__ constexpr int ring_stage_bytes(bool split) { return ring_slab_cols(split) * 256 * 2; }
 constexpr int kMaxGemm = 16;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // producer warp, MMA warp, 8 epilogue warps
 
 enum { SRC_H = 0, SRC_XPE = 1, SRC_XAUX = 2 };
 enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
@@ -59,7 +58,7 @@ struct TcPlan {
 int pad16(int x) { return (x + 15) / 16 * 16; }
 
 bool build_plan(const NetDims& nd, TcPlan* p) {
-    if (nd.L % 32 != 0 || nd.L > 256 || nd.L < 32 || nd.rgb_dim > 32 || nd.affine || nd.layers > 12) return false;
+    if (nd.L % 64 != 0 || nd.L > 256 || nd.L < 64 || nd.rgb_dim > 32 || nd.affine || nd.layers > 12) return false;
     TcPlan& P = *p;
     P = TcPlan{};
     P.L = nd.L;
@@ -301,43 +300,56 @@ struct TcArgs {
 
 struct SmemLayout {
     // byte offsets inside dynamic shared memory
-    int ring, h, xa, f32, bars, total;
+    int ring, h, xa, f32, sigp, bars, total, stages;
 };
+
+constexpr int kSmemMax = 227 * 1024;
 
 __host__ __device__ inline SmemLayout smem_layout(const TcPlan& p, bool split) {
     SmemLayout s;
-    s.ring = 0;
-    s.h = s.ring + ring_stages(split) * ring_stage_bytes(split);
-    s.xa = s.h + p.L * kTileM * 2 * (split ? 2 : 1);   // split: hi plane then lo plane
     const int kx = p.kpe > p.kaux ? p.kpe : p.kaux;
+    const int fixed = p.L * kTileM * 2 * (split ? 2 : 1) + kx * kTileM * 2 + ((p.f32_floats * 4 + 15) / 16) * 16 + 1024 + 256;
+    int st = (kSmemMax - fixed) / ring_stage_bytes(split);
+    if (st > kMaxStages) st = kMaxStages;
+    s.stages = st;
+    s.ring = 0;
+    s.h = s.ring + st * ring_stage_bytes(split);
+    s.xa = s.h + p.L * kTileM * 2 * (split ? 2 : 1);   // split: hi plane then lo plane
     s.f32 = s.xa + kx * kTileM * 2;
-    s.bars = s.f32 + ((p.f32_floats * 4 + 15) / 16) * 16;
+    s.sigp = s.f32 + ((p.f32_floats * 4 + 15) / 16) * 16;
+    s.bars = s.sigp + 1024;
     s.total = s.bars + 256;
     return s;
 }
 
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue.  Epilogue warp w owns TMEM lanes
+// 32*(w%4).. (hardware rule) and, within every 64-column slab of the accumulator, the 32-column half
+// (w-2)/4; a slab of the next layer's A operand is published (mbarrier hready[slab]) as soon as all eight
+// warps have written their part, so the next layer's MMAs trail the epilogue slab by slab while the
+// other accumulator buffer is still being drained.
 template <bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
-    constexpr int kStages = ring_stages(kSplit);
     constexpr int kSlabCols = ring_slab_cols(kSplit);
     constexpr int kStageBytes = ring_stage_bytes(kSplit);
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
     const SmemLayout SL = smem_layout(P, kSplit);
+    const int kStages = SL.stages;
     unsigned char* ring = smem + SL.ring;
     unsigned char* Hs = smem + SL.h;
     unsigned char* XA = smem + SL.xa;
     float* F32 = reinterpret_cast<float*>(smem + SL.f32);
+    float* SIGP = reinterpret_cast<float*>(smem + SL.sigp);   // [2][128] partial sigma dot products
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bars);
-    uint64_t* full = bars;                  // [kStages]
-    uint64_t* empty = bars + kMaxStages;    // [kStages]
+    uint64_t* full = bars;                  // [kMaxStages]
+    uint64_t* empty = bars + kMaxStages;    // [kMaxStages]
     uint64_t* xa_full = bars + 2 * kMaxStages;
     uint64_t* xa_empty = xa_full + 1;
-    uint64_t* acc_full = xa_full + 2;
-    uint64_t* epi_done = xa_full + 3;
-    uint64_t* f32_full = xa_full + 4;
-    uint64_t* f32_empty = xa_full + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xa_full + 6);
+    uint64_t* acc_full = xa_full + 2;       // [2]
+    uint64_t* hready = xa_full + 4;         // [4]
+    uint64_t* f32_full = xa_full + 8;
+    uint64_t* f32_empty = xa_full + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xa_full + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_slots = A.m.counters ? A.m.counters[CNT_NSLOTS] : A.m.B;
@@ -345,13 +357,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
     const int n_gemm = A.m.sigma_only ? P.n_trunk : P.n_gemm;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(xa_full, 1);
         mbar_init(xa_empty, 1);
-        mbar_init(acc_full, 1);
-        mbar_init(epi_done, 128);
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&hready[i], 8);
         mbar_init(f32_full, 1);
-        mbar_init(f32_empty, 128);
+        mbar_init(f32_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -377,15 +390,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
     if (warp == 0) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, xphase = 0, fphase = 0;
+            int stage = 0;
+            uint32_t phase = 0, xphase = 0, fphase = 0;
+            const uint32_t f32_bytes = (uint32_t)(((P.f32_floats * 4 + 15) / 16) * 16);
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int sub = sub_of(tile);
                 const unsigned char* wsub = A.wpack + (size_t)sub * P.sub_bytes;
                 const size_t f32_off = (size_t)P.plane_bytes * 2;   // both planes are always packed
                 // biases + sigma weights of this tile's sub-module
                 mbar_wait(f32_empty, fphase ^ 1);
-                mbar_expect_tx(f32_full, (uint32_t)(((P.f32_floats * 4 + 15) / 16) * 16));
-                bulk_g2s(F32, wsub + f32_off, (uint32_t)(((P.f32_floats * 4 + 15) / 16) * 16), f32_full);
+                mbar_expect_tx(f32_full, f32_bytes);
+                bulk_g2s(F32, wsub + f32_off, f32_bytes, f32_full);
                 fphase ^= 1;
                 for (int gi = 0; gi < n_gemm; ++gi) {
                     const TcGemm& g = P.g[gi];
@@ -422,27 +437,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, xphase = 0, n_epi_waits = 0;
-            bool first = true;
+            int stage = 0;
+            uint32_t phase = 0, xphase = 0, gidx = 0;
+            uint32_t hphase[4] = {0, 0, 0, 0};
             const uint32_t h_base = smem_u32(Hs), xa_base = smem_u32(XA), ring_base = smem_u32(ring);
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int gi = 0; gi < n_gemm; ++gi) {
+                for (int gi = 0; gi < n_gemm; ++gi, ++gidx) {
                     const TcGemm& g = P.g[gi];
                     const uint32_t idesc = make_idesc(g.n);
-                    if (!first) {
-                        // previous GEMM's accumulator drained and its activations written (and fenced)
-                        mbar_wait(epi_done, n_epi_waits & 1);
-                        ++n_epi_waits;
-                        tc_fence_after();
-                    }
-                    first = false;
+                    const uint32_t d_tmem = tmem_base + (gidx & 1u) * 256u;
                     uint32_t accum = 0;
                     for (int pass = 0; pass < npass; ++pass) {
                         for (int sgi = 0; sgi < g.nseg; ++sgi) {
                             const int kseg = g.k[sgi];
                             const bool from_x = g.src[sgi] != SRC_H;
                             // lo plane of H lives right after the hi plane in the H buffer (split mode)
-                            uint32_t a_base = from_x ? xa_base : h_base + (pass == 2 ? (uint32_t)(P.L * kTileM * 2) : 0u);
+                            const uint32_t a_base = from_x ? xa_base : h_base + (pass == 2 ? (uint32_t)(P.L * kTileM * 2) : 0u);
                             if (from_x) {
                                 mbar_wait(xa_full, xphase);
                                 xphase ^= 1;
@@ -450,21 +460,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                             }
                             for (int k0 = 0; k0 < kseg; k0 += kSlabCols) {
                                 const int kc = min(kSlabCols, kseg - k0);
+                                if (!from_x && pass == 0 && (k0 & 63) == 0) {
+                                    // the previous GEMM's epilogue has published this 64-column slab of H
+                                    const int hs = k0 >> 6;
+                                    mbar_wait(&hready[hs], hphase[hs]);
+                                    hphase[hs] ^= 1;
+                                    tc_fence_after();
+                                }
                                 mbar_wait(&full[stage], phase);
                                 tc_fence_after();
-                                const uint32_t b_base = ring_base + stage * kStageBytes;
+                                const uint32_t b_base = ring_base + (uint32_t)stage * kStageBytes;
                                 for (int kk = 0; kk < kc; kk += 16) {
                                     const uint32_t a_addr = a_base + (uint32_t)((k0 + kk) / 8) * (kTileM * 16);
                                     const uint32_t b_addr = b_base + (uint32_t)(kk / 8) * (uint32_t)(g.n * 16);
-                                    uint64_t ad, bd;
-                                    if (!A.desc_swap) {
-                                        ad = make_desc(a_addr, kTileM * 16, 128);
-                                        bd = make_desc(b_addr, (uint32_t)g.n * 16, 128);
-                                    } else {
-                                        ad = make_desc(a_addr, 128, kTileM * 16);
-                                        bd = make_desc(b_addr, 128, (uint32_t)g.n * 16);
-                                    }
-                                    tc_mma_f16(tmem_base, ad, bd, idesc, accum);
+                                    const uint64_t ad = make_desc(a_addr, kTileM * 16, 128);
+                                    const uint64_t bd = make_desc(b_addr, (uint32_t)g.n * 16, 128);
+                                    tc_mma_f16(d_tmem, ad, bd, idesc, accum);
                                     accum = 1;
                                 }
                                 tc_commit(&empty[stage]);   // frees the ring stage when these MMAs retire
@@ -473,16 +484,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                             if (from_x) tc_commit(xa_empty);
                         }
                     }
-                    tc_commit(acc_full);
+                    tc_commit(&acc_full[gidx & 1u]);
                 }
             }
         }
     } else {
-        // =========================== epilogue (4 warps, one TMEM lane quarter each) ===========================
-        const int q = warp & 3;
+        // =========================== epilogue (8 warps) ===========================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;            // which 32-column half of every 64-column slab
         const int r = q * 32 + lane;                 // row of the tile == TMEM lane
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t acc_phase = 0, fphase = 0;
+        uint32_t acc_phase[2] = {0, 0}, fphase = 0, gidx = 0;
         const int L = P.L;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t slot = tile * kTileM + r;
@@ -491,86 +503,107 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
             mbar_wait(f32_full, fphase);
             fphase ^= 1;
             float sigma = 0.0f;
-            for (int gi = 0; gi < n_gemm; ++gi) {
+            for (int gi = 0; gi < n_gemm; ++gi, ++gidx) {
                 const TcGemm& g = P.g[gi];
-                mbar_wait(acc_full, acc_phase);
-                acc_phase ^= 1;
+                const uint32_t ab = gidx & 1u;
+                mbar_wait(&acc_full[ab], acc_phase[ab]);
+                acc_phase[ab] ^= 1;
                 tc_fence_after();
+                const uint32_t t_acc = t_lane + ab * 256u;
                 const float* bias = F32 + g.bias_off;
                 if (g.epi == EPI_RGB) {
-                    uint32_t v[32];
-                    tmem_ld32(t_lane, v);
-                    tmem_ld_wait();
-                    if (row >= 0) {
-                        const NetDims& nd = A.m.nd;
-                        const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
-                        const float w = A.m.slot_w ? A.m.slot_w[slot] : 1.0f;
+                    if (half == 0) {
+                        uint32_t v[32];
+                        tmem_ld32(t_acc, v);
+                        tmem_ld_wait();
+                        if (row >= 0) {
+                            const NetDims& nd = A.m.nd;
+                            const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
+                            const float w = A.m.slot_w ? A.m.slot_w[slot] : 1.0f;
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            if (c < nd.rgb_dim) {
-                                float x = __uint_as_float(v[c]) + bias[c];
-                                if (nd.rgb_dim == 3) x = mn_sigmoid(x);
-                                A.m.out[o + c] = A.m.slot_w ? x * w : x;
+                            for (int c = 0; c < 32; ++c) {
+                                if (c < nd.rgb_dim) {
+                                    float x = __uint_as_float(v[c]) + bias[c];
+                                    if (nd.rgb_dim == 3) x = mn_sigmoid(x);
+                                    A.m.out[o + c] = A.m.slot_w ? x * w : x;
+                                }
                             }
+                            A.m.out[o + nd.rgb_dim] = A.m.slot_w ? sigma * w : sigma;
                         }
-                        A.m.out[o + nd.rgb_dim] = A.m.slot_w ? sigma * w : sigma;
                     }
+                    tc_fence_before();
                 } else {
                     const bool relu = g.epi != EPI_LINEAR;
                     const bool want_sigma = g.epi == EPI_RELU_SIGMA;
+                    const bool publish = !(want_sigma && A.m.sigma_only);   // nobody reads H after the last trunk layer
                     const float* sw = F32 + P.sigma_w_off;
                     float sacc = 0.0f;
-                    for (int c0 = 0; c0 < g.n; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(t_lane + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                        float f[32];
+                    const int nslab = (g.n + 63) >> 6;
+                    for (int j = 0; j < nslab; ++j) {
+                        const int c0 = 64 * j + 32 * half;
+                        if (c0 < g.n) {
+                            uint32_t v[32];
+                            tmem_ld32(t_acc + (uint32_t)c0, v);
+                            tmem_ld_wait();
+                            float f[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float x = __uint_as_float(v[j]) + bias[c0 + j];
-                            if (relu) x = fmaxf(x, 0.0f);
-                            f[j] = x;
-                        }
-                        if (want_sigma) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) sacc = fmaf(f[j], sw[c0 + j], sacc);
-                        }
-#pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) {
-                            uint32_t hi[4], lo[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float x0 = f[j8 * 8 + 2 * e], x1 = f[j8 * 8 + 2 * e + 1];
-                                const __half2 h2 = __floats2half2_rn(x0, x1);
-                                hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                                if (kSplit) {
-                                    const float2 back = __half22float2(h2);
-                                    const __half2 l2 = __floats2half2_rn(x0 - back.x, x1 - back.y);
-                                    lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
-                                }
+                            for (int i = 0; i < 32; ++i) {
+                                float x = __uint_as_float(v[i]) + bias[c0 + i];
+                                if (relu) x = fmaxf(x, 0.0f);
+                                f[i] = x;
                             }
-                            const int chunk = (c0 >> 3) + j8;
-                            unsigned char* dst = Hs + (size_t)chunk * (kTileM * 16) + (size_t)r * 16;
-                            *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            if (kSplit)
-                                *reinterpret_cast<uint4*>(dst + (size_t)L * kTileM * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            if (want_sigma) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) sacc = fmaf(f[i], sw[c0 + i], sacc);
+                            }
+                            if (publish) {
+#pragma unroll
+                                for (int j8 = 0; j8 < 4; ++j8) {
+                                    uint32_t hi[4], lo[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float x0 = f[j8 * 8 + 2 * e], x1 = f[j8 * 8 + 2 * e + 1];
+                                        const __half2 h2 = __floats2half2_rn(x0, x1);
+                                        hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                                        if (kSplit) {
+                                            const float2 back = __half22float2(h2);
+                                            const __half2 l2 = __floats2half2_rn(x0 - back.x, x1 - back.y);
+                                            lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                                        }
+                                    }
+                                    const int chunk = (c0 >> 3) + j8;
+                                    unsigned char* dst = Hs + (size_t)chunk * (kTileM * 16) + (size_t)r * 16;
+                                    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                    if (kSplit)
+                                        *reinterpret_cast<uint4*>(dst + (size_t)L * kTileM * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                }
+                                fence_proxy_async();   // generic-proxy stores to H -> visible to the tensor core (async proxy)
+                            }
+                        }
+                        if (publish) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&hready[j]);
                         }
                     }
                     if (want_sigma) {
-                        float s = sacc + sw[L];   // sigma bias stored right after sigma_w
-                        if (A.m.sigma_noise && row >= 0) s = s + A.m.sigma_noise[row];
-                        sigma = A.m.nd.softplus ? mn_softplus_shifted(s) : fmaxf(s, 0.0f);
-                        if (A.m.sigma_only && row >= 0) {
-                            const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
-                            A.m.out[o] = A.m.slot_w ? sigma * A.m.slot_w[slot] : sigma;
+                        SIGP[half * kTileM + r] = sacc;
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (half == 0) {
+                            float s = (SIGP[r] + SIGP[kTileM + r]) + sw[L];   // sigma bias stored right after sigma_w
+                            if (A.m.sigma_noise && row >= 0) s = s + A.m.sigma_noise[row];
+                            sigma = A.m.nd.softplus ? mn_softplus_shifted(s) : fmaxf(s, 0.0f);
+                            if (A.m.sigma_only && row >= 0) {
+                                const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
+                                A.m.out[o] = A.m.slot_w ? sigma * A.m.slot_w[slot] : sigma;
+                            }
                         }
+                        tc_fence_before();
                     }
-                    fence_proxy_async();   // generic-proxy stores to H -> visible to the tensor core (async proxy)
                 }
-                tc_fence_before();
-                mbar_arrive(epi_done);
             }
-            mbar_arrive(f32_empty);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(f32_empty);
         }
     }
     tc_fence_before();
@@ -675,7 +708,7 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
 
     const SmemLayout SL = smem_layout(P, split != 0);
     const int total = SL.total;
-    if (total > 227 * 1024) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core MLP: shared-memory budget exceeded");
+    if (total > kSmemMax || SL.stages < 2) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core MLP: shared-memory budget exceeded");
     const unsigned grid = (unsigned)(n_tiles128 < ctx->sm_count ? n_tiles128 : ctx->sm_count);
     if (split) {
         MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
