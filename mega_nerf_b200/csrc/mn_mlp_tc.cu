@@ -28,7 +28,8 @@ constexpr int kMaxStages = 4;
 __host__ __device__ constexpr int ring_slab_cols(bool split) { return split ? 32 : 64; }
 __host__ __device__ constexpr int ring_stage_bytes(bool split) { return ring_slab_cols(split) * 256 * 2; }
 constexpr int kMaxGemm = 16;
-constexpr int kThreads = 320;   // producer warp, MMA warp, 8 epilogue warps
+constexpr int kThreads = 576;   // producer warp, MMA warp, 16 epilogue warps
+constexpr int kEpiWarps = 16;
 
 enum { SRC_H = 0, SRC_XPE = 1, SRC_XAUX = 2 };
 enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
@@ -176,6 +177,77 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// One 16-column piece of the epilogue for one accumulator row: TMEM -> +bias -> (ReLU) -> fp16 (hi [, lo]) ->
+// two 16-byte stores into the next layer's A operand.  Returns the partial sigma dot product if kSigma.
+template <bool kSplit, bool kRelu, bool kSigma>
+__device__ __forceinline__ float epi_piece16(uint32_t taddr, const float* __restrict__ bias16, const float* __restrict__ sw16,
+                                             unsigned char* dst, size_t lo_off, bool store) {
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+    const float4* b4 = reinterpret_cast<const float4*>(bias16);
+    const float4 b0 = b4[0], b1 = b4[1], b2 = b4[2], b3 = b4[3];
+    const float b[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+    tmem_ld_wait();
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + b[i];
+    float sacc = 0.0f;
+    if (kSigma || kSplit) {
+        if (kRelu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+        }
+    }
+    if (kSigma) {
+        const float4* s4 = reinterpret_cast<const float4*>(sw16);
+        const float4 s0 = s4[0], s1 = s4[1], s2 = s4[2], s3 = s4[3];
+        const float sw[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sacc = fmaf(f[i], sw[i], sacc);
+    }
+    if (store) {
+        uint32_t hi[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hi[e] = pack_h2(f[2 * e], f[2 * e + 1]);
+        if (kRelu && !(kSigma || kSplit)) {
+            // ReLU after the fp16 rounding (max(round(x),0) == round(max(x,0))): one HMNMX2 per pair
+            const __half2 z = __float2half2_rn(0.0f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                __half2 h = __hmax2(*reinterpret_cast<__half2*>(&hi[e]), z);
+                hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+        }
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + kTileM * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        if (kSplit) {
+            uint32_t lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
+                lo[e] = pack_h2(f[2 * e] - back.x, f[2 * e + 1] - back.y);
+            }
+            *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(dst + lo_off + kTileM * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+    }
+    return sacc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight packing: nn.Linear weight [N_src][K_src] fp32 -> image [K/8][N][8] fp16 (hi) and the residual (lo)
 // ------------------------------------------------------------------------------------------------
@@ -308,7 +380,7 @@ constexpr int kSmemMax = 227 * 1024;
 __host__ __device__ inline SmemLayout smem_layout(const TcPlan& p, bool split) {
     SmemLayout s;
     const int kx = p.kpe > p.kaux ? p.kpe : p.kaux;
-    const int fixed = p.L * kTileM * 2 * (split ? 2 : 1) + kx * kTileM * 2 + ((p.f32_floats * 4 + 15) / 16) * 16 + 1024 + 256;
+    const int fixed = p.L * kTileM * 2 * (split ? 2 : 1) + kx * kTileM * 2 + ((p.f32_floats * 4 + 15) / 16) * 16 + 2048 + 256;
     int st = (kSmemMax - fixed) / ring_stage_bytes(split);
     if (st > kMaxStages) st = kMaxStages;
     s.stages = st;
@@ -317,7 +389,7 @@ __host__ __device__ inline SmemLayout smem_layout(const TcPlan& p, bool split) {
     s.xa = s.h + p.L * kTileM * 2 * (split ? 2 : 1);   // split: hi plane then lo plane
     s.f32 = s.xa + kx * kTileM * 2;
     s.sigp = s.f32 + ((p.f32_floats * 4 + 15) / 16) * 16;
-    s.bars = s.sigp + 1024;
+    s.bars = s.sigp + 2048;
     s.total = s.bars + 256;
     return s;
 }
@@ -339,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
     unsigned char* Hs = smem + SL.h;
     unsigned char* XA = smem + SL.xa;
     float* F32 = reinterpret_cast<float*>(smem + SL.f32);
-    float* SIGP = reinterpret_cast<float*>(smem + SL.sigp);   // [2][128] partial sigma dot products
+    float* SIGP = reinterpret_cast<float*>(smem + SL.sigp);   // [4][128] partial sigma dot products
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bars);
     uint64_t* full = bars;                  // [kMaxStages]
     uint64_t* empty = bars + kMaxStages;    // [kMaxStages]
@@ -362,9 +434,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
         mbar_init(xa_empty, 1);
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
-        for (int i = 0; i < 4; ++i) mbar_init(&hready[i], 8);
+        for (int i = 0; i < 4; ++i) mbar_init(&hready[i], kEpiWarps);
         mbar_init(f32_full, 1);
-        mbar_init(f32_empty, 8);
+        mbar_init(f32_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -489,13 +561,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
             }
         }
     } else {
-        // =========================== epilogue (8 warps) ===========================
+        // =========================== epilogue (16 warps) ===========================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;            // which 32-column half of every 64-column slab
+        const int part = (warp - 2) >> 2;            // which 16-column piece of every 64-column slab
         const int r = q * 32 + lane;                 // row of the tile == TMEM lane
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t acc_phase[2] = {0, 0}, fphase = 0, gidx = 0;
+        uint32_t acc_phase0 = 0, acc_phase1 = 0, fphase = 0, gidx = 0;
         const int L = P.L;
+        const size_t lo_off = (size_t)L * kTileM * 2;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t slot = tile * kTileM + r;
             int64_t row = -1;
@@ -506,13 +579,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
             for (int gi = 0; gi < n_gemm; ++gi, ++gidx) {
                 const TcGemm& g = P.g[gi];
                 const uint32_t ab = gidx & 1u;
-                mbar_wait(&acc_full[ab], acc_phase[ab]);
-                acc_phase[ab] ^= 1;
+                if (ab) { mbar_wait(&acc_full[1], acc_phase1); acc_phase1 ^= 1; }
+                else    { mbar_wait(&acc_full[0], acc_phase0); acc_phase0 ^= 1; }
                 tc_fence_after();
                 const uint32_t t_acc = t_lane + ab * 256u;
                 const float* bias = F32 + g.bias_off;
                 if (g.epi == EPI_RGB) {
-                    if (half == 0) {
+                    if (part == 0) {
                         uint32_t v[32];
                         tmem_ld32(t_acc, v);
                         tmem_ld_wait();
@@ -533,52 +606,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                     }
                     tc_fence_before();
                 } else {
-                    const bool relu = g.epi != EPI_LINEAR;
                     const bool want_sigma = g.epi == EPI_RELU_SIGMA;
                     const bool publish = !(want_sigma && A.m.sigma_only);   // nobody reads H after the last trunk layer
                     const float* sw = F32 + P.sigma_w_off;
                     float sacc = 0.0f;
                     const int nslab = (g.n + 63) >> 6;
                     for (int j = 0; j < nslab; ++j) {
-                        const int c0 = 64 * j + 32 * half;
+                        const int c0 = 64 * j + 16 * part;
                         if (c0 < g.n) {
-                            uint32_t v[32];
-                            tmem_ld32(t_acc + (uint32_t)c0, v);
-                            tmem_ld_wait();
-                            float f[32];
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                float x = __uint_as_float(v[i]) + bias[c0 + i];
-                                if (relu) x = fmaxf(x, 0.0f);
-                                f[i] = x;
-                            }
-                            if (want_sigma) {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) sacc = fmaf(f[i], sw[c0 + i], sacc);
-                            }
-                            if (publish) {
-#pragma unroll
-                                for (int j8 = 0; j8 < 4; ++j8) {
-                                    uint32_t hi[4], lo[4];
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const float x0 = f[j8 * 8 + 2 * e], x1 = f[j8 * 8 + 2 * e + 1];
-                                        const __half2 h2 = __floats2half2_rn(x0, x1);
-                                        hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                                        if (kSplit) {
-                                            const float2 back = __half22float2(h2);
-                                            const __half2 l2 = __floats2half2_rn(x0 - back.x, x1 - back.y);
-                                            lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
-                                        }
-                                    }
-                                    const int chunk = (c0 >> 3) + j8;
-                                    unsigned char* dst = Hs + (size_t)chunk * (kTileM * 16) + (size_t)r * 16;
-                                    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                                    if (kSplit)
-                                        *reinterpret_cast<uint4*>(dst + (size_t)L * kTileM * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                                }
-                                fence_proxy_async();   // generic-proxy stores to H -> visible to the tensor core (async proxy)
-                            }
+                            unsigned char* dst = Hs + (size_t)(c0 >> 3) * (kTileM * 16) + (size_t)r * 16;
+                            if (g.epi == EPI_RELU)
+                                epi_piece16<kSplit, true, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, lo_off, true);
+                            else if (g.epi == EPI_LINEAR)
+                                epi_piece16<kSplit, false, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, lo_off, true);
+                            else
+                                sacc += epi_piece16<kSplit, true, true>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, lo_off, publish);
+                            if (publish) fence_proxy_async();   // generic-proxy stores to H -> visible to the tensor core
                         }
                         if (publish) {
                             tc_fence_before();
@@ -587,10 +630,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                         }
                     }
                     if (want_sigma) {
-                        SIGP[half * kTileM + r] = sacc;
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
-                        if (half == 0) {
-                            float s = (SIGP[r] + SIGP[kTileM + r]) + sw[L];   // sigma bias stored right after sigma_w
+                        SIGP[part * kTileM + r] = sacc;
+                        asm volatile("bar.sync 1, 512;" ::: "memory");
+                        if (part == 0) {
+                            // sigma bias is stored right after sigma_w
+                            float s = ((SIGP[r] + SIGP[kTileM + r]) + (SIGP[2 * kTileM + r] + SIGP[3 * kTileM + r])) + sw[L];
                             if (A.m.sigma_noise && row >= 0) s = s + A.m.sigma_noise[row];
                             sigma = A.m.nd.softplus ? mn_softplus_shifted(s) : fmaxf(s, 0.0f);
                             if (A.m.sigma_only && row >= 0) {
