@@ -177,6 +177,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -508,16 +518,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // The whole warp runs the loop (so addresses/descriptors stay in uniform registers); one elected lane
+        // issues tcgen05.mma / tcgen05.commit.
+        {
             int stage = 0;
             uint32_t phase = 0, xphase = 0, gidx = 0;
-            uint32_t hphase[4] = {0, 0, 0, 0};
+            uint32_t hph0 = 0, hph1 = 0, hph2 = 0, hph3 = 0;
             const uint32_t h_base = smem_u32(Hs), xa_base = smem_u32(XA), ring_base = smem_u32(ring);
+            const uint64_t a_step = (uint64_t)((2 * kTileM * 16) >> 4);           // +16 K-columns of A (descriptor address field)
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int gi = 0; gi < n_gemm; ++gi, ++gidx) {
                     const TcGemm& g = P.g[gi];
                     const uint32_t idesc = make_idesc(g.n);
                     const uint32_t d_tmem = tmem_base + (gidx & 1u) * 256u;
+                    const uint64_t b_step = (uint64_t)((2 * g.n * 16) >> 4);      // +16 K-columns of B
                     uint32_t accum = 0;
                     for (int pass = 0; pass < npass; ++pass) {
                         for (int sgi = 0; sgi < g.nseg; ++sgi) {
@@ -528,35 +542,41 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                             if (from_x) {
                                 mbar_wait(xa_full, xphase);
                                 xphase ^= 1;
-                                tc_fence_after();
                             }
                             for (int k0 = 0; k0 < kseg; k0 += kSlabCols) {
                                 const int kc = min(kSlabCols, kseg - k0);
                                 if (!from_x && pass == 0 && (k0 & 63) == 0) {
                                     // the previous GEMM's epilogue has published this 64-column slab of H
                                     const int hs = k0 >> 6;
-                                    mbar_wait(&hready[hs], hphase[hs]);
-                                    hphase[hs] ^= 1;
-                                    tc_fence_after();
+                                    if (hs == 0) { mbar_wait(&hready[0], hph0); hph0 ^= 1; }
+                                    else if (hs == 1) { mbar_wait(&hready[1], hph1); hph1 ^= 1; }
+                                    else if (hs == 2) { mbar_wait(&hready[2], hph2); hph2 ^= 1; }
+                                    else { mbar_wait(&hready[3], hph3); hph3 ^= 1; }
                                 }
                                 mbar_wait(&full[stage], phase);
                                 tc_fence_after();
-                                const uint32_t b_base = ring_base + (uint32_t)stage * kStageBytes;
-                                for (int kk = 0; kk < kc; kk += 16) {
-                                    const uint32_t a_addr = a_base + (uint32_t)((k0 + kk) / 8) * (kTileM * 16);
-                                    const uint32_t b_addr = b_base + (uint32_t)(kk / 8) * (uint32_t)(g.n * 16);
-                                    const uint64_t ad = make_desc(a_addr, kTileM * 16, 128);
-                                    const uint64_t bd = make_desc(b_addr, (uint32_t)g.n * 16, 128);
-                                    tc_mma_f16(d_tmem, ad, bd, idesc, accum);
-                                    accum = 1;
+                                uint64_t ad = make_desc(a_base + (uint32_t)(k0 / 8) * (kTileM * 16), kTileM * 16, 128);
+                                uint64_t bd = make_desc(ring_base + (uint32_t)stage * kStageBytes, (uint32_t)g.n * 16, 128);
+                                const int nk = kc >> 4;
+                                if (elect_one()) {
+                                    for (int i = 0; i < nk; ++i) {
+                                        tc_mma_f16(d_tmem, ad, bd, idesc, accum);
+                                        accum = 1;
+                                        ad += a_step;
+                                        bd += b_step;
+                                    }
+                                    tc_commit(&empty[stage]);   // frees the ring stage when these MMAs retire
                                 }
-                                tc_commit(&empty[stage]);   // frees the ring stage when these MMAs retire
+                                accum = 1;
+                                __syncwarp();
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
-                            if (from_x) tc_commit(xa_empty);
+                            if (from_x && elect_one()) tc_commit(xa_empty);
+                            __syncwarp();
                         }
                     }
-                    tc_commit(&acc_full[gidx & 1u]);
+                    if (elect_one()) tc_commit(&acc_full[gidx & 1u]);
+                    __syncwarp();
                 }
             }
         }
