@@ -677,6 +677,305 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Ping-pong variant (single-pass fp16): two 128-row tiles per CTA, each with its own activation buffer
+// and TMEM accumulator.  GEMMs are issued X_l, Y_l, X_l+1, Y_l+1, ...: the epilogue of X_l (16 warps)
+// runs entirely under the MMAs of Y_l and vice versa, so the tensor pipe only idles at pipeline fill.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPPStages = 3;
+constexpr int kPPSlabCols = 32;
+constexpr int kPPStageBytes = kPPSlabCols * 256 * 2;
+
+struct PPLayout {
+    int ring, h, xa, f32, f32_stride, sigp, bars, total;
+};
+
+__host__ __device__ inline PPLayout pp_layout(const TcPlan& p) {
+    PPLayout s;
+    const int kx = p.kpe > p.kaux ? p.kpe : p.kaux;
+    s.ring = 0;
+    s.h = kPPStages * kPPStageBytes;
+    s.xa = s.h + 2 * p.L * kTileM * 2;
+    s.f32 = s.xa + kx * kTileM * 2;
+    s.f32_stride = ((p.f32_floats * 4 + 15) / 16) * 16;
+    s.sigp = s.f32 + 2 * s.f32_stride;
+    s.bars = s.sigp + 2048;
+    s.total = s.bars + 256;
+    return s;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TcPlan& P = A.plan;
+    const PPLayout SL = pp_layout(P);
+    unsigned char* ring = smem + SL.ring;
+    unsigned char* Hs = smem + SL.h;
+    unsigned char* XA = smem + SL.xa;
+    float* F32 = reinterpret_cast<float*>(smem + SL.f32);
+    float* SIGP = reinterpret_cast<float*>(smem + SL.sigp);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bars);
+    uint64_t* full = bars;            // [3]
+    uint64_t* empty = bars + 4;       // [3]
+    uint64_t* xa_full = bars + 8;
+    uint64_t* xa_empty = bars + 9;
+    uint64_t* acc_full = bars + 10;   // [2] per tile slot
+    uint64_t* epi_done = bars + 12;   // [2]
+    uint64_t* f32_full = bars + 14;   // [2]
+    uint64_t* f32_empty = bars + 16;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_slots = A.m.counters ? A.m.counters[CNT_NSLOTS] : A.m.B;
+    const int64_t n_tiles = (n_slots + kTileM - 1) / kTileM;
+    const int n_gemm = A.m.sigma_only ? P.n_trunk : P.n_gemm;
+    const int h_bytes = P.L * kTileM * 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kPPStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(xa_full, 1);
+        mbar_init(xa_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&epi_done[i], kEpiWarps);
+            mbar_init(&f32_full[i], 1);
+            mbar_init(&f32_empty[i], kEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto sub_of = [&](int64_t tile) -> int {
+        int sub = A.m.fixed_sub;
+        if (A.m.counters) {
+            sub = 0;
+            const int64_t s0 = tile * kTileM;
+            while (sub + 1 < A.m.n_sub && s0 >= A.m.counters[CNT_START + sub + 1]) ++sub;
+        }
+        return sub;
+    };
+    const int64_t stride2 = 2 * (int64_t)gridDim.x;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, xphase = 0, fph[2] = {0, 0};
+            const uint32_t f32_bytes = (uint32_t)SL.f32_stride;
+            for (int64_t t0 = blockIdx.x; t0 < n_tiles; t0 += stride2) {
+                const int64_t tiles[2] = {t0, t0 + gridDim.x};
+                const unsigned char* wsub[2] = {nullptr, nullptr};
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (tiles[sl] >= n_tiles) continue;
+                    wsub[sl] = A.wpack + (size_t)sub_of(tiles[sl]) * P.sub_bytes;
+                    mbar_wait(&f32_empty[sl], fph[sl] ^ 1);
+                    mbar_expect_tx(&f32_full[sl], f32_bytes);
+                    bulk_g2s(reinterpret_cast<unsigned char*>(F32) + (size_t)sl * SL.f32_stride,
+                             wsub[sl] + (size_t)P.plane_bytes * 2, f32_bytes, &f32_full[sl]);
+                    fph[sl] ^= 1;
+                }
+                for (int gi = 0; gi < n_gemm; ++gi) {
+                    const TcGemm& g = P.g[gi];
+                    for (int sl = 0; sl < 2; ++sl) {
+                        if (!wsub[sl]) continue;
+                        const unsigned char* wimg = wsub[sl] + g.w_off;
+                        int kbase = 0;
+                        for (int sgi = 0; sgi < g.nseg; ++sgi) {
+                            const int kseg = g.k[sgi];
+                            if (g.src[sgi] != SRC_H) {
+                                const __half* xt = A.ximg + tiles[sl] * (int64_t)(P.kpe + P.kaux) * kTileM +
+                                                   (g.src[sgi] == SRC_XAUX ? (int64_t)P.kpe * kTileM : 0);
+                                mbar_wait(xa_empty, xphase ^ 1);
+                                mbar_expect_tx(xa_full, (uint32_t)(kseg * kTileM * 2));
+                                bulk_g2s(XA, xt, (uint32_t)(kseg * kTileM * 2), xa_full);
+                                xphase ^= 1;
+                            }
+                            for (int k0 = 0; k0 < kseg; k0 += kPPSlabCols) {
+                                const int kc = min(kPPSlabCols, kseg - k0);
+                                const uint32_t bytes = (uint32_t)(kc * g.n * 2);
+                                mbar_wait(&empty[stage], phase ^ 1);
+                                mbar_expect_tx(&full[stage], bytes);
+                                bulk_g2s(ring + (size_t)stage * kPPStageBytes, wimg + (size_t)(kbase + k0) * g.n * 2, bytes,
+                                         &full[stage]);
+                                if (++stage == kPPStages) { stage = 0; phase ^= 1; }
+                            }
+                            kbase += kseg;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
+        int stage = 0;
+        uint32_t phase = 0, xphase = 0, eph0 = 0, eph1 = 0;
+        bool started0 = false, started1 = false;
+        const uint32_t h_base = smem_u32(Hs), xa_base = smem_u32(XA), ring_base = smem_u32(ring);
+        const uint64_t a_step = (uint64_t)((2 * kTileM * 16) >> 4);
+        for (int64_t t0 = blockIdx.x; t0 < n_tiles; t0 += stride2) {
+            const bool valid1 = t0 + gridDim.x < n_tiles;
+            for (int gi = 0; gi < n_gemm; ++gi) {
+                const TcGemm& g = P.g[gi];
+                const uint32_t idesc = make_idesc(g.n);
+                const uint64_t b_step = (uint64_t)((2 * g.n * 16) >> 4);
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (sl == 1 && !valid1) continue;
+                    // the previous GEMM of this tile slot has been drained from TMEM and its activations are in H[sl]
+                    if (sl == 0) { if (started0) { mbar_wait(&epi_done[0], eph0); eph0 ^= 1; } started0 = true; }
+                    else         { if (started1) { mbar_wait(&epi_done[1], eph1); eph1 ^= 1; } started1 = true; }
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)sl * 256u;
+                    uint32_t accum = 0;
+                    for (int sgi = 0; sgi < g.nseg; ++sgi) {
+                        const int kseg = g.k[sgi];
+                        const bool from_x = g.src[sgi] != SRC_H;
+                        const uint32_t a_base = from_x ? xa_base : h_base + (uint32_t)(sl * h_bytes);
+                        if (from_x) {
+                            mbar_wait(xa_full, xphase);
+                            xphase ^= 1;
+                        }
+                        for (int k0 = 0; k0 < kseg; k0 += kPPSlabCols) {
+                            const int kc = min(kPPSlabCols, kseg - k0);
+                            mbar_wait(&full[stage], phase);
+                            tc_fence_after();
+                            uint64_t ad = make_desc(a_base + (uint32_t)(k0 / 8) * (kTileM * 16), kTileM * 16, 128);
+                            uint64_t bd = make_desc(ring_base + (uint32_t)stage * kPPStageBytes, (uint32_t)g.n * 16, 128);
+                            const int nk = kc >> 4;
+                            if (elect_one()) {
+                                for (int i = 0; i < nk; ++i) {
+                                    tc_mma_f16(d_tmem, ad, bd, idesc, accum);
+                                    accum = 1;
+                                    ad += a_step;
+                                    bd += b_step;
+                                }
+                                tc_commit(&empty[stage]);
+                            }
+                            accum = 1;
+                            __syncwarp();
+                            if (++stage == kPPStages) { stage = 0; phase ^= 1; }
+                        }
+                        if (from_x && elect_one()) tc_commit(xa_empty);
+                        __syncwarp();
+                    }
+                    if (elect_one()) tc_commit(&acc_full[sl]);
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // =========================== epilogue (16 warps) ===========================
+        const int q = warp & 3;
+        const int part = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t aph0 = 0, aph1 = 0, fph0 = 0, fph1 = 0;
+        const int L = P.L;
+        for (int64_t t0 = blockIdx.x; t0 < n_tiles; t0 += stride2) {
+            const bool valid1 = t0 + gridDim.x < n_tiles;
+            int64_t slot_[2], row_[2] = {-1, -1};
+            float sigma_[2] = {0.0f, 0.0f};
+            for (int sl = 0; sl < 2; ++sl) {
+                if (sl == 1 && !valid1) continue;
+                slot_[sl] = (t0 + (int64_t)sl * gridDim.x) * kTileM + r;
+                if (slot_[sl] < n_slots) row_[sl] = A.m.slot_row ? (int64_t)A.m.slot_row[slot_[sl]] : slot_[sl];
+                if (sl == 0) { mbar_wait(&f32_full[0], fph0); fph0 ^= 1; }
+                else         { mbar_wait(&f32_full[1], fph1); fph1 ^= 1; }
+            }
+            for (int gi = 0; gi < n_gemm; ++gi) {
+                const TcGemm& g = P.g[gi];
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (sl == 1 && !valid1) continue;
+                    if (sl == 0) { mbar_wait(&acc_full[0], aph0); aph0 ^= 1; }
+                    else         { mbar_wait(&acc_full[1], aph1); aph1 ^= 1; }
+                    tc_fence_after();
+                    const uint32_t t_acc = t_lane + (uint32_t)sl * 256u;
+                    const float* Fb = F32 + (size_t)sl * (SL.f32_stride / 4);
+                    const float* bias = Fb + g.bias_off;
+                    const int64_t row = row_[sl], slot = slot_[sl];
+                    if (g.epi == EPI_RGB) {
+                        if (part == 0) {
+                            uint32_t v[32];
+                            tmem_ld32(t_acc, v);
+                            tmem_ld_wait();
+                            if (row >= 0) {
+                                const NetDims& nd = A.m.nd;
+                                const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
+                                const float w = A.m.slot_w ? A.m.slot_w[slot] : 1.0f;
+                                const float sigma = sigma_[sl];
+#pragma unroll
+                                for (int c = 0; c < 32; ++c) {
+                                    if (c < nd.rgb_dim) {
+                                        float x = __uint_as_float(v[c]) + bias[c];
+                                        if (nd.rgb_dim == 3) x = mn_sigmoid(x);
+                                        A.m.out[o + c] = A.m.slot_w ? x * w : x;
+                                    }
+                                }
+                                A.m.out[o + nd.rgb_dim] = A.m.slot_w ? sigma * w : sigma;
+                            }
+                        }
+                    } else {
+                        const bool want_sigma = g.epi == EPI_RELU_SIGMA;
+                        const bool publish = !(want_sigma && A.m.sigma_only);
+                        const float* sw = Fb + P.sigma_w_off;
+                        unsigned char* Hsl = Hs + (size_t)sl * h_bytes;
+                        float sacc = 0.0f;
+                        const int nslab = (g.n + 63) >> 6;
+                        for (int j = 0; j < nslab; ++j) {
+                            const int c0 = 64 * j + 16 * part;
+                            if (c0 < g.n) {
+                                unsigned char* dst = Hsl + (size_t)(c0 >> 3) * (kTileM * 16) + (size_t)r * 16;
+                                if (g.epi == EPI_RELU)
+                                    epi_piece16<false, true, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
+                                else if (g.epi == EPI_LINEAR)
+                                    epi_piece16<false, false, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
+                                else
+                                    sacc += epi_piece16<false, true, true>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, publish);
+                            }
+                        }
+                        if (publish) fence_proxy_async();
+                        if (want_sigma) {
+                            SIGP[part * kTileM + r] = sacc;
+                            asm volatile("bar.sync 1, 512;" ::: "memory");
+                            if (part == 0) {
+                                float s = ((SIGP[r] + SIGP[kTileM + r]) + (SIGP[2 * kTileM + r] + SIGP[3 * kTileM + r])) + sw[L];
+                                if (A.m.sigma_noise && row >= 0) s = s + A.m.sigma_noise[row];
+                                const float sg = A.m.nd.softplus ? mn_softplus_shifted(s) : fmaxf(s, 0.0f);
+                                sigma_[sl] = sg;
+                                if (A.m.sigma_only && row >= 0) {
+                                    const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
+                                    A.m.out[o] = A.m.slot_w ? sg * A.m.slot_w[slot] : sg;
+                                }
+                            }
+                            asm volatile("bar.sync 1, 512;" ::: "memory");   // SIGP is reused by the other tile slot
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&epi_done[sl]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&f32_empty[0]);
+                if (valid1) mbar_arrive(&f32_empty[1]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -779,9 +1078,22 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         mn_prof_begin(ctx, st);
         tc_mlp_kernel<true><<<grid, kThreads, total, st>>>(A);
     } else {
-        MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
-        mn_prof_begin(ctx, st);
-        tc_mlp_kernel<false><<<grid, kThreads, total, st>>>(A);
+        static int use_pp = -1;
+        if (use_pp < 0) {
+            const char* e = getenv("MN_TC_PINGPONG");
+            use_pp = (e && e[0] == '0') ? 0 : 1;
+        }
+        const PPLayout PL = pp_layout(P);
+        if (use_pp && PL.total <= kSmemMax) {
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
+            const unsigned grid_pp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
+            mn_prof_begin(ctx, st);
+            tc_mlp_pp_kernel<<<grid_pp, kThreads, PL.total, st>>>(A);
+        } else {
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
+            mn_prof_begin(ctx, st);
+            tc_mlp_kernel<false><<<grid, kThreads, total, st>>>(A);
+        }
     }
     mn_prof_end(ctx, st);
     MN_LAUNCH_CHECK(ctx);
