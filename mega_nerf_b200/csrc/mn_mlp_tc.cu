@@ -678,6 +678,53 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
 }
 
 
+
+// ---- lean primitives for the MMA-issuing warp (raw shared-memory addresses, no per-slab descriptor rebuild) ----
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+    if (ok) return;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) {
+            printf("mn_mlp_tc: mbarrier timeout (mma) block %d\n", (int)blockIdx.x);
+            __trap();
+        }
+    }
+}
+// one ring stage worth of MMAs (one or two K=16 steps) + the commit that releases the stage, issued by one
+// elected lane; everything is predicated, no branches.
+__device__ __forceinline__ void mma_stage(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint64_t ad2, uint64_t bd2, uint32_t idesc,
+                                          uint32_t accum, uint32_t two, uint32_t empty_bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, q;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.and.b32 q, %7, 0, e;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %5, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %4, %5, 1;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}"
+        ::"r"(d_tmem), "l"(ad), "l"(bd), "l"(ad2), "l"(bd2), "r"(idesc), "r"(accum), "r"(two), "r"(empty_bar_addr)
+        : "memory");
+}
+__device__ __forceinline__ void commit_elect(uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar_addr) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // Ping-pong variant (single-pass fp16): two 128-row tiles per CTA, each with its own activation buffer
 // and TMEM accumulator.  GEMMs are issued X_l, Y_l, X_l+1, Y_l+1, ...: the epilogue of X_l (16 warps)
@@ -818,54 +865,48 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
         uint32_t phase = 0, xphase = 0, eph0 = 0, eph1 = 0;
         bool started0 = false, started1 = false;
         const uint32_t h_base = smem_u32(Hs), xa_base = smem_u32(XA), ring_base = smem_u32(ring);
+        const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+        const uint32_t xa_full_a = smem_u32(xa_full), xa_empty_a = smem_u32(xa_empty);
+        const uint32_t acc_full_a = smem_u32(acc_full), epi_done_a = smem_u32(epi_done);
         const uint64_t a_step = (uint64_t)((2 * kTileM * 16) >> 4);
+        const uint64_t st_step = (uint64_t)(kPPStageBytes >> 4);
         for (int64_t t0 = blockIdx.x; t0 < n_tiles; t0 += stride2) {
             const bool valid1 = t0 + gridDim.x < n_tiles;
             for (int gi = 0; gi < n_gemm; ++gi) {
                 const TcGemm& g = P.g[gi];
                 const uint32_t idesc = make_idesc(g.n);
                 const uint64_t b_step = (uint64_t)((2 * g.n * 16) >> 4);
+                const uint64_t bd0 = make_desc(ring_base, (uint32_t)g.n * 16, 128);
                 for (int sl = 0; sl < 2; ++sl) {
                     if (sl == 1 && !valid1) continue;
                     // the previous GEMM of this tile slot has been drained from TMEM and its activations are in H[sl]
-                    if (sl == 0) { if (started0) { mbar_wait(&epi_done[0], eph0); eph0 ^= 1; } started0 = true; }
-                    else         { if (started1) { mbar_wait(&epi_done[1], eph1); eph1 ^= 1; } started1 = true; }
+                    if (sl == 0) { if (started0) { mbar_wait_a(epi_done_a, eph0); eph0 ^= 1; } started0 = true; }
+                    else         { if (started1) { mbar_wait_a(epi_done_a + 8, eph1); eph1 ^= 1; } started1 = true; }
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)sl * 256u;
                     uint32_t accum = 0;
                     for (int sgi = 0; sgi < g.nseg; ++sgi) {
-                        const int kseg = g.k[sgi];
+                        int rem = g.k[sgi];
                         const bool from_x = g.src[sgi] != SRC_H;
-                        const uint32_t a_base = from_x ? xa_base : h_base + (uint32_t)(sl * h_bytes);
+                        uint64_t ad = make_desc(from_x ? xa_base : h_base + (uint32_t)(sl * h_bytes), kTileM * 16, 128);
                         if (from_x) {
-                            mbar_wait(xa_full, xphase);
+                            mbar_wait_a(xa_full_a, xphase);
                             xphase ^= 1;
                         }
-                        for (int k0 = 0; k0 < kseg; k0 += kPPSlabCols) {
-                            const int kc = min(kPPSlabCols, kseg - k0);
-                            mbar_wait(&full[stage], phase);
+                        while (rem > 0) {
+                            const uint32_t two = rem >= 32 ? 1u : 0u;
+                            const uint64_t bd = bd0 + (uint64_t)stage * st_step;
+                            mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
                             tc_fence_after();
-                            uint64_t ad = make_desc(a_base + (uint32_t)(k0 / 8) * (kTileM * 16), kTileM * 16, 128);
-                            uint64_t bd = make_desc(ring_base + (uint32_t)stage * kPPStageBytes, (uint32_t)g.n * 16, 128);
-                            const int nk = kc >> 4;
-                            if (elect_one()) {
-                                for (int i = 0; i < nk; ++i) {
-                                    tc_mma_f16(d_tmem, ad, bd, idesc, accum);
-                                    accum = 1;
-                                    ad += a_step;
-                                    bd += b_step;
-                                }
-                                tc_commit(&empty[stage]);
-                            }
+                            mma_stage(d_tmem, ad, bd, ad + a_step, bd + b_step, idesc, accum, two, empty_a + 8u * (uint32_t)stage);
                             accum = 1;
-                            __syncwarp();
+                            ad += two ? 2 * a_step : a_step;
+                            rem -= 32;
                             if (++stage == kPPStages) { stage = 0; phase ^= 1; }
                         }
-                        if (from_x && elect_one()) tc_commit(xa_empty);
-                        __syncwarp();
+                        if (from_x) commit_elect(xa_empty_a);
                     }
-                    if (elect_one()) tc_commit(&acc_full[sl]);
-                    __syncwarp();
+                    commit_elect(acc_full_a + 8u * (uint32_t)sl);
                 }
             }
         }
