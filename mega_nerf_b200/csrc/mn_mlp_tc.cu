@@ -717,27 +717,6 @@ __device__ __forceinline__ void mma_stage(uint32_t d_tmem, uint64_t ad, uint64_t
         ::"r"(d_tmem), "l"(ad), "l"(bd), "l"(ad2), "l"(bd2), "r"(idesc), "r"(accum), "r"(two), "r"(empty_bar_addr)
         : "memory");
 }
-// two ring stages (4 K=16 steps, 64 K-columns) in one go: halves the issuing warp's per-MMA overhead
-__device__ __forceinline__ void mma_stage2(uint32_t d_tmem, uint64_t ad, uint64_t a_step, uint64_t bd_s0, uint64_t bd_s1,
-                                           uint64_t b_step, uint32_t idesc, uint32_t accum, uint32_t empty0, uint32_t empty1) {
-    asm volatile(
-        "{\n\t.reg .pred e, p;\n\t.reg .b64 a1, a2, a3, b1, b3;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %7, 0;\n\t"
-        "add.u64 a1, %1, %2;\n\t"
-        "add.u64 a2, a1, %2;\n\t"
-        "add.u64 a3, a2, %2;\n\t"
-        "add.u64 b1, %3, %5;\n\t"
-        "add.u64 b3, %4, %5;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %6, p;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %6, 1;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, %4, %6, 1;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %6, 1;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t}"
-        ::"r"(d_tmem), "l"(ad), "l"(a_step), "l"(bd_s0), "l"(bd_s1), "l"(b_step), "r"(idesc), "r"(accum), "r"(empty0), "r"(empty1)
-        : "memory");
-}
 __device__ __forceinline__ void commit_elect(uint32_t bar_addr) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
@@ -913,21 +892,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                         if (from_x) {
                             mbar_wait_a(xa_full_a, xphase);
                             xphase ^= 1;
-                        }
-                        while (rem >= 64) {
-                            const int stage1 = stage == kPPStages - 1 ? 0 : stage + 1;
-                            const uint32_t phase1 = stage == kPPStages - 1 ? phase ^ 1u : phase;
-                            mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
-                            mbar_wait_a(full_a + 8u * (uint32_t)stage1, phase1);
-                            tc_fence_after();
-                            mma_stage2(d_tmem, ad, a_step, bd0 + (uint64_t)stage * st_step, bd0 + (uint64_t)stage1 * st_step, b_step,
-                                       idesc, accum, empty_a + 8u * (uint32_t)stage, empty_a + 8u * (uint32_t)stage1);
-                            accum = 1;
-                            ad += 4 * a_step;
-                            rem -= 64;
-                            stage = stage1;
-                            phase = phase1;
-                            if (++stage == kPPStages) { stage = 0; phase ^= 1; }
                         }
                         while (rem > 0) {
                             const uint32_t two = rem >= 32 ? 1u : 0u;
