@@ -318,11 +318,12 @@ __global__ void __launch_bounds__(kTileM) tc_encode_kernel(const MlpArgs a, int 
         for (int c = 0; c < ktot; ++c) put(c, 0.0f);
     } else {
         float x[4];
-        for (int j = 0; j < nd.xyz_dim; ++j) { x[j] = a.src.xyz(row, j); put(j, x[j]); }
+        double xp[4];
+        for (int j = 0; j < nd.xyz_dim; ++j) { x[j] = a.src.xyz(row, j); put(j, x[j]); xp[j] = mn_pe_prescale(x[j]); }
         for (int k = 0; k < nd.nf_xyz; ++k)
             for (int j = 0; j < nd.xyz_dim; ++j) {
                 float s, c;
-                mn_pe_sincos(x[j], k, &s, &c);
+                mn_pe_sincos_pi(xp[j], k, &s, &c);
                 const int base = nd.xyz_dim + k * 2 * nd.xyz_dim;
                 put(base + j, s);
                 put(base + nd.xyz_dim + j, c);
@@ -333,11 +334,12 @@ __global__ void __launch_bounds__(kTileM) tc_encode_kernel(const MlpArgs a, int 
             if (!a.sigma_only) {
                 if (nd.nf_dir > 0) {
                     float d[3];
-                    for (int j = 0; j < 3; ++j) { d[j] = a.src.dir(row, j); put(col + j, d[j]); }
+                    double dp[3];
+                    for (int j = 0; j < 3; ++j) { d[j] = a.src.dir(row, j); put(col + j, d[j]); dp[j] = mn_pe_prescale(d[j]); }
                     for (int k = 0; k < nd.nf_dir; ++k)
                         for (int j = 0; j < 3; ++j) {
                             float s, c;
-                            mn_pe_sincos(d[j], k, &s, &c);
+                            mn_pe_sincos_pi(dp[j], k, &s, &c);
                             put(col + 3 + k * 6 + j, s);
                             put(col + 3 + k * 6 + 3 + j, c);
                         }
@@ -730,7 +732,7 @@ __device__ __forceinline__ void commit_elect(uint32_t bar_addr) {
 // and TMEM accumulator.  GEMMs are issued X_l, Y_l, X_l+1, Y_l+1, ...: the epilogue of X_l (16 warps)
 // runs entirely under the MMAs of Y_l and vice versa, so the tensor pipe only idles at pipeline fill.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPPStages = 3;
+constexpr int kPPMaxStages = 4;
 constexpr int kPPSlabCols = 32;
 constexpr int kPPStageBytes = kPPSlabCols * 256 * 2;
 
@@ -738,24 +740,29 @@ struct PPLayout {
     int ring, h, xa, f32, f32_stride, sigp, bars, total;
 };
 
-__host__ __device__ inline PPLayout pp_layout(const TcPlan& p) {
+__host__ __device__ inline PPLayout pp_layout(const TcPlan& p, bool bias_global) {
     PPLayout s;
+    const int kPPStages = bias_global ? 4 : 3;
     const int kx = p.kpe > p.kaux ? p.kpe : p.kaux;
     s.ring = 0;
     s.h = kPPStages * kPPStageBytes;
     s.xa = s.h + 2 * p.L * kTileM * 2;
     s.f32 = s.xa + kx * kTileM * 2;
     s.f32_stride = ((p.f32_floats * 4 + 15) / 16) * 16;
-    s.sigp = s.f32 + 2 * s.f32_stride;
+    s.sigp = s.f32 + (bias_global ? 0 : 2 * s.f32_stride);
     s.bars = s.sigp + 2048;
     s.total = s.bars + 256;
     return s;
 }
 
+// kBiasGlobal: biases / sigma weights are read straight from global memory (L2) by the epilogue instead of being
+// staged in shared memory; the 24 KiB saved buy a fourth weight-ring stage.
+template <bool kBiasGlobal>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) {
+    constexpr int kPPStages = kBiasGlobal ? 4 : 3;
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
-    const PPLayout SL = pp_layout(P);
+    const PPLayout SL = pp_layout(P, kBiasGlobal);
     unsigned char* ring = smem + SL.ring;
     unsigned char* Hs = smem + SL.h;
     unsigned char* XA = smem + SL.xa;
@@ -763,7 +770,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     float* SIGP = reinterpret_cast<float*>(smem + SL.sigp);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bars);
     uint64_t* full = bars;            // [3]
-    uint64_t* empty = bars + 4;       // [3]
+    uint64_t* empty = bars + 4;       // [<=4]
     uint64_t* xa_full = bars + 8;
     uint64_t* xa_empty = bars + 9;
     uint64_t* acc_full = bars + 10;   // [2] per tile slot
@@ -822,6 +829,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                 for (int sl = 0; sl < 2; ++sl) {
                     if (tiles[sl] >= n_tiles) continue;
                     wsub[sl] = A.wpack + (size_t)sub_of(tiles[sl]) * P.sub_bytes;
+                    if (kBiasGlobal) continue;
                     mbar_wait(&f32_empty[sl], fph[sl] ^ 1);
                     mbar_expect_tx(&f32_full[sl], f32_bytes);
                     bulk_g2s(reinterpret_cast<unsigned char*>(F32) + (size_t)sl * SL.f32_stride,
@@ -922,12 +930,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
             const bool valid1 = t0 + gridDim.x < n_tiles;
             int64_t slot_[2], row_[2] = {-1, -1};
             float sigma_[2] = {0.0f, 0.0f};
+            const float* fb_[2] = {nullptr, nullptr};
             for (int sl = 0; sl < 2; ++sl) {
                 if (sl == 1 && !valid1) continue;
                 slot_[sl] = (t0 + (int64_t)sl * gridDim.x) * kTileM + r;
                 if (slot_[sl] < n_slots) row_[sl] = A.m.slot_row ? (int64_t)A.m.slot_row[slot_[sl]] : slot_[sl];
-                if (sl == 0) { mbar_wait(&f32_full[0], fph0); fph0 ^= 1; }
-                else         { mbar_wait(&f32_full[1], fph1); fph1 ^= 1; }
+                if (kBiasGlobal) {
+                    fb_[sl] = reinterpret_cast<const float*>(A.wpack + (size_t)sub_of(t0 + (int64_t)sl * gridDim.x) * P.sub_bytes +
+                                                             (size_t)P.plane_bytes * 2);
+                } else {
+                    fb_[sl] = F32 + (size_t)sl * (SL.f32_stride / 4);
+                    if (sl == 0) { mbar_wait(&f32_full[0], fph0); fph0 ^= 1; }
+                    else         { mbar_wait(&f32_full[1], fph1); fph1 ^= 1; }
+                }
             }
             for (int gi = 0; gi < n_gemm; ++gi) {
                 const TcGemm& g = P.g[gi];
@@ -938,7 +953,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                     else         { mbar_wait(&acc_full[1], aph1); aph1 ^= 1; }
                     tc_fence_after();
                     const uint32_t t_acc = t_lane + (uint32_t)sl * 256u;
-                    const float* Fb = F32 + (size_t)sl * (SL.f32_stride / 4);
+                    const float* Fb = fb_[sl];
                     const float* bias = Fb + g.bias_off;
                     const int64_t row = row_[sl], slot = slot_[sl];
                     if (g.epi == EPI_RGB) {
@@ -1004,7 +1019,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                 }
             }
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !kBiasGlobal) {
                 mbar_arrive(&f32_empty[0]);
                 if (valid1) mbar_arrive(&f32_empty[1]);
             }
@@ -1124,12 +1139,23 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
             const char* e = getenv("MN_TC_PINGPONG");
             use_pp = (e && e[0] == '0') ? 0 : 1;
         }
-        const PPLayout PL = pp_layout(P);
+        static int bias_global = -1;
+        if (bias_global < 0) {
+            const char* e = getenv("MN_TC_BIAS_GLOBAL");
+            bias_global = (e && e[0] == '1') ? 1 : 0;
+        }
+        const PPLayout PL = pp_layout(P, bias_global != 0);
         if (use_pp && PL.total <= kSmemMax) {
-            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
             const unsigned grid_pp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
-            mn_prof_begin(ctx, st);
-            tc_mlp_pp_kernel<<<grid_pp, kThreads, PL.total, st>>>(A);
+            if (bias_global) {
+                MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
+                mn_prof_begin(ctx, st);
+                tc_mlp_pp_kernel<true><<<grid_pp, kThreads, PL.total, st>>>(A);
+            } else {
+                MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
+                mn_prof_begin(ctx, st);
+                tc_mlp_pp_kernel<false><<<grid_pp, kThreads, PL.total, st>>>(A);
+            }
         } else {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
             mn_prof_begin(ctx, st);

@@ -226,10 +226,42 @@ __global__ void __launch_bounds__(128) composite_kernel(const CompositeArgs a) {
             zs[a.S + i] = a.z2[ray * a.S2 + i];
             ids[a.S + i] = (unsigned short)(a.S + i);
         }
-        const float pad = a.flip ? -INFINITY : INFINITY;
-        for (int i = n + lane; i < a.npad; i += 32) { zs[i] = pad; ids[i] = 0xFFFF; }
         __syncwarp();
-        warp_bitonic(zs, ids, a.npad, a.flip != 0, lane);
+        // Both runs are usually already ordered (deterministic sampling): merge by rank instead of sorting.
+        // Same total order as the bitonic path: (depth, index), own samples first on ties.
+        bool ordered = true;
+        for (int i = lane; i + 1 < a.S; i += 32) ordered &= a.flip ? (zs[i] >= zs[i + 1]) : (zs[i] <= zs[i + 1]);
+        for (int i = lane; i + 1 < a.S2; i += 32)
+            ordered &= a.flip ? (zs[a.S + i] >= zs[a.S + i + 1]) : (zs[a.S + i] <= zs[a.S + i + 1]);
+        ordered = __all_sync(0xffffffffu, ordered);
+        if (ordered) {
+            float* zm = ws;   // merged depths are built in the (still unused) weights buffer, then swapped in
+            unsigned short* idm = ids + a.npad * 4;   // second id plane (see launch: 2 planes per warp)
+            for (int i = lane; i < n; i += 32) {
+                const bool own = i < a.S;
+                const float v = zs[i];
+                const float* other = own ? zs + a.S : zs;
+                const int m = own ? a.S2 : a.S;
+                // own element: count others strictly before it; other element: count own elements before-or-equal
+                int lo = 0, hi = m;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const float o = other[mid];
+                    const bool before = a.flip ? (own ? o > v : o >= v) : (own ? o < v : o <= v);
+                    if (before) lo = mid + 1; else hi = mid;
+                }
+                const int pos = (own ? i : i - a.S) + lo;
+                zm[pos] = v;
+                idm[pos] = (unsigned short)i;
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) { const float v = zm[i]; const unsigned short id = idm[i]; zs[i] = v; ids[i] = id; }
+        } else {
+            const float pad = a.flip ? -INFINITY : INFINITY;
+            for (int i = n + lane; i < a.npad; i += 32) { zs[i] = pad; ids[i] = 0xFFFF; }
+            __syncwarp();
+            warp_bitonic(zs, ids, a.npad, a.flip != 0, lane);
+        }
     }
     __syncwarp();
 
@@ -506,7 +538,7 @@ __global__ void embed_kernel(const float* __restrict__ x, int64_t B, int dim, in
     } else {
         const int qq = q - dim, k = qq / dim, j = qq % dim;
         float s, c;
-        mn_pe_sincos(x[b * dim + j], k, &s, &c);
+        mn_pe_sincos_pi(mn_pe_prescale(x[b * dim + j]), k, &s, &c);
         o[dim + k * 2 * dim + j] = s;
         o[dim + k * 2 * dim + dim + j] = c;
     }
@@ -616,7 +648,7 @@ int mn_composite(mn_ctx* ctx, const float* raw_d, const float* z_d, const float*
     a.weights = weights_out_d; a.rgb = rgb_out_d; a.depth = depth_out_d; a.var = depth_var_out_d; a.lambda = bg_lambda_out_d;
     a.npad = S2 > 0 ? pow2_at_least(S + S2) : (S + 31) / 32 * 32;
     if (a.npad > 4096) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "mn_composite: more than 4096 samples per ray");
-    const size_t sm = (size_t)4 * a.npad * (2 * sizeof(float) + sizeof(unsigned short));
+    const size_t sm = (size_t)4 * a.npad * (2 * sizeof(float) + 2 * sizeof(unsigned short));
     MN_CUDA(ctx, cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     composite_kernel<<<(unsigned)mn_cdiv(N, 4), 128, sm, (cudaStream_t)stream>>>(a);
     MN_LAUNCH_CHECK(ctx);
