@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256, 1) mlp_simt_kernel(const MlpArgs a) {
             } else {
                 const int qq = q - nd.xyz_dim, k = qq / nd.xyz_dim, j = qq % nd.xyz_dim;
                 float s, c;
-                mn_pe_sincos_pi(mn_pe_prescale(XIN[r * 8 + j]), k, &s, &c);
+                mn_pe_sincos(XIN[r * 8 + j], k, &s, &c);
                 const int base = nd.xyz_dim + k * 2 * nd.xyz_dim;
                 PE[(base + j) * TM + r] = s;
                 PE[(base + nd.xyz_dim + j) * TM + r] = c;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256, 1) mlp_simt_kernel(const MlpArgs a) {
                     } else {
                         const int qq = q - 3, k = qq / 3, j = qq % 3;
                         float s, c;
-                        mn_pe_sincos_pi(mn_pe_prescale(XIN[r * 8 + 4 + j]), k, &s, &c);
+                        mn_pe_sincos(XIN[r * 8 + 4 + j], k, &s, &c);
                         AUX[(3 + k * 6 + j) * TM + r] = s;
                         AUX[(3 + k * 6 + 3 + j) * TM + r] = c;
                     }

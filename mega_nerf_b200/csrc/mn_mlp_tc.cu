@@ -30,6 +30,10 @@ __host__ __device__ constexpr int ring_stage_bytes(bool split) { return ring_sla
 constexpr int kMaxGemm = 16;
 constexpr int kThreads = 576;   // producer warp, MMA warp, 16 epilogue warps
 constexpr int kEpiWarps = 16;
+// Warps 0..15 = epilogue (TMEM lane quarter = warp % 4), 16 = TMA producer, 17 = MMA issuer.  The scheduler favours the
+// highest warp id on an SM sub-partition, so the latency-critical single-thread roles get the top ids.
+constexpr int kWarpProd = 16;
+constexpr int kWarpMma = 17;
 
 enum { SRC_H = 0, SRC_XPE = 1, SRC_XAUX = 2 };
 enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(kTileM) tc_encode_kernel(const MlpArgs a, int 
         for (int k = 0; k < nd.nf_xyz; ++k)
             for (int j = 0; j < nd.xyz_dim; ++j) {
                 float s, c;
-                mn_pe_sincos_pi(xp[j], k, &s, &c);
+                mn_pe_sincos(x[j], k, &s, &c);
                 const int base = nd.xyz_dim + k * 2 * nd.xyz_dim;
                 put(base + j, s);
                 put(base + nd.xyz_dim + j, c);
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(kTileM) tc_encode_kernel(const MlpArgs a, int 
                     for (int k = 0; k < nd.nf_dir; ++k)
                         for (int j = 0; j < 3; ++j) {
                             float s, c;
-                            mn_pe_sincos_pi(dp[j], k, &s, &c);
+                            mn_pe_sincos(d[j], k, &s, &c);
                             put(col + 3 + k * 6 + j, s);
                             put(col + 3 + k * 6 + 3 + j, c);
                         }
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
         mbar_init(f32_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == kWarpProd) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
     };
     constexpr int npass = kSplit ? 3 : 1;
 
-    if (warp == 0) {
+    if (warp == kWarpProd) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
             int stage = 0;
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kWarpMma) {
         // =========================== MMA issuer ===========================
         // The whole warp runs the loop (so addresses/descriptors stay in uniform registers); one elected lane
         // issues tcgen05.mma / tcgen05.commit.
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
     } else {
         // =========================== epilogue (16 warps) ===========================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
-        const int part = (warp - 2) >> 2;            // which 16-column piece of every 64-column slab
+        const int part = warp >> 2;            // which 16-column piece of every 64-column slab
         const int r = q * 32 + lane;                 // row of the tile == TMEM lane
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t acc_phase0 = 0, acc_phase1 = 0, fphase = 0, gidx = 0;
@@ -674,7 +678,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == kWarpProd) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }
 }
@@ -797,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == kWarpProd) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -817,7 +821,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     };
     const int64_t stride2 = 2 * (int64_t)gridDim.x;
 
-    if (warp == 0) {
+    if (warp == kWarpProd) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
             int stage = 0;
@@ -867,7 +871,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kWarpMma) {
         // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
         int stage = 0;
         uint32_t phase = 0, xphase = 0, eph0 = 0, eph1 = 0;
@@ -921,7 +925,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     } else {
         // =========================== epilogue (16 warps) ===========================
         const int q = warp & 3;
-        const int part = (warp - 2) >> 2;
+        const int part = warp >> 2;
         const int r = q * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t aph0 = 0, aph1 = 0, fph0 = 0, fph1 = 0;
@@ -1027,7 +1031,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == kWarpProd) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }
 }

@@ -10,75 +10,55 @@
 
 namespace {
 
-struct RoutePoint {
+__device__ __forceinline__ void distances(const RowSrc& src, int64_t row, const float* __restrict__ cent, int K,
+                                          int s, bool direct, float* d) {
     float x[3];
-    float xn;      // |x|^2 over the clustered dims (matmul path)
-};
-
-__device__ __forceinline__ RoutePoint load_point(const RowSrc& src, int64_t row, int s) {
-    RoutePoint p;
-    p.x[0] = p.x[1] = p.x[2] = 0.0f;
-    for (int j = s; j < 3; ++j) p.x[j] = src.route_xyz(row, j);
-    p.xn = p.x[s] * p.x[s];
-    for (int j = s + 1; j < 3; ++j) p.xn = p.xn + p.x[j] * p.x[j];
-    return p;
-}
-
-// distance to centroid k (cent = [K,3] in shared memory), restating torch.cdist (see file header)
-__device__ __forceinline__ float dist_to(const RoutePoint& p, const float* __restrict__ cent, int k, int s, bool direct) {
+    for (int j = s; j < 3; ++j) x[j] = src.route_xyz(row, j);
     if (direct) {
-        float acc = 0.0f;
-        for (int j = s; j < 3; ++j) {
-            const float t = p.x[j] - cent[k * 3 + j];
-            acc = fmaf(t, t, acc);  // torch's direct cdist kernel contracts this (probe: 100% bitwise)
-        }
-        return sqrtf(acc);
-    }
-    float cn = cent[k * 3 + s] * cent[k * 3 + s];
-    for (int j = s + 1; j < 3; ++j) cn = cn + cent[k * 3 + j] * cent[k * 3 + j];
-    float acc = 0.0f;
-    for (int j = s; j < 3; ++j) acc = fmaf(-2.0f * p.x[j], cent[k * 3 + j], acc);
-    acc = fmaf(p.xn, 1.0f, acc);
-    acc = fmaf(1.0f, cn, acc);
-    return sqrtf(fmaxf(acc, 0.0f));
-}
-
-// Routing decision of one point without per-thread arrays (distances are recomputed per pass; K is small).
-struct RouteDecision {
-    float dmin, sum;   // minimum distance; sum of masked inverse distances (margin > 1)
-    int amin;
-};
-
-__device__ __forceinline__ RouteDecision route_decide(const RoutePoint& p, const float* __restrict__ cent, int K, int s,
-                                                      bool direct, float margin) {
-    RouteDecision r;
-    r.dmin = dist_to(p, cent, 0, s, direct);
-    r.amin = 0;
-    for (int k = 1; k < K; ++k) {
-        const float d = dist_to(p, cent, k, s, direct);
-        if (d < r.dmin) { r.dmin = d; r.amin = k; }
-    }
-    r.sum = 0.0f;
-    if (margin > 1.0f) {
-        const float thr = margin * r.dmin;
         for (int k = 0; k < K; ++k) {
-            const float d = dist_to(p, cent, k, s, direct);
-            float inv = 1.0f / (d + 1e-8f);
-            if (d > thr) inv = 0.0f;
-            r.sum = r.sum + inv;
+            float acc = 0.0f;
+            for (int j = s; j < 3; ++j) {
+                const float t = x[j] - cent[k * 3 + j];
+                acc = fmaf(t, t, acc);  // torch's direct cdist kernel contracts this (probe: 100% bitwise)
+            }
+            d[k] = sqrtf(acc);
         }
+        return;
     }
-    return r;
+    float xn = x[s] * x[s];
+    for (int j = s + 1; j < 3; ++j) xn = xn + x[j] * x[j];
+    for (int k = 0; k < K; ++k) {
+        float cn = cent[k * 3 + s] * cent[k * 3 + s];
+        for (int j = s + 1; j < 3; ++j) cn = cn + cent[k * 3 + j] * cent[k * 3 + j];
+        float acc = 0.0f;
+        for (int j = s; j < 3; ++j) acc = fmaf(-2.0f * x[j], cent[k * 3 + j], acc);
+        acc = fmaf(xn, 1.0f, acc);
+        acc = fmaf(1.0f, cn, acc);
+        d[k] = sqrtf(fmaxf(acc, 0.0f));
+    }
 }
 
-// blend weight of sub-module k (0 when masked out); for hard routing 1 for the argmin
-__device__ __forceinline__ float route_weight(const RoutePoint& p, const RouteDecision& r, const float* __restrict__ cent, int k,
-                                              int s, bool direct, float margin) {
-    if (!(margin > 1.0f)) return k == r.amin ? 1.0f : 0.0f;
-    const float d = dist_to(p, cent, k, s, direct);
-    float inv = 1.0f / (d + 1e-8f);
-    if (d > margin * r.dmin) inv = 0.0f;
-    return inv / r.sum;
+// -> number of active sub-modules; mask bits; for margin > 1 the normalised weights in w[]
+__device__ __forceinline__ uint64_t route_row(const float* d, int K, float margin, float* w) {
+    float dmin = d[0];
+    int amin = 0;
+    for (int k = 1; k < K; ++k)
+        if (d[k] < dmin) { dmin = d[k]; amin = k; }
+    if (!(margin > 1.0f)) return 1ull << amin;
+    uint64_t mask = 0;
+    float sum = 0.0f;
+    const float thr = margin * dmin;
+    for (int k = 0; k < K; ++k) {
+        float inv = 1.0f / (d[k] + 1e-8f);
+        if (d[k] > thr) inv = 0.0f;
+        w[k] = inv;
+        sum = sum + inv;
+    }
+    for (int k = 0; k < K; ++k) {
+        w[k] = w[k] / sum;
+        if (w[k] > 0.0f) mask |= 1ull << k;
+    }
+    return mask;
 }
 
 __global__ void route_count_kernel(RowSrc src, int64_t B, const float* __restrict__ cent, int K, int s, float margin,
@@ -89,16 +69,14 @@ __global__ void route_count_kernel(RowSrc src, int64_t B, const float* __restric
     for (int i = threadIdx.x; i < K; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = row < B;
-    RoutePoint p{};
-    RouteDecision r{};
-    if (live) {
-        p = load_point(src, row, s);
-        r = route_decide(p, sc, K, s, direct, margin);
+    uint64_t mask = 0;
+    if (row < B) {
+        float d[MN_MAX_SUB], w[MN_MAX_SUB];
+        distances(src, row, sc, K, s, direct, d);
+        mask = route_row(d, K, margin, w);
     }
     for (int k = 0; k < K; ++k) {
-        const bool on = live && route_weight(p, r, sc, k, s, direct, margin) > 0.0f;
-        const unsigned b = __ballot_sync(0xffffffffu, on);
+        const unsigned b = __ballot_sync(0xffffffffu, (mask >> k) & 1);
         if ((threadIdx.x & 31) == 0 && b) atomicAdd(&hist[k], __popc(b));
     }
     __syncthreads();
@@ -130,19 +108,18 @@ __global__ void route_scatter_kernel(RowSrc src, int64_t B, const float* __restr
     __syncthreads();
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool live = row < B;
-    RoutePoint p{};
-    RouteDecision r{};
-    if (live) {
-        p = load_point(src, row, s);
-        r = route_decide(p, sc, K, s, direct, margin);
+    uint64_t mask = 0;
+    float w[MN_MAX_SUB];
+    if (row < B) {
+        float d[MN_MAX_SUB];
+        distances(src, row, sc, K, s, direct, d);
+        mask = route_row(d, K, margin, w);
     }
     for (int k = 0; k < K; ++k) {
-        const float w = live ? route_weight(p, r, sc, k, s, direct, margin) : 0.0f;
-        const bool on = w > 0.0f;
+        const bool on = (mask >> k) & 1;
         const unsigned b = __ballot_sync(0xffffffffu, on);
         if (!b) {
-            if (live && row_slots) row_slots[row * K + k] = -1;
+            if (row < B && row_slots) row_slots[row * K + k] = -1;
             continue;
         }
         int base = 0;
@@ -157,10 +134,10 @@ __global__ void route_scatter_kernel(RowSrc src, int64_t B, const float* __restr
                 slot = -1;
             } else {
                 slot_row[slot] = (int)row;
-                if (slot_w) slot_w[slot] = w;
+                if (slot_w) slot_w[slot] = w[k];
             }
         }
-        if (live && row_slots) row_slots[row * K + k] = slot;
+        if (row < B && row_slots) row_slots[row * K + k] = slot;
     }
 }
 
@@ -182,12 +159,13 @@ __global__ void route_only_kernel(RowSrc src, int64_t B, const float* __restrict
                                   int direct, int* assign, float* weights) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= B) return;
-    const RoutePoint p = load_point(src, row, s);
-    const RouteDecision r = route_decide(p, cent, K, s, direct, margin);
+    float d[MN_MAX_SUB], w[MN_MAX_SUB];
+    distances(src, row, cent, K, s, direct, d);
+    const uint64_t mask = route_row(d, K, margin, w);
     if (margin > 1.0f) {
-        for (int k = 0; k < K; ++k) weights[row * K + k] = route_weight(p, r, cent, k, s, direct, margin);
+        for (int k = 0; k < K; ++k) weights[row * K + k] = w[k];
     } else {
-        assign[row] = r.amin;
+        assign[row] = __ffsll((long long)mask) - 1;
     }
 }
 

@@ -538,7 +538,7 @@ __global__ void embed_kernel(const float* __restrict__ x, int64_t B, int dim, in
     } else {
         const int qq = q - dim, k = qq / dim, j = qq % dim;
         float s, c;
-        mn_pe_sincos_pi(mn_pe_prescale(x[b * dim + j]), k, &s, &c);
+        mn_pe_sincos(x[b * dim + j], k, &s, &c);
         o[dim + k * 2 * dim + j] = s;
         o[dim + k * 2 * dim + dim + j] = c;
     }
