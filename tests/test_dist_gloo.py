@@ -1,0 +1,83 @@
+"""CPU-only, world_size 2 over gloo: host logic of the ray-sharded multi-GPU path (shard bounds, the single
+padded all-gather, result reassembly).  The render function is a stand-in with render_rays' signature — the
+CUDA path itself has no CPU fallback."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import cases  # noqa: F401
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def fake_render(rays, idx, scale):
+    rgb = rays[:, 0:3] * scale + (idx.unsqueeze(-1) if idx is not None else 0)
+    return {'rgb_fine': rgb, 'depth_fine': rays[:, 6] + rays[:, 7]}, bool((rays[:, 7] > 0.55).any())
+
+
+def worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    from mega_nerf_b200 import dist as D
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    rays = torch.rand(n, 8, generator=g)
+    idx = torch.randint(0, 10, (n,), generator=g).float()
+    res, present = D.render_rays_sharded(fake_render, rays, idx, 2.0)
+    ref, ref_present = fake_render(rays, idx, 2.0)
+    ok = all(torch.equal(res[k], ref[k]) for k in ref) and set(res) == set(ref) and present == ref_present
+    q.put((rank, ok, D.shard_bounds(n, world, rank)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+_port = [0]
+
+
+def free_port():
+    import socket
+    with socket.socket() as s_:
+        s_.bind(('127.0.0.1', 0))
+        return s_.getsockname()[1]
+
+
+def run(n):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = free_port()
+    ps = [ctx.Process(target=worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return sorted(out)
+
+
+def test_sharded_render_matches_single_rank_even():
+    out = run(64)
+    assert all(ok for _, ok, _ in out)
+    assert out[0][2] == (0, 32) and out[1][2] == (32, 64)
+
+
+def test_sharded_render_ragged_and_tiny():
+    out = run(33)                      # ragged: 17 + 16
+    assert all(ok for _, ok, _ in out)
+    assert out[0][2] == (0, 17) and out[1][2] == (17, 33)
+    out = run(1)                       # one rank gets nothing
+    assert all(ok for _, ok, _ in out)
+
+
+def test_shard_bounds_cover():
+    from mega_nerf_b200 import dist as D
+    for n in (0, 1, 7, 4096, 65536 + 3):
+        for w in (1, 2, 4, 8):
+            spans = [D.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
