@@ -284,6 +284,26 @@ __global__ void tc_pack_kernel(const float* __restrict__ wt /* packed fp32, K-ma
     if (lo) lo[i] = __float2half_rn(v - __half2float(h));
 }
 
+// half-major image for the TS kernel: [N-half][K/8][nw][8] fp16 (nw = min(N,128))
+__global__ void tc_pack_half_kernel(const float* __restrict__ wt, int n_src, int k_src, int N, int K, int nw, int k_real0, int k_pad0,
+                                    __half* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * K) return;
+    const int k8 = (int)(i % 8);
+    const int n = (int)((i / 8) % nw);
+    const int64_t rest = i / (8 * (int64_t)nw);
+    const int kc = (int)(rest % (K / 8));
+    const int h = (int)(rest / (K / 8));
+    const int k = kc * 8 + k8;
+    const int ng = h * nw + n;
+    int ks;
+    if (k < k_pad0) ks = k < k_real0 ? k : -1;
+    else ks = k_real0 + (k - k_pad0);
+    float v = 0.0f;
+    if (ks >= 0 && ks < k_src && ng < n_src) v = wt[(int64_t)ks * n_src + ng];
+    out[i] = __float2half_rn(v);
+}
+
 __global__ void tc_pack_f32_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_dst) dst[i] = i < n ? src[i] : 0.0f;
@@ -1036,6 +1056,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     }
 }
 
+#include "mn_mlp_ts.cuh"
+
 }  // namespace
 
 // =================================================================================================
@@ -1053,7 +1075,9 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         return MN_OK;  // configuration only served by the fp32 kernel
     }
     const NetDims& nd = m->nd;
-    const size_t sub_bytes = mn_align((size_t)P.plane_bytes * 2 + (size_t)P.f32_floats * 4, 256);
+    // [hi plane][lo plane][fp32 block, 256-aligned][half-major hi plane for the TS kernel]
+    const size_t ts_off = (size_t)P.plane_bytes * 2 + (size_t)(((P.f32_floats * 4 + 255) / 256) * 256);
+    const size_t sub_bytes = mn_align(ts_off + (size_t)P.plane_bytes, 256);
     if (!m->tc_packed) {
         MN_CUDA(ctx, cudaMalloc(&m->tc_packed, sub_bytes * m->d.n_sub));
         MN_CUDA(ctx, cudaMemsetAsync(m->tc_packed, 0, sub_bytes * m->d.n_sub, st));
@@ -1069,6 +1093,9 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         __half* hi = reinterpret_cast<__half*>(base + g.w_off);
         __half* lo = reinterpret_cast<__half*>(base + P.plane_bytes + g.w_off);
         tc_pack_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, k_real0, k_pad0, hi, lo);
+        MN_LAUNCH_CHECK(ctx);
+        tc_pack_half_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, g.n < 128 ? g.n : 128, k_real0, k_pad0,
+                                                                    reinterpret_cast<__half*>(base + ts_off + g.w_off));
         MN_LAUNCH_CHECK(ctx);
         tc_pack_f32_kernel<<<1, 256, 0, st>>>(bias, n_bias, f32 + g.bias_off, 256);
         MN_LAUNCH_CHECK(ctx);
@@ -1148,8 +1175,18 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
             const char* e = getenv("MN_TC_BIAS_GLOBAL");
             bias_global = (e && e[0] == '1') ? 1 : 0;
         }
+        static int use_ts = -1;
+        if (use_ts < 0) {
+            const char* e = getenv("MN_TC_TS");
+            use_ts = (e && e[0] == '1') ? 1 : 0;
+        }
         const PPLayout PL = pp_layout(P, bias_global != 0);
-        if (use_pp && PL.total <= kSmemMax) {
+        const TsLayout TL = ts_layout(P);
+        if (use_ts && P.L % 128 == 0 && TL.stages >= 4) {
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL.total));
+            mn_prof_begin(ctx, st);
+            tc_mlp_ts_kernel<<<grid, kThreads, TL.total, st>>>(A);
+        } else if (use_pp && PL.total <= kSmemMax) {
             const unsigned grid_pp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
             if (bias_global) {
                 MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
