@@ -87,6 +87,29 @@ __device__ __forceinline__ void ts_stage_smem(uint32_t d_tmem, uint64_t ad, uint
         : "memory");
 }
 
+// Probe up to four mbarriers back to back (their ~100-cycle try_wait latencies overlap), then block on whatever
+// was not ready yet.  Unused slots repeat a valid (address, parity) pair.
+__device__ __forceinline__ void mbar_wait4(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1, uint32_t a2, uint32_t p2, uint32_t a3,
+                                           uint32_t p3) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred q0, q1, q2, q3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
+        "and.pred q0, q0, q1;\n\tand.pred q2, q2, q3;\n\tand.pred q0, q0, q2;\n\t"
+        "selp.u32 %0, 1, 0, q0;\n\t}"
+        : "=r"(ok)
+        : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2), "r"(a3), "r"(p3)
+        : "memory");
+    if (ok) return;
+    mbar_wait_a(a0, p0);
+    mbar_wait_a(a1, p1);
+    mbar_wait_a(a2, p2);
+    mbar_wait_a(a3, p3);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
@@ -225,26 +248,46 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) 
                             xphase ^= 1;
                             tc_fence_after();
                         }
-                        for (int k0 = 0; k0 < kseg; k0 += kTsStageCols) {
-                            const int kc = min(kTsStageCols, kseg - k0);
+                        // two ring stages (up to 128 K-columns, 8 MMAs) per iteration; all barrier probes go out together
+                        for (int k0 = 0; k0 < kseg; k0 += 2 * kTsStageCols) {
+                            const int kc0 = min(kTsStageCols, kseg - k0);
+                            const int kc1 = min(kTsStageCols, kseg - k0 - kTsStageCols);     // <= 0: single stage
+                            const bool two = kc1 > 0;
+                            const int st0 = stage;
+                            const uint32_t ph0 = phase;
+                            int st1 = stage + 1;
+                            uint32_t ph1 = phase;
+                            if (st1 == kStages) { st1 = 0; ph1 ^= 1; }
+                            const uint32_t f0 = full_a + 8u * (uint32_t)st0, f1 = two ? full_a + 8u * (uint32_t)st1 : f0;
+                            const uint32_t fp1 = two ? ph1 : ph0;
                             if (!from_x && h == 0) {
-                                // K-slab k0/64 of the A operand has been published by the previous epilogue
-                                const int s = k0 >> 6;
-                                if (s == 0) { mbar_wait_a(aready_a, rph0); rph0 ^= 1; }
-                                else if (s == 1) { mbar_wait_a(aready_a + 8, rph1); rph1 ^= 1; }
-                                else if (s == 2) { mbar_wait_a(aready_a + 16, rph2); rph2 ^= 1; }
-                                else { mbar_wait_a(aready_a + 24, rph3); rph3 ^= 1; }
+                                // K-slabs k0/64 (and the next one) of the A operand have been published by the previous epilogue
+                                const int s0 = k0 >> 6;
+                                const uint32_t r0 = s0 == 0 ? rph0 : rph2;      // s0 is 0 or 2
+                                const uint32_t r1 = s0 == 0 ? rph1 : rph3;
+                                const uint32_t ra0 = aready_a + 8u * (uint32_t)s0, ra1 = two ? ra0 + 8u : ra0;
+                                mbar_wait4(ra0, r0, ra1, two ? r1 : r0, f0, ph0, f1, fp1);
+                                if (s0 == 0) { rph0 ^= 1; if (two) rph1 ^= 1; } else { rph2 ^= 1; if (two) rph3 ^= 1; }
+                            } else {
+                                mbar_wait4(f0, ph0, f1, fp1, f0, ph0, f1, fp1);
                             }
-                            mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
                             tc_fence_after();
-                            const uint64_t bd = bd0 + (uint64_t)stage * st_step;
-                            if (from_x)
-                                ts_stage_smem(d_tmem, make_desc(xa_base + (uint32_t)(k0 / 8) * (kTileM * 16), kTileM * 16, 128), a_step, bd,
-                                              b_step, idesc, accum, kc >> 4, empty_a + 8u * (uint32_t)stage);
-                            else
-                                ts_stage_tmem(d_tmem, a_tm + (uint32_t)(k0 >> 1), bd, b_step, idesc, accum, kc >> 4,
-                                              empty_a + 8u * (uint32_t)stage);
+                            const uint64_t bdA = bd0 + (uint64_t)st0 * st_step, bdB = bd0 + (uint64_t)st1 * st_step;
+                            if (from_x) {
+                                ts_stage_smem(d_tmem, make_desc(xa_base + (uint32_t)(k0 / 8) * (kTileM * 16), kTileM * 16, 128), a_step, bdA,
+                                              b_step, idesc, accum, kc0 >> 4, empty_a + 8u * (uint32_t)st0);
+                                if (two)
+                                    ts_stage_smem(d_tmem, make_desc(xa_base + (uint32_t)((k0 + kTsStageCols) / 8) * (kTileM * 16), kTileM * 16, 128),
+                                                  a_step, bdB, b_step, idesc, 1u, kc1 >> 4, empty_a + 8u * (uint32_t)st1);
+                            } else {
+                                ts_stage_tmem(d_tmem, a_tm + (uint32_t)(k0 >> 1), bdA, b_step, idesc, accum, kc0 >> 4,
+                                              empty_a + 8u * (uint32_t)st0);
+                                if (two)
+                                    ts_stage_tmem(d_tmem, a_tm + (uint32_t)((k0 + kTsStageCols) >> 1), bdB, b_step, idesc, 1u, kc1 >> 4,
+                                                  empty_a + 8u * (uint32_t)st1);
+                            }
                             accum = 1;
+                            if (two) { stage = st1; phase = ph1; }
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
                         if (from_x && h == nh - 1) commit_elect(xa_empty_a);
