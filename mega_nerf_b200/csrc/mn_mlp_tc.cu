@@ -1185,7 +1185,7 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         if (use_ts && P.L % 128 == 0 && TL.stages >= 4) {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL.total));
             mn_prof_begin(ctx, st);
-            tc_mlp_ts_kernel<<<grid, kThreads, TL.total, st>>>(A);
+            tc_mlp_ts_kernel<<<grid, kTsThreads, TL.total, st>>>(A);
         } else if (use_pp && PL.total <= kSmemMax) {
             const unsigned grid_pp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
             if (bias_global) {

@@ -13,7 +13,9 @@
 
 constexpr int kTsStageCols = 64;                       // K-columns per ring stage
 constexpr int kTsStageBytes = kTsStageCols * 128 * 2;  // x 128 weight rows (one N-half) x fp16 = 16 KiB
-constexpr int kTsMaxStages = 10;
+constexpr int kTsMaxStages = 10;                      // split into two rings of 5 (one per N-half / issuing warp)
+constexpr int kTsThreads = 640;                        // 16 epilogue warps + 2 producers + 2 MMA issuers
+constexpr int kTsWarpProd0 = 16, kTsWarpProd1 = 17, kTsWarpMma0 = 18, kTsWarpMma1 = 19;
 
 struct TsLayout {
     int ring, stages, xa, f32, sigp, bars, total;
@@ -110,12 +112,14 @@ __device__ __forceinline__ void mbar_wait4(uint32_t a0, uint32_t p0, uint32_t a1
     mbar_wait_a(a3, p3);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) {
+// Two MMA-issuing warps (one per N-half, each with its own weight ring and producer warp): a single issuing
+// thread needs ~170 cycles of scalar work per tcgen05.mma and cannot keep the tensor pipe (64 cycles per N=128 MMA) fed.
+__global__ void __launch_bounds__(kTsThreads, 1) tc_mlp_ts_kernel(const TcArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
     const TsLayout SL = ts_layout(P);
-    const int kStages = SL.stages;
-    unsigned char* ring = smem + SL.ring;
+    const int kStages = SL.stages / 2;            // per ring
+    unsigned char* ring_all = smem + SL.ring;
     unsigned char* XA = smem + SL.xa;
     float* F32 = reinterpret_cast<float*>(smem + SL.f32);
     float* SIGP = reinterpret_cast<float*>(smem + SL.sigp);
@@ -139,14 +143,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTsMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(xa_full, 1);
-        mbar_init(xa_empty, 1);
+        mbar_init(xa_empty, 2);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], kEpiWarps); }
         for (int i = 0; i < 4; ++i) mbar_init(&aready[i], 8);
         mbar_init(f32_full, 1);
         mbar_init(f32_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kWarpProd) {
+    if (warp == kTsWarpProd0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -167,29 +171,36 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) 
     // byte offset of the half-major TS weight plane inside one sub-module's pack
     const size_t ts_off = (size_t)P.plane_bytes * 2 + (size_t)(((P.f32_floats * 4 + 255) / 256) * 256);
 
-    if (warp == kWarpProd) {
-        // =========================== TMA producer ===========================
+    if (warp == kTsWarpProd0 || warp == kTsWarpProd1) {
+        // =========================== TMA producers (ring `me` feeds N-half `me`) ===========================
+        const int me = warp == kTsWarpProd1 ? 1 : 0;
+        unsigned char* ring = ring_all + (size_t)me * kStages * kTsStageBytes;
+        uint64_t* full_me = full + me * (kTsMaxStages / 2);
+        uint64_t* empty_me = empty + me * (kTsMaxStages / 2);
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, xphase = 0, fphase = 0;
             const uint32_t f32_bytes = (uint32_t)(((P.f32_floats * 4 + 15) / 16) * 16);
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const unsigned char* wsub = A.wpack + (size_t)sub_of(tile) * P.sub_bytes;
-                mbar_wait(f32_empty, fphase ^ 1);
-                mbar_expect_tx(f32_full, f32_bytes);
-                bulk_g2s(F32, wsub + (size_t)P.plane_bytes * 2, f32_bytes, f32_full);
-                fphase ^= 1;
+                if (me == 0) {
+                    mbar_wait(f32_empty, fphase ^ 1);
+                    mbar_expect_tx(f32_full, f32_bytes);
+                    bulk_g2s(F32, wsub + (size_t)P.plane_bytes * 2, f32_bytes, f32_full);
+                    fphase ^= 1;
+                }
                 for (int gi = 0; gi < n_gemm; ++gi) {
                     const TcGemm& g = P.g[gi];
                     const int nw = g.n < 128 ? g.n : 128;
                     const int nh = (g.n + 127) / 128;
                     const int K = g.k[0] + (g.nseg > 1 ? g.k[1] : 0);
                     for (int h = 0; h < nh; ++h) {
+                        if (h != me) continue;
                         const unsigned char* wimg = wsub + ts_off + g.w_off + (size_t)h * K * nw * 2;
                         int kbase = 0;
                         for (int sgi = 0; sgi < g.nseg; ++sgi) {
                             const int kseg = g.k[sgi];
-                            if (g.src[sgi] != SRC_H && h == 0) {
+                            if (g.src[sgi] != SRC_H && me == 0) {
                                 const __half* xt = A.ximg + tile * (int64_t)(P.kpe + P.kaux) * kTileM +
                                                    (g.src[sgi] == SRC_XAUX ? (int64_t)P.kpe * kTileM : 0);
                                 mbar_wait(xa_empty, xphase ^ 1);
@@ -200,9 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) 
                             for (int k0 = 0; k0 < kseg; k0 += kTsStageCols) {
                                 const int kc = min(kTsStageCols, kseg - k0);
                                 const uint32_t bytes = (uint32_t)(kc * nw * 2);
-                                mbar_wait(&empty[stage], phase ^ 1);
-                                mbar_expect_tx(&full[stage], bytes);
-                                bulk_g2s(ring + (size_t)stage * kTsStageBytes, wimg + (size_t)(kbase + k0) * nw * 2, bytes, &full[stage]);
+                                mbar_wait(&empty_me[stage], phase ^ 1);
+                                mbar_expect_tx(&full_me[stage], bytes);
+                                bulk_g2s(ring + (size_t)stage * kTsStageBytes, wimg + (size_t)(kbase + k0) * nw * 2, bytes, &full_me[stage]);
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
                             kbase += kseg;
@@ -211,14 +222,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) 
                 }
             }
         }
-    } else if (warp == kWarpMma) {
-        // =========================== MMA issuer (whole warp; one elected lane issues) ===========================
+    } else if (warp == kTsWarpMma0 || warp == kTsWarpMma1) {
+        // =========================== MMA issuers (whole warp; one elected lane issues) ===========================
+        const int me = warp == kTsWarpMma1 ? 1 : 0;
+        unsigned char* ring = ring_all + (size_t)me * kStages * kTsStageBytes;
+        uint64_t* full_me = full + me * (kTsMaxStages / 2);
+        uint64_t* empty_me = empty + me * (kTsMaxStages / 2);
         int stage = 0;
         uint32_t phase = 0, xphase = 0, gidx = 0;
         uint32_t fph0 = 0, fph1 = 0, rph0 = 0, rph1 = 0, rph2 = 0, rph3 = 0;
         bool used0 = false, used1 = false;
         const uint32_t xa_base = smem_u32(XA), ring_base = smem_u32(ring);
-        const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+        const uint32_t full_a = smem_u32(full_me), empty_a = smem_u32(empty_me);
         const uint32_t xa_full_a = smem_u32(xa_full), xa_empty_a = smem_u32(xa_empty);
         const uint32_t acc_full_a = smem_u32(acc_full), acc_free_a = smem_u32(acc_free), aready_a = smem_u32(aready);
         const uint64_t a_step = (uint64_t)((2 * kTileM * 16) >> 4);
@@ -233,7 +248,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) 
                 const uint64_t bd0 = make_desc(ring_base, (uint32_t)nw * 16, 128);
                 // A operand of this GEMM (written by the previous epilogue): buffer (gidx-1)&1  ==  (gidx+1)&1
                 const uint32_t a_tm = tmem_base + 256u + ((gidx + 1u) & 1u) * 128u;
+                if (nh == 1 && me == 1) {
+                    // nothing to issue for a single-half GEMM, but the shared encoding buffer is released by both issuers
+                    for (int sgi = 0; sgi < g.nseg; ++sgi)
+                        if (g.src[sgi] != SRC_H) {
+                            mbar_wait_a(xa_full_a, xphase);
+                            xphase ^= 1;
+                            commit_elect(xa_empty_a);
+                        }
+                    continue;
+                }
                 for (int h = 0; h < nh; ++h) {
+                    if (h != me) continue;
                     // accumulator half h must have been drained by the previous epilogue that used it
                     if (h == 0) { if (used0) { mbar_wait_a(acc_free_a, fph0); fph0 ^= 1; } used0 = true; }
                     else        { if (used1) { mbar_wait_a(acc_free_a + 8, fph1); fph1 ^= 1; } used1 = true; }
@@ -243,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) 
                     for (int sgi = 0; sgi < g.nseg; ++sgi) {
                         const int kseg = g.k[sgi];
                         const bool from_x = g.src[sgi] != SRC_H;
-                        if (from_x && h == 0) {
+                        if (from_x) {
                             mbar_wait_a(xa_full_a, xphase);
                             xphase ^= 1;
                             tc_fence_after();
@@ -260,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) 
                             if (st1 == kStages) { st1 = 0; ph1 ^= 1; }
                             const uint32_t f0 = full_a + 8u * (uint32_t)st0, f1 = two ? full_a + 8u * (uint32_t)st1 : f0;
                             const uint32_t fp1 = two ? ph1 : ph0;
-                            if (!from_x && h == 0) {
+                            if (!from_x) {
                                 // K-slabs k0/64 (and the next one) of the A operand have been published by the previous epilogue
                                 const int s0 = k0 >> 6;
                                 const uint32_t r0 = s0 == 0 ? rph0 : rph2;      // s0 is 0 or 2
@@ -290,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) 
                             if (two) { stage = st1; phase = ph1; }
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
-                        if (from_x && h == nh - 1) commit_elect(xa_empty_a);
+                        if (from_x) commit_elect(xa_empty_a);
                     }
                     commit_elect(acc_full_a + 8u * (uint32_t)h);
                 }
@@ -415,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_ts_kernel(const TcArgs A) 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kWarpProd) {
+    if (warp == kTsWarpProd0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }
 }
