@@ -250,12 +250,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_mlp_ts_kernel(const TcArgs A
                 const uint32_t a_tm = tmem_base + 256u + ((gidx + 1u) & 1u) * 128u;
                 if (nh == 1 && me == 1) {
                     // nothing to issue for a single-half GEMM, but the shared encoding buffer is released by both issuers
-                    for (int sgi = 0; sgi < g.nseg; ++sgi)
+                    for (int sgi = 0; sgi < g.nseg; ++sgi) {
                         if (g.src[sgi] != SRC_H) {
                             mbar_wait_a(xa_full_a, xphase);
                             xphase ^= 1;
                             commit_elect(xa_empty_a);
+                        } else {
+                            // keep this warp's parities of the A-slab barriers in step with the publications it skips
+                            const int ns = (g.k[sgi] + 63) >> 6;
+                            if (ns > 0) rph0 ^= 1;
+                            if (ns > 1) rph1 ^= 1;
+                            if (ns > 2) rph2 ^= 1;
+                            if (ns > 3) rph3 ^= 1;
                         }
+                    }
                     continue;
                 }
                 for (int h = 0; h < nh; ++h) {

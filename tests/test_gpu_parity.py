@@ -116,6 +116,21 @@ def test_nerf_large_batch_matches_oracle():
     assert relerr(product_net(net)(x.to(DEV)), ref) <= 1e-5
 
 
+@pytest.mark.parametrize('prec', PRECS)
+def test_nerf_many_tiles_per_cta(prec):
+    """More 128-row tiles than 3 x 148 SMs: exercises the persistent kernels' tile loop, barrier parities across
+    tiles and the ragged last tile."""
+    M().set_precision(prec)
+    spec = O.NerfSpec()
+    net = O.make_net('nerf', spec, seed=4)
+    n = 148 * 128 * 3 + 77
+    x = C.nerf_rows(spec, n, 13)
+    with torch.inference_mode():
+        ref = O.nerf_forward(spec, net.weights[0], x)
+    out = product_net(net)(x.to(DEV))
+    assert relerr(out, ref) <= MLP_TOL[prec]
+
+
 @pytest.mark.parametrize('mname', list(C.MEGA_VARIANTS))
 def test_router(golden, mname):
     import ctypes as Ct
