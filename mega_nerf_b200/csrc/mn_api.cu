@@ -232,8 +232,8 @@ int mn_model_set_weights(mn_model* m, int sub, const mn_nerf_weights* w, void* s
 }
 
 static int64_t slot_capacity(const mn_model* m, int64_t B) {
-    if (m->d.kind != 2) return mn_cdiv(B, MN_TILE) * MN_TILE;
-    return mn_cdiv(B * m->max_multiplicity, MN_TILE) * MN_TILE + (int64_t)m->d.n_sub * MN_TILE;
+    if (m->d.kind != 2) return mn_cdiv(B, MN_BUCKET) * MN_BUCKET;
+    return mn_cdiv(B * m->max_multiplicity, MN_BUCKET) * MN_BUCKET + (int64_t)m->d.n_sub * MN_BUCKET;
 }
 
 size_t mn_model_workspace_bytes(const mn_model* m, int64_t B, int precision) {

@@ -1057,6 +1057,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
 }
 
 #include "mn_mlp_ts.cuh"
+#include "mn_mlp_c2.cuh"
 
 }  // namespace
 
@@ -1077,7 +1078,8 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
     const NetDims& nd = m->nd;
     // [hi plane][lo plane][fp32 block, 256-aligned][half-major hi plane for the TS kernel]
     const size_t ts_off = (size_t)P.plane_bytes * 2 + (size_t)(((P.f32_floats * 4 + 255) / 256) * 256);
-    const size_t sub_bytes = mn_align(ts_off + (size_t)P.plane_bytes, 256);
+    const size_t c2_off = ts_off + (size_t)P.plane_bytes;      // [N-half of CTA 0][N-half of CTA 1] images for cta_group::2
+    const size_t sub_bytes = mn_align(c2_off + (size_t)P.plane_bytes, 256);
     if (!m->tc_packed) {
         MN_CUDA(ctx, cudaMalloc(&m->tc_packed, sub_bytes * m->d.n_sub));
         MN_CUDA(ctx, cudaMemsetAsync(m->tc_packed, 0, sub_bytes * m->d.n_sub, st));
@@ -1096,6 +1098,9 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         MN_LAUNCH_CHECK(ctx);
         tc_pack_half_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, g.n < 128 ? g.n : 128, k_real0, k_pad0,
                                                                     reinterpret_cast<__half*>(base + ts_off + g.w_off));
+        MN_LAUNCH_CHECK(ctx);
+        tc_pack_half_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, g.n / 2, k_real0, k_pad0,
+                                                                    reinterpret_cast<__half*>(base + c2_off + g.w_off));
         MN_LAUNCH_CHECK(ctx);
         tc_pack_f32_kernel<<<1, 256, 0, st>>>(bias, n_bias, f32 + g.bias_off, 256);
         MN_LAUNCH_CHECK(ctx);
@@ -1180,8 +1185,22 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
             const char* e = getenv("MN_TC_TS");
             use_ts = (e && e[0] == '1') ? 1 : 0;
         }
+        static int use_c2 = -1;
+        if (use_c2 < 0) {
+            const char* e = getenv("MN_TC_C2");
+            use_c2 = (e && e[0] == '1') ? 1 : 0;
+        }
         const PPLayout PL = pp_layout(P, bias_global != 0);
         const TsLayout TL = ts_layout(P);
+        const C2Layout CL = c2_layout(P);
+        if (use_c2 && CL.total <= kSmemMax && (n_tiles128 % 2) == 0) {
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL.total));
+            int64_t n_super = n_tiles128 / 2;
+            int64_t n_cl = (n_super + 1) / 2 < ctx->sm_count / 2 ? (n_super + 1) / 2 : ctx->sm_count / 2;
+            if (n_cl < 1) n_cl = 1;
+            mn_prof_begin(ctx, st);
+            tc_mlp_c2_kernel<<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A);
+        } else
         if (use_ts && P.L % 128 == 0 && TL.stages >= 4) {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL.total));
             mn_prof_begin(ctx, st);

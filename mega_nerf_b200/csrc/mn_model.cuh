@@ -4,7 +4,8 @@
 
 #define MN_MAX_LAYERS 16
 #define MN_MAX_SUB 64
-#define MN_TILE 128   // slot-space bucket alignment == rows of one tensor-core MLP tile
+#define MN_TILE 128     // rows of one tensor-core MLP tile
+#define MN_BUCKET 256   // slot-space bucket alignment: a CTA pair (cta_group::2, 2 x 128 rows) never mixes sub-modules
 
 // Offsets (in floats) of each packed tensor inside one sub-module's fp32 buffer.  All matrices are
 // stored K-major ("transposed": Wt[k][n] = W[n][k]) so that consecutive output channels are contiguous.

@@ -91,7 +91,7 @@ __global__ void route_scan_kernel(int* counters, int K) {
             counters[CNT_START + k] = off;
             const int c = counters[CNT_COUNT + k];
             pairs += c;
-            off += (c + MN_TILE - 1) / MN_TILE * MN_TILE;
+            off += (c + MN_BUCKET - 1) / MN_BUCKET * MN_BUCKET;
             counters[CNT_CURSOR + k] = 0;
         }
         counters[CNT_START + K] = off;
