@@ -117,15 +117,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
     float* F32 = reinterpret_cast<float*>(smem + SL.f32);
     float* SIGP = reinterpret_cast<float*>(smem + SL.sigp);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bars);
-    uint64_t* full = bars;            // [3]   (leader's copies are the live ones)
-    uint64_t* empty = bars + 4;       // [3]   per CTA
-    uint64_t* xa_full = bars + 8;     //       leader's
-    uint64_t* xa_empty = bars + 9;    //       per CTA
-    uint64_t* acc_full = bars + 10;   // [2]   per CTA
-    uint64_t* epi_done = bars + 12;   // [2]   leader's
-    uint64_t* f32_full = bars + 14;   // [2]   per CTA
-    uint64_t* f32_empty = bars + 16;  // [2]   per CTA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* full = bars;            // [3]   per CTA: this CTA's weight-half has landed
+    uint64_t* empty = bars + 3;       // [3]   per CTA (released by the leader's multicast commit)
+    uint64_t* pfull = bars + 6;       // [3]   leader's: the PEER's weight-half has landed (relayed by the peer's warp 17)
+    uint64_t* xa_full = bars + 9;     //       per CTA
+    uint64_t* xa_empty = bars + 10;   //       per CTA
+    uint64_t* pxa_full = bars + 11;   //       leader's: relayed
+    uint64_t* acc_full = bars + 12;   // [2]   per CTA
+    uint64_t* epi_done = bars + 14;   // [2]   leader's
+    uint64_t* f32_full = bars + 16;   // [2]   per CTA
+    uint64_t* f32_empty = bars + 18;  // [2]   per CTA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -140,9 +142,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
     const int64_t stride2 = 2 * ncl;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kC2Stages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
-        mbar_init(xa_full, 2);
+        for (int i = 0; i < kC2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&pfull[i], 1); }
+        mbar_init(xa_full, 1);
         mbar_init(xa_empty, 1);
+        mbar_init(pxa_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&epi_done[i], 2 * kEpiWarps);
@@ -178,7 +181,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
             int stage = 0;
             uint32_t phase = 0, xphase = 0, fph[2] = {0, 0};
             const uint32_t f32_bytes = (uint32_t)SL.f32_stride;
-            const uint32_t full_l = mapa_u32(smem_u32(full), 0), xa_full_l = mapa_u32(smem_u32(xa_full), 0);   // leader's barriers
             for (int64_t t0 = cl; t0 < n_super; t0 += stride2) {
                 const int64_t sup[2] = {t0, t0 + ncl};
                 const unsigned char* wsub[2] = {nullptr, nullptr};
@@ -206,17 +208,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
                                 const __half* xt = A.ximg + my_tile * (int64_t)(P.kpe + P.kaux) * kTileM +
                                                    (g.src[sgi] == SRC_XAUX ? (int64_t)P.kpe * kTileM : 0);
                                 mbar_wait(xa_empty, xphase ^ 1);
-                                mbar_expect_tx_cluster(xa_full_l, (uint32_t)(kseg * kTileM * 2));
-                                bulk_g2s_cbar(XA, xt, (uint32_t)(kseg * kTileM * 2), xa_full_l);
+                                mbar_expect_tx(xa_full, (uint32_t)(kseg * kTileM * 2));
+                                bulk_g2s(XA, xt, (uint32_t)(kseg * kTileM * 2), xa_full);
                                 xphase ^= 1;
                             }
                             for (int k0 = 0; k0 < kseg; k0 += kC2StageCols) {
                                 const int kc = min(kC2StageCols, kseg - k0);
                                 const uint32_t bytes = (uint32_t)(kc * nhalf * 2);
                                 mbar_wait(&empty[stage], phase ^ 1);
-                                mbar_expect_tx_cluster(full_l + 8u * (uint32_t)stage, bytes);
-                                bulk_g2s_cbar(ring + (size_t)stage * kC2StageBytes, wimg + (size_t)(kbase + k0) * nhalf * 2, bytes,
-                                              full_l + 8u * (uint32_t)stage);
+                                mbar_expect_tx(&full[stage], bytes);
+                                bulk_g2s(ring + (size_t)stage * kC2StageBytes, wimg + (size_t)(kbase + k0) * nhalf * 2, bytes, &full[stage]);
                                 if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
                             }
                             kbase += kseg;
@@ -232,8 +233,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
             uint32_t phase = 0, xphase = 0, eph0 = 0, eph1 = 0;
             bool started0 = false, started1 = false;
             const uint32_t h_base = smem_u32(Hs), xa_base = smem_u32(XA), ring_base = smem_u32(ring);
-            const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
-            const uint32_t xa_full_a = smem_u32(xa_full), xa_empty_a = smem_u32(xa_empty);
+            const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), pfull_a = smem_u32(pfull);
+            const uint32_t xa_full_a = smem_u32(xa_full), xa_empty_a = smem_u32(xa_empty), pxa_full_a = smem_u32(pxa_full);
             const uint32_t acc_full_a = smem_u32(acc_full), epi_done_a = smem_u32(epi_done);
             const uint64_t a_step = (uint64_t)((2 * kTileM * 16) >> 4);
             const uint64_t st_step = (uint64_t)(kC2StageBytes >> 4);
@@ -258,12 +259,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
                             const bool from_x = g.src[sgi] != SRC_H;
                             uint64_t ad = make_desc(from_x ? xa_base : h_base + (uint32_t)(sl * h_bytes), kTileM * 16, 128);
                             if (from_x) {
-                                mbar_wait_cluster(xa_full_a, xphase);
+                                mbar_wait_a(xa_full_a, xphase);
+                                mbar_wait_cluster(pxa_full_a, xphase);
                                 xphase ^= 1;
                             }
                             for (int k0 = 0; k0 < kseg; k0 += kC2StageCols) {
                                 const int kc = min(kC2StageCols, kseg - k0);
-                                mbar_wait_cluster(full_a + 8u * (uint32_t)stage, phase);
+                                mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
+                                mbar_wait_cluster(pfull_a + 8u * (uint32_t)stage, phase);
                                 tc_fence_after();
                                 c2_stage(d_tmem, ad, a_step, bd0 + (uint64_t)stage * st_step, b_step, idesc, accum, kc >> 4,
                                          empty_a + 8u * (uint32_t)stage);
@@ -274,6 +277,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
                             if (from_x) c2_commit_both(xa_empty_a);
                         }
                         c2_commit_both(acc_full_a + 8u * (uint32_t)sl);
+                    }
+                }
+            }
+        } else if (lane == 0) {
+            // peer CTA: relay "my half of this stage has landed" to the leader, in the exact consumption order
+            int stage = 0;
+            uint32_t phase = 0, xphase = 0;
+            const uint32_t pfull_l = mapa_u32(smem_u32(pfull), 0), pxa_full_l = mapa_u32(smem_u32(pxa_full), 0);
+            for (int64_t t0 = cl; t0 < n_super; t0 += stride2) {
+                const bool valid1 = t0 + ncl < n_super;
+                for (int gi = 0; gi < n_gemm; ++gi) {
+                    const TcGemm& g = P.g[gi];
+                    for (int sl = 0; sl < 2; ++sl) {
+                        if (sl == 1 && !valid1) continue;
+                        for (int sgi = 0; sgi < g.nseg; ++sgi) {
+                            const int kseg = g.k[sgi];
+                            if (g.src[sgi] != SRC_H) {
+                                mbar_wait(xa_full, xphase);
+                                xphase ^= 1;
+                                mbar_arrive_cluster(pxa_full_l);
+                            }
+                            for (int k0 = 0; k0 < kseg; k0 += kC2StageCols) {
+                                mbar_wait(&full[stage], phase);
+                                mbar_arrive_cluster(pfull_l + 8u * (uint32_t)stage);
+                                if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
+                            }
+                        }
                     }
                 }
             }
