@@ -23,6 +23,20 @@
 namespace {
 
 constexpr int kTileM = 128;
+
+// Optional in-kernel timeline (MN_TC_TRACE=1): CTA 0 records (event, tile-slot, gemm, clock) tuples.
+__device__ unsigned long long g_trace[4 * 4096];
+__device__ unsigned int g_trace_n[2];
+__device__ __forceinline__ void trace_ev(int on, int who, int ev, int sl, int gi) {
+    if (!on || blockIdx.x != 0) return;
+    const unsigned int i = atomicAdd(&g_trace_n[who], 1u);
+    if (i < 2048) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[(who * 2048 + i) * 2 + 0] = ((unsigned long long)ev << 32) | ((unsigned long long)sl << 16) | (unsigned long long)gi;
+        g_trace[(who * 2048 + i) * 2 + 1] = t;
+    }
+}
 constexpr int kMaxStages = 4;
 // weight ring geometry: single pass = 3 stages x 64 K-columns (32 KiB); split mode (H holds hi+lo planes) = 4 x 32 columns
 __host__ __device__ constexpr int ring_slab_cols(bool split) { return split ? 32 : 64; }
@@ -402,7 +416,7 @@ struct TcArgs {
     const __half* ximg;           // feature tiles (hi plane; lo plane at +x_plane_halves)
     int64_t x_plane_halves;
     int split;                    // 1: three MMA passes (hi*hi + hi*lo + lo*hi)
-    int desc_swap;                // debug: swap LBO / SBO roles
+    int desc_swap;                // debug: 1 = record the in-kernel timeline (MN_TC_TRACE)
     int64_t n_tiles_cap;
 };
 
@@ -915,6 +929,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                     if (sl == 0) { if (started0) { mbar_wait_a(epi_done_a, eph0); eph0 ^= 1; } started0 = true; }
                     else         { if (started1) { mbar_wait_a(epi_done_a + 8, eph1); eph1 ^= 1; } started1 = true; }
                     tc_fence_after();
+                    if (lane == 0) trace_ev(A.desc_swap, 0, 1, sl, gi);          // MMA: dependencies satisfied, start issuing
                     const uint32_t d_tmem = tmem_base + (uint32_t)sl * 256u;
                     uint32_t accum = 0;
                     for (int sgi = 0; sgi < g.nseg; ++sgi) {
@@ -939,6 +954,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                         if (from_x) commit_elect(xa_empty_a);
                     }
                     commit_elect(acc_full_a + 8u * (uint32_t)sl);
+                    if (lane == 0) trace_ev(A.desc_swap, 0, 2, sl, gi);          // MMA: all MMAs of this GEMM issued
                 }
             }
         }
@@ -976,6 +992,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                     if (sl == 0) { mbar_wait(&acc_full[0], aph0); aph0 ^= 1; }
                     else         { mbar_wait(&acc_full[1], aph1); aph1 ^= 1; }
                     tc_fence_after();
+                    if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 3, sl, gi);   // epilogue: accumulator ready
                     const uint32_t t_acc = t_lane + (uint32_t)sl * 256u;
                     const float* Fb = fb_[sl];
                     const float* bias = Fb + g.bias_off;
@@ -1039,6 +1056,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                     }
                     tc_fence_before();
                     __syncwarp();
+                    if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 4, sl, gi);   // epilogue: this warp done
                     if (lane == 0) mbar_arrive(&epi_done[sl]);
                 }
             }
@@ -1144,7 +1162,7 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     A.split = split;
     static int desc_swap = -1;
     if (desc_swap < 0) {
-        const char* e = getenv("MN_TC_DESC_SWAP");
+        const char* e = getenv("MN_TC_TRACE");
         desc_swap = (e && e[0] == '1') ? 1 : 0;
     }
     A.desc_swap = desc_swap;
@@ -1225,4 +1243,15 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     mn_prof_end(ctx, st);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
+}
+
+extern "C" int mn_debug_read_trace(unsigned long long* out, unsigned int* counts, int reset) {
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 4 * 4096);
+    if (counts) cudaMemcpyFromSymbol(counts, g_trace_n, sizeof(unsigned int) * 2);
+    if (reset) {
+        unsigned int z[2] = {0, 0};
+        cudaMemcpyToSymbol(g_trace_n, z, sizeof(z));
+    }
+    return 0;
 }
