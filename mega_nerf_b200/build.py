@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write('\n'.join(log))
             raise RuntimeError(f'nvcc failed on {src}')
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcuda']
+    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

@@ -107,7 +107,17 @@ __device__ __forceinline__ uint32_t make_idesc_m(int m, int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_c2_kernel(const TcArgs A) {
+// 2-D tensor TMA (rows of 256 B) into THIS CTA's shared memory; with .cta_group::2 the completion may be signalled on
+// the peer CTA's mbarrier (cluster address), which the non-tensor bulk copy cannot do.
+__device__ __forceinline__ void tma2d_c2(uint32_t dst_smem, const CUtensorMap* tm, int row, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst_smem), "l"(tm), "r"(0), "r"(row), "r"(bar_cluster_addr)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    tc_mlp_c2_kernel(const TcArgs A, const __grid_constant__ CUtensorMap tm_big, const __grid_constant__ CUtensorMap tm_small) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
     const C2Layout SL = c2_layout(P);
@@ -142,7 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
     const int64_t stride2 = 2 * ncl;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kC2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&pfull[i], 1); }
+        for (int i = 0; i < kC2Stages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); mbar_init(&pfull[i], 1); }
         mbar_init(xa_full, 1);
         mbar_init(xa_empty, 1);
         mbar_init(pxa_full, 1);
@@ -181,6 +191,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
             int stage = 0;
             uint32_t phase = 0, xphase = 0, fph[2] = {0, 0};
             const uint32_t f32_bytes = (uint32_t)SL.f32_stride;
+            const uint32_t full_l = mapa_u32(smem_u32(full), 0);          // the LEADER's full[] barriers count both weight halves
+            const uint32_t ring_a = smem_u32(ring);
             for (int64_t t0 = cl; t0 < n_super; t0 += stride2) {
                 const int64_t sup[2] = {t0, t0 + ncl};
                 const unsigned char* wsub[2] = {nullptr, nullptr};
@@ -216,8 +228,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
                                 const int kc = min(kC2StageCols, kseg - k0);
                                 const uint32_t bytes = (uint32_t)(kc * nhalf * 2);
                                 mbar_wait(&empty[stage], phase ^ 1);
-                                mbar_expect_tx(&full[stage], bytes);
-                                bulk_g2s(ring + (size_t)stage * kC2StageBytes, wimg + (size_t)(kbase + k0) * nhalf * 2, bytes, &full[stage]);
+                                mbar_expect_tx_cluster(full_l + 8u * (uint32_t)stage, bytes);
+                                const int row0 = (int)((size_t)((wimg + (size_t)(kbase + k0) * nhalf * 2) - A.wpack) >> 8);
+                                const uint32_t dst = ring_a + (uint32_t)stage * kC2StageBytes;
+                                if (bytes == 16384u) {
+                                    tma2d_c2(dst, &tm_big, row0, full_l + 8u * (uint32_t)stage);
+                                } else {
+                                    for (uint32_t b = 0; b < bytes; b += 2048u)
+                                        tma2d_c2(dst + b, &tm_small, row0 + (int)(b >> 8), full_l + 8u * (uint32_t)stage);
+                                }
                                 if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
                             }
                             kbase += kseg;
@@ -265,8 +284,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
                             }
                             for (int k0 = 0; k0 < kseg; k0 += kC2StageCols) {
                                 const int kc = min(kC2StageCols, kseg - k0);
-                                mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
-                                mbar_wait_cluster(pfull_a + 8u * (uint32_t)stage, phase);
+                                mbar_wait_cluster(full_a + 8u * (uint32_t)stage, phase);
                                 tc_fence_after();
                                 c2_stage(d_tmem, ad, a_step, bd0 + (uint64_t)stage * st_step, b_step, idesc, accum, kc >> 4,
                                          empty_a + 8u * (uint32_t)stage);
@@ -282,9 +300,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
             }
         } else if (lane == 0) {
             // peer CTA: relay "my half of this stage has landed" to the leader, in the exact consumption order
-            int stage = 0;
-            uint32_t phase = 0, xphase = 0;
-            const uint32_t pfull_l = mapa_u32(smem_u32(pfull), 0), pxa_full_l = mapa_u32(smem_u32(pxa_full), 0);
+            uint32_t xphase = 0;
+            const uint32_t pxa_full_l = mapa_u32(smem_u32(pxa_full), 0);
             for (int64_t t0 = cl; t0 < n_super; t0 += stride2) {
                 const bool valid1 = t0 + ncl < n_super;
                 for (int gi = 0; gi < n_gemm; ++gi) {
@@ -297,11 +314,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_mlp_
                                 mbar_wait(xa_full, xphase);
                                 xphase ^= 1;
                                 mbar_arrive_cluster(pxa_full_l);
-                            }
-                            for (int k0 = 0; k0 < kseg; k0 += kC2StageCols) {
-                                mbar_wait(&full[stage], phase);
-                                mbar_arrive_cluster(pfull_l + 8u * (uint32_t)stage);
-                                if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
                             }
                         }
                     }

@@ -14,6 +14,7 @@
 // i.e. [K/8][R][8] fp16.  UMMA descriptor: LBO = R*16 (next 8-column chunk), SBO = 128 (next 8-row group).
 // The epilogue's per-row 16-byte stores and the packer's images are contiguous in this layout, any K that
 // is a multiple of 16 works, and no TMA tensor map is needed (plain 1-D bulk copies).
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -1102,6 +1103,29 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         MN_CUDA(ctx, cudaMalloc(&m->tc_packed, sub_bytes * m->d.n_sub));
         MN_CUDA(ctx, cudaMemsetAsync(m->tc_packed, 0, sub_bytes * m->d.n_sub, st));
         m->tc_sub_bytes = sub_bytes;
+        // tensor maps for the cta_group::2 kernel (its TMA loads must be the .tensor form to signal the peer CTA's barrier)
+        const cuuint64_t rows = (cuuint64_t)(sub_bytes * m->d.n_sub / 256);
+        const cuuint64_t gdim[2] = {256, rows};
+        const cuuint64_t gstride[1] = {256};
+        const cuuint32_t estr[2] = {1, 1};
+        const cuuint32_t box_big[2] = {256, 64}, box_small[2] = {256, 8};
+        // resolved through the runtime so that the library does not link against libcuda (it must load on GPU-less hosts)
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUresult r1 = CUDA_ERROR_NOT_FOUND, r2 = CUDA_ERROR_NOT_FOUND;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn) {
+            EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
+            r1 = enc(reinterpret_cast<CUtensorMap*>(m->tmap_big), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, m->tc_packed, gdim, gstride, box_big, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            r2 = enc(reinterpret_cast<CUtensorMap*>(m->tmap_small), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, m->tc_packed, gdim, gstride, box_small, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        m->tmap_ready = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) ? 1 : 0;
     }
     unsigned char* base = (unsigned char*)m->tc_packed + (size_t)sub * sub_bytes;
     const float* Pk = m->packed + (size_t)sub * m->lay.total;
@@ -1211,13 +1235,14 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         const PPLayout PL = pp_layout(P, bias_global != 0);
         const TsLayout TL = ts_layout(P);
         const C2Layout CL = c2_layout(P);
-        if (use_c2 && CL.total <= kSmemMax && (n_tiles128 % 2) == 0) {
+        if (use_c2 && m->tmap_ready && CL.total <= kSmemMax && (n_tiles128 % 2) == 0) {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL.total));
             int64_t n_super = n_tiles128 / 2;
             int64_t n_cl = (n_super + 1) / 2 < ctx->sm_count / 2 ? (n_super + 1) / 2 : ctx->sm_count / 2;
             if (n_cl < 1) n_cl = 1;
             mn_prof_begin(ctx, st);
-            tc_mlp_c2_kernel<<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A);
+            tc_mlp_c2_kernel<<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A, *reinterpret_cast<const CUtensorMap*>(m->tmap_big),
+                                                                            *reinterpret_cast<const CUtensorMap*>(m->tmap_small));
         } else
         if (use_ts && P.L % 128 == 0 && TL.stages >= 4) {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL.total));
