@@ -776,19 +776,22 @@ constexpr int kPPSlabCols = 32;
 constexpr int kPPStageBytes = kPPSlabCols * 256 * 2;
 
 struct PPLayout {
-    int ring, h, xa, f32, f32_stride, sigp, bars, total;
+    int ring, h, xa, f32, f32_stride, sigp, bars, total, stages;
 };
 
 __host__ __device__ inline PPLayout pp_layout(const TcPlan& p, bool bias_global) {
     PPLayout s;
-    const int kPPStages = bias_global ? 4 : 3;
+    const int kx0 = p.kpe > p.kaux ? p.kpe : p.kaux;
+    const int fixed = 2 * p.L * kTileM * 2 + kx0 * kTileM * 2 + (bias_global ? 0 : ((p.f32_floats * 4 + 15) / 16) * 16) + 2048 + 256;
+    const int kPPStages = (kSmemMax - fixed) / kPPStageBytes >= 4 ? 4 : 3;
     const int kx = p.kpe > p.kaux ? p.kpe : p.kaux;
+    s.stages = kPPStages;
     s.ring = 0;
     s.h = kPPStages * kPPStageBytes;
     s.xa = s.h + 2 * p.L * kTileM * 2;
     s.f32 = s.xa + kx * kTileM * 2;
     s.f32_stride = ((p.f32_floats * 4 + 15) / 16) * 16;
-    s.sigp = s.f32 + (bias_global ? 0 : 2 * s.f32_stride);
+    s.sigp = s.f32 + (bias_global ? 0 : s.f32_stride);    // ONE block: both tiles of a pair belong to the same sub-module
     s.bars = s.sigp + 2048;
     s.total = s.bars + 256;
     return s;
@@ -798,10 +801,10 @@ __host__ __device__ inline PPLayout pp_layout(const TcPlan& p, bool bias_global)
 // staged in shared memory; the 24 KiB saved buy a fourth weight-ring stage.
 template <bool kBiasGlobal>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) {
-    constexpr int kPPStages = kBiasGlobal ? 4 : 3;
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
     const PPLayout SL = pp_layout(P, kBiasGlobal);
+    const int kPPStages = SL.stages;
     unsigned char* ring = smem + SL.ring;
     unsigned char* Hs = smem + SL.h;
     unsigned char* XA = smem + SL.xa;
@@ -825,7 +828,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     const int h_bytes = P.L * kTileM * 2;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kPPStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kPPMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(xa_full, 1);
         mbar_init(xa_empty, 1);
         for (int i = 0; i < 2; ++i) {
@@ -854,7 +857,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
         }
         return sub;
     };
-    const int64_t stride2 = 2 * (int64_t)gridDim.x;
+    // a CTA works on PAIRS of adjacent tiles (2p, 2p+1): buckets are 256-row aligned, so both belong to one sub-module
+    const int64_t n_pairs = (n_tiles + 1) / 2;
 
     if (warp == kWarpProd) {
         // =========================== TMA producer ===========================
@@ -862,18 +866,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
             int stage = 0;
             uint32_t phase = 0, xphase = 0, fph[2] = {0, 0};
             const uint32_t f32_bytes = (uint32_t)SL.f32_stride;
-            for (int64_t t0 = blockIdx.x; t0 < n_tiles; t0 += stride2) {
-                const int64_t tiles[2] = {t0, t0 + gridDim.x};
+            for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+            const int64_t t0 = 2 * pr;
+                const int64_t tiles[2] = {t0, t0 + 1};
                 const unsigned char* wsub[2] = {nullptr, nullptr};
                 for (int sl = 0; sl < 2; ++sl) {
                     if (tiles[sl] >= n_tiles) continue;
                     wsub[sl] = A.wpack + (size_t)sub_of(tiles[sl]) * P.sub_bytes;
-                    if (kBiasGlobal) continue;
-                    mbar_wait(&f32_empty[sl], fph[sl] ^ 1);
-                    mbar_expect_tx(&f32_full[sl], f32_bytes);
-                    bulk_g2s(reinterpret_cast<unsigned char*>(F32) + (size_t)sl * SL.f32_stride,
-                             wsub[sl] + (size_t)P.plane_bytes * 2, f32_bytes, &f32_full[sl]);
-                    fph[sl] ^= 1;
+                    if (kBiasGlobal || sl == 1) continue;
+                    mbar_wait(&f32_empty[0], fph[0] ^ 1);
+                    mbar_expect_tx(&f32_full[0], f32_bytes);
+                    bulk_g2s(reinterpret_cast<unsigned char*>(F32), wsub[0] + (size_t)P.plane_bytes * 2, f32_bytes, &f32_full[0]);
+                    fph[0] ^= 1;
                 }
                 for (int gi = 0; gi < n_gemm; ++gi) {
                     const TcGemm& g = P.g[gi];
@@ -917,8 +921,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
         const uint32_t acc_full_a = smem_u32(acc_full), epi_done_a = smem_u32(epi_done);
         const uint64_t a_step = (uint64_t)((2 * kTileM * 16) >> 4);
         const uint64_t st_step = (uint64_t)(kPPStageBytes >> 4);
-        for (int64_t t0 = blockIdx.x; t0 < n_tiles; t0 += stride2) {
-            const bool valid1 = t0 + gridDim.x < n_tiles;
+        for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+            const int64_t t0 = 2 * pr;
+            const bool valid1 = t0 + 1 < n_tiles;
             for (int gi = 0; gi < n_gemm; ++gi) {
                 const TcGemm& g = P.g[gi];
                 const uint32_t idesc = make_idesc(g.n);
@@ -967,22 +972,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t aph0 = 0, aph1 = 0, fph0 = 0, fph1 = 0;
         const int L = P.L;
-        for (int64_t t0 = blockIdx.x; t0 < n_tiles; t0 += stride2) {
-            const bool valid1 = t0 + gridDim.x < n_tiles;
+        for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+            const int64_t t0 = 2 * pr;
+            const bool valid1 = t0 + 1 < n_tiles;
             int64_t slot_[2], row_[2] = {-1, -1};
             float sigma_[2] = {0.0f, 0.0f};
             const float* fb_[2] = {nullptr, nullptr};
             for (int sl = 0; sl < 2; ++sl) {
                 if (sl == 1 && !valid1) continue;
-                slot_[sl] = (t0 + (int64_t)sl * gridDim.x) * kTileM + r;
+                slot_[sl] = (t0 + sl) * kTileM + r;
                 if (slot_[sl] < n_slots) row_[sl] = A.m.slot_row ? (int64_t)A.m.slot_row[slot_[sl]] : slot_[sl];
                 if (kBiasGlobal) {
-                    fb_[sl] = reinterpret_cast<const float*>(A.wpack + (size_t)sub_of(t0 + (int64_t)sl * gridDim.x) * P.sub_bytes +
+                    fb_[sl] = reinterpret_cast<const float*>(A.wpack + (size_t)sub_of(t0 + sl) * P.sub_bytes +
                                                              (size_t)P.plane_bytes * 2);
                 } else {
-                    fb_[sl] = F32 + (size_t)sl * (SL.f32_stride / 4);
+                    fb_[sl] = F32;
                     if (sl == 0) { mbar_wait(&f32_full[0], fph0); fph0 ^= 1; }
-                    else         { mbar_wait(&f32_full[1], fph1); fph1 ^= 1; }
                 }
             }
             for (int gi = 0; gi < n_gemm; ++gi) {
@@ -1062,10 +1067,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                 }
             }
             __syncwarp();
-            if (lane == 0 && !kBiasGlobal) {
-                mbar_arrive(&f32_empty[0]);
-                if (valid1) mbar_arrive(&f32_empty[1]);
-            }
+            if (lane == 0 && !kBiasGlobal) mbar_arrive(&f32_empty[0]);
         }
     }
     tc_fence_before();
