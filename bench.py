@@ -260,7 +260,6 @@ def main():
     launches0 = L.mn_launch_count(h)
     ms_total = timed(step_resident, args.steps)
     launches = L.mn_launch_count(h) - launches0
-    clocks = sampler.stop() if rank == 0 else None
     samples_per_step = N_RAYS * (COARSE + FINE) * world
     value = samples_per_step * args.steps / (ms_total * 1e-3)
 
@@ -277,6 +276,7 @@ def main():
     tot_ms, n_l = C.c_double(), C.c_longlong()
     K.check(L.mn_profile_read(h, C.byref(tot_ms), C.byref(n_l)), h)
     K.check(L.mn_profile_enable(h, 0), h)
+    clocks = sampler.stop() if rank == 0 else None      # sampled over the resident, e2e and kernel-timing sections
     slots, tiles = nat.stats(dev)                # of the last (fine) pass
     rows_fine = N_RAYS * FINE
     mult = slots / rows_fine
@@ -326,10 +326,16 @@ def main():
                     'h2d_bytes_per_step': rays_pin.numel() * 4 + idx_pin.numel() * 4, 'd2h_bytes_per_step': out_pin.numel() * 4},
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': {'bound': 'tensor', 'kernel': 'tc_mlp_kernel' if args.precision != 'fp32' else 'mlp_simt_kernel',
+            'roofline': {'bound': 'tensor',
+                         'kernel': {'fp32': 'mlp_simt_kernel', 'tc_f16': 'tc_mlp_pp_kernel', 'tc_f16x3': 'tc_mlp_kernel<split>'}[args.precision],
                          'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
                          'frac_of_sustained_peak': achieved / pk['tflops_sustained'] if pk['tflops_sustained'] else None,
-                         'peak_source': pk['src'], 'traffic': None,
+                         'peak_source': pk['src'],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the fine-pass launch (4980 tiles) from
+                         # profiles/r1_tc_mlp_pp_kernel.ncu-rep; algorithmic: 40 KiB feature tile + 2 KiB outputs per tile = 209 MB
+                         'traffic': 228.6e6 if args.precision == 'tc_f16' else None,
+                         'traffic_detail': {'algorithmic_bytes_per_launch': 4980 * (40960 + 2048),
+                                            'launch': 'fine pass, 4980 tiles x 128 rows', 'source': 'ncu --set full, profiles/'},
                          'algorithmic_flops_per_row': fl_row, 'mma_passes_per_algorithmic': passes,
                          'kernel_ms_per_step': kernel_ms_per_step, 'launches_per_step': n_l.value / args.steps},
             'parity': {'max_rel_rgb_vs_oracle_256_rays': par},
