@@ -407,6 +407,93 @@ __global__ void __launch_bounds__(kTileM) tc_encode_kernel(const MlpArgs a, int 
     }
 }
 
+
+// Specialised encoder for the common network shape (compile-time channel counts): every thread builds its row's
+// channels in registers and writes the tile image straight to global memory with 16-byte stores (thread t of a
+// chunk writes bytes [t*16, t*16+16) -> fully coalesced); no shared-memory staging, no 2-byte bank-conflicted stores.
+template <int XD, int NFX, int NFD, int APP>
+__global__ void __launch_bounds__(kTileM) tc_encode_fast_kernel(const MlpArgs a, __half* __restrict__ ximg) {
+    constexpr int IN_XYZ = XD * (1 + 2 * NFX);
+    constexpr int KPE = (IN_XYZ + 15) / 16 * 16;
+    constexpr int IN_DIR = NFD > 0 ? 3 + 6 * NFD : 0;
+    constexpr int KAUX = (IN_DIR + APP + 15) / 16 * 16;
+    const int t = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t slot0 = tile * kTileM;
+    const int64_t n_slots = a.counters ? a.counters[CNT_NSLOTS] : a.B;
+    if (slot0 >= n_slots) return;
+    const int64_t slot = slot0 + t;
+    int64_t row = -1;
+    if (slot < n_slots) row = a.slot_row ? (int64_t)a.slot_row[slot] : slot;
+    uint4* out = reinterpret_cast<uint4*>(ximg + tile * (int64_t)(KPE + KAUX) * kTileM) + t;   // + chunk * kTileM
+    {
+        float v[KPE];
+#pragma unroll
+        for (int c = 0; c < KPE; ++c) v[c] = 0.0f;
+        if (row >= 0) {
+#pragma unroll
+            for (int j = 0; j < XD; ++j) {
+                const float x = a.src.xyz(row, j);
+                v[j] = x;
+#pragma unroll
+                for (int k = 0; k < NFX; ++k) {
+                    float s, c;
+                    mn_pe_sincos(x, k, &s, &c);
+                    v[XD + k * 2 * XD + j] = s;
+                    v[XD + k * 2 * XD + XD + j] = c;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < KPE / 8; ++c)
+            out[c * kTileM] = make_uint4(pack_h2(v[8 * c], v[8 * c + 1]), pack_h2(v[8 * c + 2], v[8 * c + 3]),
+                                         pack_h2(v[8 * c + 4], v[8 * c + 5]), pack_h2(v[8 * c + 6], v[8 * c + 7]));
+    }
+    if (KAUX > 0) {
+        float v[KAUX > 0 ? KAUX : 1];
+#pragma unroll
+        for (int c = 0; c < KAUX; ++c) v[c] = 0.0f;
+        if (row >= 0 && !a.sigma_only) {
+            if (NFD > 0) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float d = a.src.dir(row, j);
+                    v[j] = d;
+#pragma unroll
+                    for (int k = 0; k < NFD; ++k) {
+                        float s, c;
+                        mn_pe_sincos(d, k, &s, &c);
+                        v[3 + k * 6 + j] = s;
+                        v[3 + k * 6 + 3 + j] = c;
+                    }
+                }
+            }
+            if (APP > 0) {
+                int sub = a.fixed_sub;
+                if (a.counters) {
+                    sub = 0;
+                    while (sub + 1 < a.n_sub && slot0 >= a.counters[CNT_START + sub + 1]) ++sub;
+                }
+                int id = (int)a.src.index(row);
+                id = min(max(id, 0), a.nd.app_count - 1);
+                const float4* e4 = reinterpret_cast<const float4*>(a.packed + (size_t)sub * a.lay.total + a.lay.emb + (size_t)id * APP);
+#pragma unroll
+                for (int j = 0; j < APP / 4; ++j) {
+                    const float4 e = __ldg(e4 + j);
+                    v[IN_DIR + 4 * j + 0] = e.x;
+                    v[IN_DIR + 4 * j + 1] = e.y;
+                    v[IN_DIR + 4 * j + 2] = e.z;
+                    v[IN_DIR + 4 * j + 3] = e.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < KAUX / 8; ++c)
+            out[(KPE / 8 + c) * kTileM] = make_uint4(pack_h2(v[8 * c], v[8 * c + 1]), pack_h2(v[8 * c + 2], v[8 * c + 3]),
+                                                     pack_h2(v[8 * c + 4], v[8 * c + 5]), pack_h2(v[8 * c + 6], v[8 * c + 7]));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the MLP kernel
 // ------------------------------------------------------------------------------------------------
@@ -1202,7 +1289,13 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
 
     const size_t enc_sm = (size_t)P.x_tile_bytes * (split ? 2 : 1);
     MN_CUDA(ctx, cudaFuncSetAttribute(tc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_sm));
-    tc_encode_kernel<<<(unsigned)n_tiles128, kTileM, enc_sm, st>>>(a, P.kpe, P.kaux, split, ximg, A.x_plane_halves);
+    const NetDims& ndE = a.nd;
+    const bool fast_shape = !split && ndE.xyz_dim == 3 && ndE.nf_xyz == 12 && ndE.nf_dir == 4 && ndE.app == 48 && ndE.app_in_dira &&
+                            (m->lay.emb % 4) == 0;
+    if (fast_shape)
+        tc_encode_fast_kernel<3, 12, 4, 48><<<(unsigned)n_tiles128, kTileM, 0, st>>>(a, ximg);
+    else
+        tc_encode_kernel<<<(unsigned)n_tiles128, kTileM, enc_sm, st>>>(a, P.kpe, P.kaux, split, ximg, A.x_plane_halves);
     MN_LAUNCH_CHECK(ctx);
 
     const SmemLayout SL = smem_layout(P, split != 0);

@@ -10,12 +10,15 @@
 
 namespace {
 
+template <int KMAX>
 __device__ __forceinline__ void distances(const RowSrc& src, int64_t row, const float* __restrict__ cent, int K,
                                           int s, bool direct, float* d) {
     float x[3];
     for (int j = s; j < 3; ++j) x[j] = src.route_xyz(row, j);
     if (direct) {
-        for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k >= K) break;
             float acc = 0.0f;
             for (int j = s; j < 3; ++j) {
                 const float t = x[j] - cent[k * 3 + j];
@@ -27,7 +30,9 @@ __device__ __forceinline__ void distances(const RowSrc& src, int64_t row, const 
     }
     float xn = x[s] * x[s];
     for (int j = s + 1; j < 3; ++j) xn = xn + x[j] * x[j];
-    for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k >= K) break;
         float cn = cent[k * 3 + s] * cent[k * 3 + s];
         for (int j = s + 1; j < 3; ++j) cn = cn + cent[k * 3 + j] * cent[k * 3 + j];
         float acc = 0.0f;
@@ -39,28 +44,37 @@ __device__ __forceinline__ void distances(const RowSrc& src, int64_t row, const 
 }
 
 // -> number of active sub-modules; mask bits; for margin > 1 the normalised weights in w[]
+template <int KMAX>
 __device__ __forceinline__ uint64_t route_row(const float* d, int K, float margin, float* w) {
     float dmin = d[0];
     int amin = 0;
-    for (int k = 1; k < K; ++k)
-        if (d[k] < dmin) { dmin = d[k]; amin = k; }
+#pragma unroll
+    for (int k = 1; k < KMAX; ++k)
+        if (k < K && d[k] < dmin) { dmin = d[k]; amin = k; }
     if (!(margin > 1.0f)) return 1ull << amin;
     uint64_t mask = 0;
     float sum = 0.0f;
     const float thr = margin * dmin;
-    for (int k = 0; k < K; ++k) {
-        float inv = 1.0f / (d[k] + 1e-8f);
-        if (d[k] > thr) inv = 0.0f;
-        w[k] = inv;
-        sum = sum + inv;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+            float inv = 1.0f / (d[k] + 1e-8f);
+            if (d[k] > thr) inv = 0.0f;
+            w[k] = inv;
+            sum = sum + inv;
+        }
     }
-    for (int k = 0; k < K; ++k) {
-        w[k] = w[k] / sum;
-        if (w[k] > 0.0f) mask |= 1ull << k;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+            w[k] = w[k] / sum;
+            if (w[k] > 0.0f) mask |= 1ull << k;
+        }
     }
     return mask;
 }
 
+template <int KMAX>
 __global__ void route_count_kernel(RowSrc src, int64_t B, const float* __restrict__ cent, int K, int s, float margin,
                                    int direct, int* counters) {
     __shared__ int hist[MN_MAX_SUB];
@@ -71,11 +85,13 @@ __global__ void route_count_kernel(RowSrc src, int64_t B, const float* __restric
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t mask = 0;
     if (row < B) {
-        float d[MN_MAX_SUB], w[MN_MAX_SUB];
-        distances(src, row, sc, K, s, direct, d);
-        mask = route_row(d, K, margin, w);
+        float d[KMAX], w[KMAX];
+        distances<KMAX>(src, row, sc, K, s, direct, d);
+        mask = route_row<KMAX>(d, K, margin, w);
     }
-    for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k >= K) break;
         const unsigned b = __ballot_sync(0xffffffffu, (mask >> k) & 1);
         if ((threadIdx.x & 31) == 0 && b) atomicAdd(&hist[k], __popc(b));
     }
@@ -100,6 +116,7 @@ __global__ void route_scan_kernel(int* counters, int K) {
     }
 }
 
+template <int KMAX>
 __global__ void route_scatter_kernel(RowSrc src, int64_t B, const float* __restrict__ cent, int K, int s, float margin,
                                      int direct, int* counters, int64_t cap, int* slot_row, float* slot_w,
                                      int* row_slots, unsigned int* status) {
@@ -109,13 +126,15 @@ __global__ void route_scatter_kernel(RowSrc src, int64_t B, const float* __restr
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     uint64_t mask = 0;
-    float w[MN_MAX_SUB];
+    float w[KMAX];
     if (row < B) {
-        float d[MN_MAX_SUB];
-        distances(src, row, sc, K, s, direct, d);
-        mask = route_row(d, K, margin, w);
+        float d[KMAX];
+        distances<KMAX>(src, row, sc, K, s, direct, d);
+        mask = route_row<KMAX>(d, K, margin, w);
     }
-    for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k >= K) break;
         const bool on = (mask >> k) & 1;
         const unsigned b = __ballot_sync(0xffffffffu, on);
         if (!b) {
@@ -155,15 +174,18 @@ __global__ void combine_kernel(int64_t B, int K, const int* __restrict__ row_slo
     out[i] = acc;
 }
 
+template <int KMAX>
 __global__ void route_only_kernel(RowSrc src, int64_t B, const float* __restrict__ cent, int K, int s, float margin,
                                   int direct, int* assign, float* weights) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= B) return;
-    float d[MN_MAX_SUB], w[MN_MAX_SUB];
-    distances(src, row, cent, K, s, direct, d);
-    const uint64_t mask = route_row(d, K, margin, w);
+    float d[KMAX], w[KMAX];
+    distances<KMAX>(src, row, cent, K, s, direct, d);
+    const uint64_t mask = route_row<KMAX>(d, K, margin, w);
     if (margin > 1.0f) {
-        for (int k = 0; k < K; ++k) weights[row * K + k] = w[k];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) weights[row * K + k] = w[k];
     } else {
         assign[row] = __ffsll((long long)mask) - 1;
     }
@@ -178,14 +200,19 @@ int mn_route_build(mn_ctx* ctx, mn_model* m, const RowSrc& src, int64_t B, int64
     MN_CUDA(ctx, cudaMemsetAsync(m->counters_d, 0, CNT_TOTAL * sizeof(int), st));
     MN_CUDA(ctx, cudaMemsetAsync(slot_row, 0xFF, (size_t)cap * sizeof(int), st));
     const unsigned blocks = (unsigned)mn_cdiv(B, 256);
-    route_count_kernel<<<blocks, 256, 0, st>>>(src, B, m->centroids_d, K, m->d.cluster_dim_start, m->d.boundary_margin,
-                                               direct, m->counters_d);
+#define MN_ROUTE_DISPATCH(KERNEL, GRID, BLOCK, ...)                                   \
+    do {                                                                              \
+        if (K <= 8) KERNEL<8><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                   \
+        else if (K <= 32) KERNEL<32><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);            \
+        else KERNEL<MN_MAX_SUB><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                 \
+    } while (0)
+    MN_ROUTE_DISPATCH(route_count_kernel, blocks, 256, src, B, m->centroids_d, K, m->d.cluster_dim_start, m->d.boundary_margin,
+                      direct, m->counters_d);
     MN_LAUNCH_CHECK(ctx);
     route_scan_kernel<<<1, 32, 0, st>>>(m->counters_d, K);
     MN_LAUNCH_CHECK(ctx);
-    route_scatter_kernel<<<blocks, 256, 0, st>>>(src, B, m->centroids_d, K, m->d.cluster_dim_start,
-                                                 m->d.boundary_margin, direct, m->counters_d, cap, slot_row, slot_w,
-                                                 row_slots, ctx->status_d);
+    MN_ROUTE_DISPATCH(route_scatter_kernel, blocks, 256, src, B, m->centroids_d, K, m->d.cluster_dim_start, m->d.boundary_margin,
+                      direct, m->counters_d, cap, slot_row, slot_w, row_slots, ctx->status_d);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
 }
@@ -209,8 +236,9 @@ extern "C" int mn_model_route(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int
     const int K = m->d.n_sub;
     const int direct = (B <= 25 && K <= 25) ? 1 : 0;
     if (B == 0) return MN_OK;
-    route_only_kernel<<<(unsigned)mn_cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(
-        src, B, m->centroids_d, K, m->d.cluster_dim_start, m->d.boundary_margin, direct, assign_out_d, weights_out_d);
+    cudaStream_t st = (cudaStream_t)stream;
+    MN_ROUTE_DISPATCH(route_only_kernel, (unsigned)mn_cdiv(B, 128), 128, src, B, m->centroids_d, K, m->d.cluster_dim_start,
+                      m->d.boundary_margin, direct, assign_out_d, weights_out_d);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
 }
