@@ -48,70 +48,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// up to four K=16 steps against one ring stage; A either from TMEM (address + 8 columns per step) or from
-// shared memory (descriptor + a_step per step); one elected lane issues, then releases the stage.
-__device__ __forceinline__ void ts_stage_tmem(uint32_t d_tmem, uint32_t a_tmem, uint64_t bd, uint64_t b_step, uint32_t idesc,
-                                              uint32_t accum, int nk, uint32_t empty_bar) {
-    asm volatile(
-        "{\n\t.reg .pred e, p, q1, q2, q3;\n\t.reg .b64 b1, b2, b3;\n\t.reg .b32 a1, a2, a3;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "setp.gt.and.s32 q1, %6, 1, e;\n\t"
-        "setp.gt.and.s32 q2, %6, 2, e;\n\t"
-        "setp.gt.and.s32 q3, %6, 3, e;\n\t"
-        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
-        "add.u64 b1, %2, %3;\n\tadd.u64 b2, b1, %3;\n\tadd.u64 b3, b2, %3;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %4, p;\n\t"
-        "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %4, 1;\n\t"
-        "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %4, 1;\n\t"
-        "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %4, 1;\n\t"
-        "@e  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(bd), "l"(b_step), "r"(idesc), "r"(accum), "r"(nk), "r"(empty_bar)
-        : "memory");
-}
-__device__ __forceinline__ void ts_stage_smem(uint32_t d_tmem, uint64_t ad, uint64_t a_step, uint64_t bd, uint64_t b_step,
-                                              uint32_t idesc, uint32_t accum, int nk, uint32_t empty_bar) {
-    asm volatile(
-        "{\n\t.reg .pred e, p, q1, q2, q3;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "setp.gt.and.s32 q1, %7, 1, e;\n\t"
-        "setp.gt.and.s32 q2, %7, 2, e;\n\t"
-        "setp.gt.and.s32 q3, %7, 3, e;\n\t"
-        "add.u64 a1, %1, %2;\n\tadd.u64 a2, a1, %2;\n\tadd.u64 a3, a2, %2;\n\t"
-        "add.u64 b1, %3, %4;\n\tadd.u64 b2, b1, %4;\n\tadd.u64 b3, b2, %4;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, p;\n\t"
-        "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %5, 1;\n\t"
-        "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %5, 1;\n\t"
-        "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %5, 1;\n\t"
-        "@e  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}"
-        ::"r"(d_tmem), "l"(ad), "l"(a_step), "l"(bd), "l"(b_step), "r"(idesc), "r"(accum), "r"(nk), "r"(empty_bar)
-        : "memory");
-}
-
-// Probe up to four mbarriers back to back (their ~100-cycle try_wait latencies overlap), then block on whatever
-// was not ready yet.  Unused slots repeat a valid (address, parity) pair.
-__device__ __forceinline__ void mbar_wait4(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1, uint32_t a2, uint32_t p2, uint32_t a3,
-                                           uint32_t p3) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred q0, q1, q2, q3;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
-        "and.pred q0, q0, q1;\n\tand.pred q2, q2, q3;\n\tand.pred q0, q0, q2;\n\t"
-        "selp.u32 %0, 1, 0, q0;\n\t}"
-        : "=r"(ok)
-        : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2), "r"(a3), "r"(p3)
-        : "memory");
-    if (ok) return;
-    mbar_wait_a(a0, p0);
-    mbar_wait_a(a1, p1);
-    mbar_wait_a(a2, p2);
-    mbar_wait_a(a3, p3);
-}
-
 // Two MMA-issuing warps (one per N-half, each with its own weight ring and producer warp): a single issuing
 // thread needs ~170 cycles of scalar work per tcgen05.mma and cannot keep the tensor pipe (64 cycles per N=128 MMA) fed.
 __global__ void __launch_bounds__(kTsThreads, 1) tc_mlp_ts_kernel(const TcArgs A) {
