@@ -668,10 +668,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
     uint64_t* xa_full = bars + 2 * kMaxStages;
     uint64_t* xa_empty = xa_full + 1;
     uint64_t* acc_full = xa_full + 2;       // [2]
-    uint64_t* hready = xa_full + 4;         // [4 slabs][4 lane quarters]: 4 arrivals each instead of 16 on one barrier
-    uint64_t* f32_full = xa_full + 20;
-    uint64_t* f32_empty = xa_full + 21;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xa_full + 22);
+    uint64_t* hready = xa_full + 4;         // [4]
+    uint64_t* f32_full = xa_full + 8;
+    uint64_t* f32_empty = xa_full + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xa_full + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_slots = A.m.counters ? A.m.counters[CNT_NSLOTS] : A.m.B;
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
         mbar_init(xa_empty, 1);
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
-        for (int i = 0; i < 16; ++i) mbar_init(&hready[i], kEpiWarps / 4);
+        for (int i = 0; i < 4; ++i) mbar_init(&hready[i], kEpiWarps);
         mbar_init(f32_full, 1);
         mbar_init(f32_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -788,13 +788,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                                 if (!from_x && pass == 0 && (k0 & 63) == 0) {
                                     // the previous GEMM's epilogue has published this 64-column slab of H
                                     const int hs = k0 >> 6;
-                                    const uint32_t hb = smem_u32(&hready[4 * hs]);
-                                    uint32_t hp;
-                                    if (hs == 0) { hp = hph0; hph0 ^= 1; }
-                                    else if (hs == 1) { hp = hph1; hph1 ^= 1; }
-                                    else if (hs == 2) { hp = hph2; hph2 ^= 1; }
-                                    else { hp = hph3; hph3 ^= 1; }
-                                    mbar_wait4(hb, hp, hb + 8, hp, hb + 16, hp, hb + 24, hp);
+                                    if (hs == 0) { mbar_wait(&hready[0], hph0); hph0 ^= 1; }
+                                    else if (hs == 1) { mbar_wait(&hready[1], hph1); hph1 ^= 1; }
+                                    else if (hs == 2) { mbar_wait(&hready[2], hph2); hph2 ^= 1; }
+                                    else { mbar_wait(&hready[3], hph3); hph3 ^= 1; }
                                 }
                                 mbar_wait(&full[stage], phase);
                                 tc_fence_after();
@@ -880,7 +877,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                         if (publish) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&hready[4 * j + q]);
+                            if (lane == 0) mbar_arrive(&hready[j]);
                         }
                     }
                     if (want_sigma) {
