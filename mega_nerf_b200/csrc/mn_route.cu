@@ -132,22 +132,38 @@ __global__ void route_scatter_kernel(RowSrc src, int64_t B, const float* __restr
         distances<KMAX>(src, row, sc, K, s, direct, d);
         mask = route_row<KMAX>(d, K, margin, w);
     }
+    // one global atomic per (block, sub-module): warp ballots -> shared per-warp counts -> block prefix
+    __shared__ int wcnt[8][KMAX];     // blockDim.x == 256
+    const int warp = threadIdx.x >> 5;
+    unsigned bal[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        bal[k] = 0;
+        if (k < K) {
+            bal[k] = __ballot_sync(0xffffffffu, (mask >> k) & 1);
+            if (lane == 0) wcnt[warp][k] = __popc(bal[k]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        const int k = threadIdx.x;
+        int tot = 0;
+        for (int wi = 0; wi < 8; ++wi) tot += wcnt[wi][k];
+        int base = tot ? atomicAdd(&counters[CNT_CURSOR + k], tot) : 0;
+        base += counters[CNT_START + k];
+        for (int wi = 0; wi < 8; ++wi) {
+            const int c = wcnt[wi][k];
+            wcnt[wi][k] = base;
+            base += c;
+        }
+    }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         if (k >= K) break;
-        const bool on = (mask >> k) & 1;
-        const unsigned b = __ballot_sync(0xffffffffu, on);
-        if (!b) {
-            if (row < B && row_slots) row_slots[row * K + k] = -1;
-            continue;
-        }
-        int base = 0;
-        const int leader = __ffs(b) - 1;
-        if (lane == leader) base = atomicAdd(&counters[CNT_CURSOR + k], __popc(b));
-        base = __shfl_sync(0xffffffffu, base, leader);
         int slot = -1;
-        if (on) {
-            slot = counters[CNT_START + k] + base + __popc(b & ((1u << lane) - 1));
+        if ((mask >> k) & 1) {
+            slot = wcnt[warp][k] + __popc(bal[k] & ((1u << lane) - 1));
             if (slot >= cap) {
                 atomicOr(status, MN_STATUS_OVERFLOW);
                 slot = -1;
