@@ -34,6 +34,23 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 N_RAYS = 4096
 COARSE, FINE = 64, 128
 MARGIN = 1.15
+# The graded line is 'c2' (BASELINE configs[1]).  'c4' / 'c5' are the other single-GPU-sized BASELINE shapes, selectable
+# for diagnostics only (python bench.py --workload c4); their lines carry the same keys.
+WORKLOADS = {
+    'c2': dict(desc='BASELINE configs[1]: mega-nerf 8-submodule 256-ch', rays=4096, spec={}, grid=(2, 4), sh_deg=None,
+               kernel='tc_mlp_pp_kernel'),
+    'c4': dict(desc='BASELINE configs[3] shape: mega-nerf 25-submodule 512-ch', rays=4096, spec=dict(layer_dim=512), grid=(5, 5),
+               sh_deg=None, kernel='tc_mlp_wide_kernel'),
+    'c5': dict(desc='BASELINE configs[4]: mega-nerf-sh-3 (SH degree 2 head) 8-submodule 256-ch', rays=8192,
+               spec=dict(pos_dir_dim=0, rgb_dim=27), grid=(2, 4), sh_deg=2, kernel='tc_mlp_pp_kernel'),
+}
+WL = WORKLOADS['c2']
+
+
+def select_workload(name: str) -> None:
+    global WL, N_RAYS
+    WL = WORKLOADS[name]
+    N_RAYS = WL['rays']
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -47,13 +64,13 @@ def peaks():
 
 def workload(seed_shift: int = 0):
     from oracle import mn_oracle as O
-    spec = O.NerfSpec()
-    cents = O.grid_centroids(2, 4)
-    net = O.make_net('mega', spec, seed=0, n_sub=8, centroids=cents, boundary_margin=MARGIN, cluster_2d=True)
+    spec = O.NerfSpec(**WL['spec'])
+    cents = O.grid_centroids(*WL['grid'])
+    net = O.make_net('mega', spec, seed=0, n_sub=cents.shape[0], centroids=cents, boundary_margin=MARGIN, cluster_2d=True)
     rays = O.synthetic_rays(N_RAYS, seed=seed_shift)
     idx = O.synthetic_indices(N_RAYS, spec.appearance_count, seed=1 + seed_shift)
-    opts = O.RenderOpts(coarse_samples=COARSE, fine_samples=FINE, use_cascade=False, perturb=1.0, pos_dir_dim=4,
-                        sh_deg=None, model_chunk_size=32 * 1024)
+    opts = O.RenderOpts(coarse_samples=COARSE, fine_samples=FINE, use_cascade=False, perturb=1.0, pos_dir_dim=spec.pos_dir_dim,
+                        sh_deg=WL['sh_deg'], model_chunk_size=32 * 1024)
     return spec, net, rays, idx, opts
 
 
@@ -153,7 +170,7 @@ def run_reference(args, rank: int):
         'impl': 'reference', 'metric': 'ray-samples/sec (MLP+composite)', 'value': value, 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'mega-nerf 8-submodule 256-ch, {N_RAYS} rays x ({COARSE}+{FINE}) samples, margin {MARGIN}; '
+        'config': {'workload': f'{WL["desc"]}, {N_RAYS} rays x ({COARSE}+{FINE}) samples, margin {MARGIN}; '
                                f'each CPU step renders a {sample}-ray sample of it'},
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                          'sample': f'{sample} of {N_RAYS} rays per step, {args.steps} steps'},
@@ -178,7 +195,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('MN_B200_PRECISION', 'tc_f16'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
     rank = int(os.environ.get('RANK', '0'))
@@ -317,7 +336,7 @@ def main():
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', 'tc_f16': 'f16 operands / f32 accumulate', 'tc_f16x3': 'f16x3 split / f32 accumulate'}[args.precision],
             'data': 'synthetic',
-            'config': {'workload': f'BASELINE configs[1]: mega-nerf 8-submodule 256-ch, {N_RAYS} rays x ({COARSE} coarse + {FINE} fine) '
+            'config': {'workload': f'{WL["desc"]}, {N_RAYS} rays x ({COARSE} coarse + {FINE} fine) '
                                    f'per GPU, boundary_margin {MARGIN} (m = {mult:.3f} sub-modules/sample), random-init weights',
                        'parallelism': f'ray-sharded x{world}, weights replicated, 1 all-gather of [rays,4] per step' if world > 1 else 'single GPU',
                        'precision': args.precision, 'l2': f'flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)',
@@ -327,15 +346,16 @@ def main():
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'tensor',
-                         'kernel': {'fp32': 'mlp_simt_kernel', 'tc_f16': 'tc_mlp_pp_kernel', 'tc_f16x3': 'tc_mlp_kernel<split>'}[args.precision],
+                         'kernel': {'fp32': 'mlp_simt_kernel', 'tc_f16': WL['kernel'], 'tc_f16x3': 'tc_mlp_kernel<split>'}[args.precision],
                          'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
                          'frac_of_sustained_peak': achieved / pk['tflops_sustained'] if pk['tflops_sustained'] else None,
                          'peak_source': pk['src'],
                          # dram__bytes_read.sum + dram__bytes_write.sum of the fine-pass launch (4980 tiles) from
                          # profiles/r1_tc_mlp_pp_kernel.ncu-rep; algorithmic: 40 KiB feature tile + 2 KiB outputs per tile = 209 MB
-                         'traffic': 228.6e6 if args.precision == 'tc_f16' else None,
+                         'traffic': 229.5e6 if (args.precision == 'tc_f16' and args.workload == 'c2') else None,
                          'traffic_detail': {'algorithmic_bytes_per_launch': 4980 * (40960 + 2048),
-                                            'launch': 'fine pass, 4980 tiles x 128 rows', 'source': 'ncu --set full, profiles/'},
+                                            'launch': 'fine pass, 4980 tiles x 128 rows',
+                                            'source': 'ncu --set full, profiles/'} if args.workload == 'c2' else None,
                          'algorithmic_flops_per_row': fl_row, 'mma_passes_per_algorithmic': passes,
                          'kernel_ms_per_step': kernel_ms_per_step, 'launches_per_step': n_l.value / args.steps},
             'parity': {'max_rel_rgb_vs_oracle_256_rays': par},

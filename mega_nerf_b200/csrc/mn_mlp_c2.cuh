@@ -2,36 +2,42 @@
 //
 // A cluster of two CTAs (one SM pair) runs tcgen05.mma.cta_group::2: one instruction issued by the leader CTA drives
 // both SMs' tensor cores on a 256-row tile (128 rows per CTA).  Each CTA stages only HALF of every weight slab
-// (N/2 rows of B), so per SM the TMA fill traffic, the B reads from shared memory and — decisive for this kernel —
-// the scalar issue work per FLOP are all halved, and a 64-column stage (4 MMAs per barrier wait) fits the same 16 KiB.
-// Everything else follows tc_mlp_pp_kernel: two 256-row tiles (X, Y) per cluster, GEMMs issued X_l, Y_l, X_l+1, ...,
-// each CTA's 16 epilogue warps drain its own 128 TMEM lanes under the other tile's MMAs.
+// (N/2 rows of B): measured on B200, the single-CTA kernel is bound by shared-memory traffic - per 128x256x16 MMA the
+// tensor core fetches 12 KiB of operands (A 4 KiB + B 8 KiB, ~182 cycles instead of 128) while TMA writes another
+// 8 KiB of weights into the ring; the pair halves both B terms per SM and a ring stage holds 64 K-columns (4 MMAs).
+// Everything else follows tc_mlp_pp_kernel: two 256-row tiles (X, Y) per cluster - four consecutive 128-row tiles,
+// one sub-module thanks to the 512-row bucket alignment - GEMMs issued X_l, Y_l, X_l+1, ..., each CTA's 16 epilogue
+// warps drain its own 128 TMEM lanes under the other tile's MMAs; feature columns ride in the weight ring.
 //
 // Cross-CTA signalling (all barriers live at identical offsets in both CTAs):
-//   full[s], xa_full   leader's barrier counts both producers: the peer arrives/expect_tx's and lets its TMA
-//                      complete_tx on the LEADER's barrier (shared::cluster address from mapa);
-//   empty[s], xa_empty, acc_full[slot]   tcgen05.commit ... multicast::cluster to both CTAs;
+//   full[s]            the LEADER's barrier counts both producers: each arrives with expect_tx and its tensor-map TMA
+//                      copies (.cta_group::2) complete_tx on the leader's barrier (shared::cluster address from mapa);
+//   empty[s], acc_full[slot]   tcgen05.commit ... multicast::cluster to both CTAs;
 //   epi_done[slot]     leader's barrier, 32 arrivals (16 epilogue warps per CTA, the peer's arrive remotely).
 #pragma once
 
 
-constexpr int kC2Stages = 3;
-constexpr int kC2StageCols = 64;
-constexpr int kC2StageBytes = kC2StageCols * 128 * 2;   // 64 K-columns x 128 weight rows (half of N = 256) x fp16
+constexpr int kC2MaxStages = 8;
+constexpr int kC2StageCols = 64;                        // activation segments: 64 K-columns x (N/2 <= 128) weight rows = <= 16 KiB
+constexpr int kC2StageBytes = kC2StageCols * 128 * 2;
+constexpr int kC2XCols = 32;                            // feature segments: 32 K-columns of weights (<= 8 KiB) + 32 feature columns (8 KiB)
+constexpr int kC2XOff = 8192;
 
 struct C2Layout {
-    int ring, h, xa, f32, f32_stride, sigp, bars, total;
+    int ring, h, f32, f32_stride, sigp, bars, total, stages;
 };
 
 __host__ __device__ inline C2Layout c2_layout(const TcPlan& p) {
     C2Layout s;
-    const int kx = p.kpe > p.kaux ? p.kpe : p.kaux;
-    s.ring = 0;
-    s.h = kC2Stages * kC2StageBytes;
-    s.xa = s.h + 2 * p.L * kTileM * 2;
-    s.f32 = s.xa + kx * kTileM * 2;
     s.f32_stride = ((p.f32_floats * 4 + 15) / 16) * 16;
-    s.sigp = s.f32 + 2 * s.f32_stride;
+    const int fixed = 2 * p.L * kTileM * 2 + s.f32_stride + 2048 + 256;
+    int st = (kSmemMax - fixed) / kC2StageBytes;
+    if (st > kC2MaxStages) st = kC2MaxStages;
+    s.stages = st;
+    s.ring = 0;
+    s.h = st * kC2StageBytes;
+    s.f32 = s.h + 2 * p.L * kTileM * 2;
+    s.sigp = s.f32 + s.f32_stride;
     s.bars = s.sigp + 2048;
     s.total = s.bars + 256;
     return s;
@@ -116,28 +122,38 @@ __device__ __forceinline__ void tma2d_c2(uint32_t dst_smem, const CUtensorMap* t
         : "memory");
 }
 
+struct C2Maps {
+    CUtensorMap w64, w32, w8;   // packed weights viewed as rows of 256 B: boxes of 64 / 32 / 8 rows
+    CUtensorMap x32, x16;       // feature tile images, same view: boxes of 32 / 16 rows (= K-columns)
+};
+
+// copies `rows` x 256 B starting at row `row0` of a rows-of-256-B tensor map into this CTA's shared memory, using the
+// largest boxes first (box heights ra > rb > rc; a map pointer may be null)
+__device__ __forceinline__ void c2_copy_rows(uint32_t dst, int row0, int rows, uint32_t bar, const CUtensorMap* ma, int ra,
+                                             const CUtensorMap* mb, int rb, const CUtensorMap* mc, int rc) {
+    while (ma && rows >= ra) { tma2d_c2(dst, ma, row0, bar); dst += (uint32_t)ra * 256u; row0 += ra; rows -= ra; }
+    while (mb && rows >= rb) { tma2d_c2(dst, mb, row0, bar); dst += (uint32_t)rb * 256u; row0 += rb; rows -= rb; }
+    while (mc && rows >= rc) { tma2d_c2(dst, mc, row0, bar); dst += (uint32_t)rc * 256u; row0 += rc; rows -= rc; }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-    tc_mlp_c2_kernel(const TcArgs A, const __grid_constant__ CUtensorMap tm_big, const __grid_constant__ CUtensorMap tm_small) {
+    tc_mlp_c2_kernel(const TcArgs A, const __grid_constant__ C2Maps TM) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
     const C2Layout SL = c2_layout(P);
+    const int kStages = SL.stages;
     unsigned char* ring = smem + SL.ring;
     unsigned char* Hs = smem + SL.h;
-    unsigned char* XA = smem + SL.xa;
     float* F32 = reinterpret_cast<float*>(smem + SL.f32);
     float* SIGP = reinterpret_cast<float*>(smem + SL.sigp);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bars);
-    uint64_t* full = bars;            // [3]   per CTA: this CTA's weight-half has landed
-    uint64_t* empty = bars + 3;       // [3]   per CTA (released by the leader's multicast commit)
-    uint64_t* pfull = bars + 6;       // [3]   leader's: the PEER's weight-half has landed (relayed by the peer's warp 17)
-    uint64_t* xa_full = bars + 9;     //       per CTA
-    uint64_t* xa_empty = bars + 10;   //       per CTA
-    uint64_t* pxa_full = bars + 11;   //       leader's: relayed
-    uint64_t* acc_full = bars + 12;   // [2]   per CTA
-    uint64_t* epi_done = bars + 14;   // [2]   leader's
-    uint64_t* f32_full = bars + 16;   // [2]   per CTA
-    uint64_t* f32_empty = bars + 18;  // [2]   per CTA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* full = bars;            // [<=8] LEADER's: both CTAs' halves of the stage have landed
+    uint64_t* empty = bars + 8;       // [<=8] per CTA (released by the leader's multicast commit)
+    uint64_t* acc_full = bars + 16;   // [2]   per CTA
+    uint64_t* epi_done = bars + 18;   // [2]   leader's
+    uint64_t* f32_full = bars + 20;   //       per CTA
+    uint64_t* f32_empty = bars + 21;  //       per CTA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -145,23 +161,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_slots = A.m.counters ? A.m.counters[CNT_NSLOTS] : A.m.B;
     const int64_t n_tiles = (n_slots + kTileM - 1) / kTileM;        // 128-row tiles
-    const int64_t n_super = (n_tiles + 1) / 2;                       // 256-row tiles (one per CTA pair)
+    const int64_t n_quads = (n_tiles + 3) / 4;                       // a cluster iteration = 4 consecutive tiles
     const int n_gemm = A.m.sigma_only ? P.n_trunk : P.n_gemm;
     const int h_bytes = P.L * kTileM * 2;
     const int64_t cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;        // cluster index / count
-    const int64_t stride2 = 2 * ncl;
+    const int xrows_tile = P.kpe + P.kaux;                           // 256-byte rows per feature tile image (one per K-column)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kC2Stages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); mbar_init(&pfull[i], 1); }
-        mbar_init(xa_full, 1);
-        mbar_init(xa_empty, 1);
-        mbar_init(pxa_full, 1);
+        for (int i = 0; i < kC2MaxStages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&epi_done[i], 2 * kEpiWarps);
-            mbar_init(&f32_full[i], 1);
-            mbar_init(&f32_empty[i], kEpiWarps);
         }
+        mbar_init(f32_full, 1);
+        mbar_init(f32_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpProd) {
@@ -189,55 +202,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         // =========================== TMA producer (each CTA streams its N-half of every weight slab) ===========================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0, xphase = 0, fph[2] = {0, 0};
+            uint32_t phase = 0, fph = 0;
             const uint32_t f32_bytes = (uint32_t)SL.f32_stride;
-            const uint32_t full_l = mapa_u32(smem_u32(full), 0);          // the LEADER's full[] barriers count both weight halves
+            const uint32_t full_l = mapa_u32(smem_u32(full), 0);          // the LEADER's full[] barriers count both halves
             const uint32_t ring_a = smem_u32(ring);
-            for (int64_t t0 = cl; t0 < n_super; t0 += stride2) {
-                const int64_t sup[2] = {t0, t0 + ncl};
-                const unsigned char* wsub[2] = {nullptr, nullptr};
-                for (int sl = 0; sl < 2; ++sl) {
-                    if (sup[sl] >= n_super) continue;
-                    wsub[sl] = A.wpack + (size_t)sub_of(2 * sup[sl]) * P.sub_bytes;
-                    mbar_wait(&f32_empty[sl], fph[sl] ^ 1);
-                    mbar_expect_tx(&f32_full[sl], f32_bytes);
-                    bulk_g2s(reinterpret_cast<unsigned char*>(F32) + (size_t)sl * SL.f32_stride,
-                             wsub[sl] + (size_t)P.plane_bytes * 2, f32_bytes, &f32_full[sl]);
-                    fph[sl] ^= 1;
-                }
+            for (int64_t q = cl; q < n_quads; q += ncl) {
+                const unsigned char* wsub = A.wpack + (size_t)sub_of(4 * q) * P.sub_bytes;
+                mbar_wait(f32_empty, fph ^ 1);
+                mbar_expect_tx(f32_full, f32_bytes);
+                bulk_g2s(reinterpret_cast<unsigned char*>(F32), wsub + (size_t)P.plane_bytes * 2, f32_bytes, f32_full);
+                fph ^= 1;
                 for (int gi = 0; gi < n_gemm; ++gi) {
                     const TcGemm& g = P.g[gi];
                     const int nhalf = g.n >> 1;                                   // weight rows held by this CTA
                     const int K = g.k[0] + (g.nseg > 1 ? g.k[1] : 0);
+                    const unsigned char* wimg = wsub + c2_off + g.w_off + (size_t)rank * K * nhalf * 2;
                     for (int sl = 0; sl < 2; ++sl) {
-                        if (!wsub[sl]) continue;
-                        const unsigned char* wimg = wsub[sl] + c2_off + g.w_off + (size_t)rank * K * nhalf * 2;
-                        const int64_t my_tile = 2 * sup[sl] + rank;              // this CTA's 128-row tile
+                        const int64_t my_tile = 4 * q + 2 * sl + rank;           // this CTA's 128-row tile of the slot
                         int kbase = 0;
                         for (int sgi = 0; sgi < g.nseg; ++sgi) {
                             const int kseg = g.k[sgi];
-                            if (g.src[sgi] != SRC_H) {
-                                const __half* xt = A.ximg + my_tile * (int64_t)(P.kpe + P.kaux) * kTileM +
-                                                   (g.src[sgi] == SRC_XAUX ? (int64_t)P.kpe * kTileM : 0);
-                                mbar_wait(xa_empty, xphase ^ 1);
-                                mbar_expect_tx(xa_full, (uint32_t)(kseg * kTileM * 2));
-                                bulk_g2s(XA, xt, (uint32_t)(kseg * kTileM * 2), xa_full);
-                                xphase ^= 1;
-                            }
-                            for (int k0 = 0; k0 < kseg; k0 += kC2StageCols) {
-                                const int kc = min(kC2StageCols, kseg - k0);
-                                const uint32_t bytes = (uint32_t)(kc * nhalf * 2);
-                                mbar_wait(&empty[stage], phase ^ 1);
-                                mbar_expect_tx_cluster(full_l + 8u * (uint32_t)stage, bytes);
-                                const int row0 = (int)((size_t)((wimg + (size_t)(kbase + k0) * nhalf * 2) - A.wpack) >> 8);
+                            const bool from_x = g.src[sgi] != SRC_H;
+                            const int step = from_x ? kC2XCols : kC2StageCols;
+                            const int xrow0 = (int)(my_tile * xrows_tile) + (g.src[sgi] == SRC_XAUX ? P.kpe : 0);
+                            for (int k0 = 0; k0 < kseg; k0 += step) {
+                                const int kc = min(step, kseg - k0);
+                                const uint32_t wbytes = (uint32_t)(kc * nhalf * 2);
+                                const uint32_t xbytes = from_x ? (uint32_t)(kc * kTileM * 2) : 0u;
+                                const uint32_t bar = full_l + 8u * (uint32_t)stage;
                                 const uint32_t dst = ring_a + (uint32_t)stage * kC2StageBytes;
-                                if (bytes == 16384u) {
-                                    tma2d_c2(dst, &tm_big, row0, full_l + 8u * (uint32_t)stage);
-                                } else {
-                                    for (uint32_t b = 0; b < bytes; b += 2048u)
-                                        tma2d_c2(dst + b, &tm_small, row0 + (int)(b >> 8), full_l + 8u * (uint32_t)stage);
-                                }
-                                if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
+                                mbar_wait(&empty[stage], phase ^ 1);
+                                mbar_expect_tx_cluster(bar, wbytes + xbytes);
+                                const int wrow0 = (int)((size_t)((wimg + (size_t)(kbase + k0) * nhalf * 2) - A.wpack) >> 8);
+                                c2_copy_rows(dst, wrow0, (int)(wbytes >> 8), bar, &TM.w64, 64, &TM.w32, 32, &TM.w8, 8);
+                                if (from_x) c2_copy_rows(dst + kC2XOff, xrow0 + k0, kc, bar, &TM.x32, 32, &TM.x16, 16, nullptr, 0);
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
                             kbase += kseg;
                         }
@@ -249,16 +248,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         // =========================== MMA issuer: leader CTA only, whole warp, one elected lane issues ===========================
         if (leader) {
             int stage = 0;
-            uint32_t phase = 0, xphase = 0, eph0 = 0, eph1 = 0;
+            uint32_t phase = 0, eph0 = 0, eph1 = 0;
             bool started0 = false, started1 = false;
-            const uint32_t h_base = smem_u32(Hs), xa_base = smem_u32(XA), ring_base = smem_u32(ring);
-            const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), pfull_a = smem_u32(pfull);
-            const uint32_t xa_full_a = smem_u32(xa_full), xa_empty_a = smem_u32(xa_empty), pxa_full_a = smem_u32(pxa_full);
+            const uint32_t h_base = smem_u32(Hs), ring_base = smem_u32(ring);
+            const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
             const uint32_t acc_full_a = smem_u32(acc_full), epi_done_a = smem_u32(epi_done);
             const uint64_t a_step = (uint64_t)((2 * kTileM * 16) >> 4);
             const uint64_t st_step = (uint64_t)(kC2StageBytes >> 4);
-            for (int64_t t0 = cl; t0 < n_super; t0 += stride2) {
-                const bool valid1 = t0 + ncl < n_super;
+            const uint64_t xd0 = make_desc(ring_base + (uint32_t)kC2XOff, kTileM * 16, 128);
+            for (int64_t q = cl; q < n_quads; q += ncl) {
                 for (int gi = 0; gi < n_gemm; ++gi) {
                     const TcGemm& g = P.g[gi];
                     const int nhalf = g.n >> 1;
@@ -266,7 +264,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     const uint64_t b_step = (uint64_t)((2 * nhalf * 16) >> 4);
                     const uint64_t bd0 = make_desc(ring_base, (uint32_t)nhalf * 16, 128);
                     for (int sl = 0; sl < 2; ++sl) {
-                        if (sl == 1 && !valid1) continue;
                         // both CTAs have drained this slot's accumulator and written its activations
                         if (sl == 0) { if (started0) { mbar_wait_cluster(epi_done_a, eph0); eph0 ^= 1; } started0 = true; }
                         else         { if (started1) { mbar_wait_cluster(epi_done_a + 8, eph1); eph1 ^= 1; } started1 = true; }
@@ -276,107 +273,65 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                         for (int sgi = 0; sgi < g.nseg; ++sgi) {
                             const int kseg = g.k[sgi];
                             const bool from_x = g.src[sgi] != SRC_H;
-                            uint64_t ad = make_desc(from_x ? xa_base : h_base + (uint32_t)(sl * h_bytes), kTileM * 16, 128);
-                            if (from_x) {
-                                mbar_wait_a(xa_full_a, xphase);
-                                mbar_wait_cluster(pxa_full_a, xphase);
-                                xphase ^= 1;
-                            }
-                            for (int k0 = 0; k0 < kseg; k0 += kC2StageCols) {
-                                const int kc = min(kC2StageCols, kseg - k0);
+                            const int step = from_x ? kC2XCols : kC2StageCols;
+                            uint64_t ad = make_desc(h_base + (uint32_t)(sl * h_bytes), kTileM * 16, 128);
+                            for (int k0 = 0; k0 < kseg; k0 += step) {
+                                const int kc = min(step, kseg - k0);
+                                const uint64_t so = (uint64_t)stage * st_step;
                                 mbar_wait_cluster(full_a + 8u * (uint32_t)stage, phase);
                                 tc_fence_after();
-                                c2_stage(d_tmem, ad, a_step, bd0 + (uint64_t)stage * st_step, b_step, idesc, accum, kc >> 4,
+                                c2_stage(d_tmem, from_x ? xd0 + so : ad, a_step, bd0 + so, b_step, idesc, accum, kc >> 4,
                                          empty_a + 8u * (uint32_t)stage);
                                 accum = 1;
                                 ad += (uint64_t)(kc >> 4) * a_step;
-                                if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
-                            if (from_x) c2_commit_both(xa_empty_a);
                         }
                         c2_commit_both(acc_full_a + 8u * (uint32_t)sl);
-                    }
-                }
-            }
-        } else if (lane == 0) {
-            // peer CTA: relay "my half of this stage has landed" to the leader, in the exact consumption order
-            uint32_t xphase = 0;
-            const uint32_t pxa_full_l = mapa_u32(smem_u32(pxa_full), 0);
-            for (int64_t t0 = cl; t0 < n_super; t0 += stride2) {
-                const bool valid1 = t0 + ncl < n_super;
-                for (int gi = 0; gi < n_gemm; ++gi) {
-                    const TcGemm& g = P.g[gi];
-                    for (int sl = 0; sl < 2; ++sl) {
-                        if (sl == 1 && !valid1) continue;
-                        for (int sgi = 0; sgi < g.nseg; ++sgi) {
-                            const int kseg = g.k[sgi];
-                            if (g.src[sgi] != SRC_H) {
-                                mbar_wait(xa_full, xphase);
-                                xphase ^= 1;
-                                mbar_arrive_cluster(pxa_full_l);
-                            }
-                        }
                     }
                 }
             }
         }
     } else {
         // =========================== epilogue (16 warps per CTA, own 128 TMEM lanes) ===========================
-        const int q = warp & 3;
+        const int q4 = warp & 3;
         const int part = warp >> 2;
-        const int r = q * 32 + lane;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t aph0 = 0, aph1 = 0, fph0 = 0, fph1 = 0;
+        const int r = q4 * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        uint32_t aph0 = 0, aph1 = 0, fph = 0;
         const int L = P.L;
         const uint32_t epi_done_l = mapa_u32(smem_u32(epi_done), 0);      // leader's barrier (local address if we are the leader)
-        for (int64_t t0 = cl; t0 < n_super; t0 += stride2) {
-            const bool valid1 = t0 + ncl < n_super;
-            int64_t slot_[2] = {0, 0}, row_[2] = {-1, -1};
+        for (int64_t q = cl; q < n_quads; q += ncl) {
+            int64_t slot_[2], row_[2] = {-1, -1};
             float sigma_[2] = {0.0f, 0.0f};
             for (int sl = 0; sl < 2; ++sl) {
-                if (sl == 1 && !valid1) continue;
-                slot_[sl] = (2 * (t0 + (int64_t)sl * ncl) + rank) * kTileM + r;
+                slot_[sl] = (4 * q + 2 * sl + rank) * kTileM + r;
                 if (slot_[sl] < n_slots) row_[sl] = A.m.slot_row ? (int64_t)A.m.slot_row[slot_[sl]] : slot_[sl];
-                if (sl == 0) { mbar_wait(&f32_full[0], fph0); fph0 ^= 1; }
-                else         { mbar_wait(&f32_full[1], fph1); fph1 ^= 1; }
             }
+            const int sub = A.m.nd.affine ? sub_of(4 * q) : 0;
+            mbar_wait(f32_full, fph);
+            fph ^= 1;
             for (int gi = 0; gi < n_gemm; ++gi) {
                 const TcGemm& g = P.g[gi];
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl) {
-                    if (sl == 1 && !valid1) continue;
                     if (sl == 0) { mbar_wait(&acc_full[0], aph0); aph0 ^= 1; }
                     else         { mbar_wait(&acc_full[1], aph1); aph1 ^= 1; }
                     tc_fence_after();
                     const uint32_t t_acc = t_lane + (uint32_t)sl * 256u;
-                    const float* Fb = F32 + (size_t)sl * (SL.f32_stride / 4);
-                    const float* bias = Fb + g.bias_off;
+                    const float* bias = F32 + g.bias_off;
                     const int64_t row = row_[sl], slot = slot_[sl];
                     if (g.epi == EPI_RGB) {
                         if (part == 0) {
                             uint32_t v[32];
                             tmem_ld32(t_acc, v);
                             tmem_ld_wait();
-                            if (row >= 0) {
-                                const NetDims& nd = A.m.nd;
-                                const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
-                                const float w = A.m.slot_w ? A.m.slot_w[slot] : 1.0f;
-                                const float sigma = sigma_[sl];
-#pragma unroll
-                                for (int c = 0; c < 32; ++c) {
-                                    if (c < nd.rgb_dim) {
-                                        float x = __uint_as_float(v[c]) + bias[c];
-                                        if (nd.rgb_dim == 3) x = mn_sigmoid(x);
-                                        A.m.out[o + c] = A.m.slot_w ? x * w : x;
-                                    }
-                                }
-                                A.m.out[o + nd.rgb_dim] = A.m.slot_w ? sigma * w : sigma;
-                            }
+                            if (row >= 0) tc_emit_rgb(A.m, sub, row, slot, v, bias, sigma_[sl]);
                         }
                     } else {
                         const bool want_sigma = g.epi == EPI_RELU_SIGMA;
                         const bool publish = !(want_sigma && A.m.sigma_only);
-                        const float* sw = Fb + P.sigma_w_off;
+                        const float* sw = F32 + P.sigma_w_off;
                         unsigned char* Hsl = Hs + (size_t)sl * h_bytes;
                         float sacc = 0.0f;
                         const int nslab = (g.n + 63) >> 6;
@@ -415,10 +370,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 }
             }
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&f32_empty[0]);
-                if (valid1) mbar_arrive(&f32_empty[1]);
-            }
+            if (lane == 0) mbar_arrive(f32_empty);
         }
     }
     tc_fence_before();

@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "mn_model.cuh"
 
@@ -73,15 +74,18 @@ struct TcPlan {
     int sub_bytes;         // total bytes per sub-module: planes (hi[,lo]) + fp32 block
     int x_tile_bytes;      // bytes of one feature tile image (one plane)
     int L;
+    int bstride;           // floats reserved per GEMM bias in the fp32 block (256; 512 for the 512-wide network)
 };
 
 int pad16(int x) { return (x + 15) / 16 * 16; }
 
 bool build_plan(const NetDims& nd, TcPlan* p) {
-    if (nd.L % 64 != 0 || nd.L > 256 || nd.L < 64 || nd.rgb_dim > 32 || nd.affine || nd.layers > 12) return false;
+    if (nd.L % 64 != 0 || (nd.L > 256 && nd.L != 512) || nd.L < 64 || nd.rgb_dim > 32 || nd.layers > 12) return false;
+    if (nd.affine && nd.rgb_dim != 3) return false;
     TcPlan& P = *p;
     P = TcPlan{};
     P.L = nd.L;
+    P.bstride = nd.L > 256 ? 512 : 256;
     P.kpe = pad16(nd.in_xyz);
     P.kaux = nd.aux > 0 ? pad16(nd.aux) : 0;
     int woff = 0, ng = 0;
@@ -91,7 +95,7 @@ bool build_plan(const NetDims& nd, TcPlan* p) {
         g.nseg = k1 > 0 ? 2 : 1;
         g.src[0] = s0; g.k[0] = k0; g.src[1] = s1; g.k[1] = k1;
         g.w_off = woff;
-        g.bias_off = ng * 256;
+        g.bias_off = ng * P.bstride;
         g.epi = epi;
         woff += (k0 + k1) * n * 2;
         ++ng;
@@ -112,8 +116,8 @@ bool build_plan(const NetDims& nd, TcPlan* p) {
     }
     P.n_gemm = ng;
     P.plane_bytes = woff;
-    P.sigma_w_off = ng * 256;
-    P.f32_floats = ng * 256 + nd.L + 4;
+    P.sigma_w_off = ng * P.bstride;
+    P.f32_floats = ng * P.bstride + nd.L + 4;
     P.x_tile_bytes = (P.kpe + P.kaux) * kTileM * 2;
     return true;
 }
@@ -275,6 +279,47 @@ __device__ __forceinline__ float epi_piece16(uint32_t taddr, const float* __rest
         }
     }
     return sacc;
+}
+
+// rgb head epilogue shared by the tensor-core kernels (nerf.py:152-160): bias, optional per-image affine appearance
+// transform (3x4 matrix = affine(embedding_a[idx]), nerf.py:156-158), sigmoid when rgb_dim == 3, blend weight.
+// v = the row's raw fp32 accumulators of the rgb GEMM.
+__device__ __forceinline__ void tc_emit_rgb(const MlpArgs& m, int sub, int64_t row, int64_t slot, const uint32_t* v,
+                                            const float* bias, float sigma) {
+    const NetDims& nd = m.nd;
+    const int64_t o = (m.scatter ? row : slot) * m.out_cols;
+    const float w = m.slot_w ? m.slot_w[slot] : 1.0f;
+    if (nd.affine && nd.app > 0) {
+        const float* Pk = m.packed + (size_t)sub * m.lay.total;
+        const float* emb = Pk + m.lay.emb;
+        const float* aw = Pk + m.lay.aff_w;   // [app][12]
+        int id = (int)m.src.index(row);
+        id = min(max(id, 0), nd.app_count - 1);
+        float T[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) T[q] = Pk[m.lay.aff_b + q];
+        for (int j = 0; j < nd.app; ++j) {
+            const float e = emb[(size_t)id * nd.app + j];
+#pragma unroll
+            for (int q = 0; q < 12; ++q) T[q] = fmaf(e, aw[j * 12 + q], T[q]);
+        }
+        const float r0 = __uint_as_float(v[0]) + bias[0], r1 = __uint_as_float(v[1]) + bias[1], r2 = __uint_as_float(v[2]) + bias[2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float x = mn_sigmoid(fmaf(T[c * 4 + 2], r2, fmaf(T[c * 4 + 1], r1, T[c * 4 + 0] * r0)) + T[c * 4 + 3]);
+            m.out[o + c] = m.slot_w ? x * w : x;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            if (c < nd.rgb_dim) {
+                float x = __uint_as_float(v[c]) + bias[c];
+                if (nd.rgb_dim == 3) x = mn_sigmoid(x);
+                m.out[o + c] = m.slot_w ? x * w : x;
+            }
+        }
+    }
+    m.out[o + nd.rgb_dim] = m.slot_w ? sigma * w : sigma;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -617,6 +662,8 @@ struct TcArgs {
     int64_t x_plane_halves;
     int split;                    // 1: three MMA passes (hi*hi + hi*lo + lo*hi)
     int desc_swap;                // debug: 1 = record the in-kernel timeline (MN_TC_TRACE)
+    int nofetch;                  // debug (MN_TC_NOFETCH=1): producers skip the TMA copies (garbage results; isolates the
+                                  // MMA + epilogue pipeline from the weight stream when timing)
     int64_t n_tiles_cap;
 };
 
@@ -840,20 +887,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
                         uint32_t v[32];
                         tmem_ld32(t_acc, v);
                         tmem_ld_wait();
-                        if (row >= 0) {
-                            const NetDims& nd = A.m.nd;
-                            const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
-                            const float w = A.m.slot_w ? A.m.slot_w[slot] : 1.0f;
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) {
-                                if (c < nd.rgb_dim) {
-                                    float x = __uint_as_float(v[c]) + bias[c];
-                                    if (nd.rgb_dim == 3) x = mn_sigmoid(x);
-                                    A.m.out[o + c] = A.m.slot_w ? x * w : x;
-                                }
-                            }
-                            A.m.out[o + nd.rgb_dim] = A.m.slot_w ? sigma * w : sigma;
-                        }
+                        if (row >= 0) tc_emit_rgb(A.m, A.m.nd.affine ? sub_of(tile) : 0, row, slot, v, bias, sigma);
                     }
                     tc_fence_before();
                 } else {
@@ -915,25 +949,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const TcArgs A) {
 // and TMEM accumulator.  GEMMs are issued X_l, Y_l, X_l+1, Y_l+1, ...: the epilogue of X_l (16 warps)
 // runs entirely under the MMAs of Y_l and vice versa, so the tensor pipe only idles at pipeline fill.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPPMaxStages = 4;
+// A ring stage (16 KiB) carries either 32 K-columns of weights (activation segment: A operand = the tile's H buffer,
+// two K=16 MMAs) or, for the feature segments (PE / direction+appearance tiles), 16 K-columns of weights (<= 8 KiB) PLUS
+// the matching 16 K-columns x 128 rows of the tile's feature image (4 KiB at +8 KiB, one MMA): the features travel in
+// the same stream as the weights, so there is no separate feature buffer and no producer stall waiting for it.
+constexpr int kPPMaxStages = 8;
 constexpr int kPPSlabCols = 32;
 constexpr int kPPStageBytes = kPPSlabCols * 256 * 2;
+constexpr int kPPXCols = 16;
+constexpr int kPPXOff = 8192;
 
 struct PPLayout {
-    int ring, h, xa, f32, f32_stride, sigp, bars, total, stages;
+    int ring, h, f32, f32_stride, sigp, bars, total, stages;
 };
 
 __host__ __device__ inline PPLayout pp_layout(const TcPlan& p, bool bias_global) {
     PPLayout s;
-    const int kx0 = p.kpe > p.kaux ? p.kpe : p.kaux;
-    const int fixed = 2 * p.L * kTileM * 2 + kx0 * kTileM * 2 + (bias_global ? 0 : ((p.f32_floats * 4 + 15) / 16) * 16) + 2048 + 256;
-    const int kPPStages = (kSmemMax - fixed) / kPPStageBytes >= 4 ? 4 : 3;
-    const int kx = p.kpe > p.kaux ? p.kpe : p.kaux;
+    const int fixed = 2 * p.L * kTileM * 2 + (bias_global ? 0 : ((p.f32_floats * 4 + 15) / 16) * 16) + 2048 + 256;
+    int kPPStages = (kSmemMax - fixed) / kPPStageBytes;
+    if (kPPStages > kPPMaxStages) kPPStages = kPPMaxStages;
     s.stages = kPPStages;
     s.ring = 0;
     s.h = kPPStages * kPPStageBytes;
-    s.xa = s.h + 2 * p.L * kTileM * 2;
-    s.f32 = s.xa + kx * kTileM * 2;
+    s.f32 = s.h + 2 * p.L * kTileM * 2;
     s.f32_stride = ((p.f32_floats * 4 + 15) / 16) * 16;
     s.sigp = s.f32 + (bias_global ? 0 : s.f32_stride);    // ONE block: both tiles of a pair belong to the same sub-module
     s.bars = s.sigp + 2048;
@@ -951,19 +989,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     const int kPPStages = SL.stages;
     unsigned char* ring = smem + SL.ring;
     unsigned char* Hs = smem + SL.h;
-    unsigned char* XA = smem + SL.xa;
     float* F32 = reinterpret_cast<float*>(smem + SL.f32);
     float* SIGP = reinterpret_cast<float*>(smem + SL.sigp);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bars);
-    uint64_t* full = bars;            // [3]
-    uint64_t* empty = bars + 4;       // [<=4]
-    uint64_t* xa_full = bars + 8;
-    uint64_t* xa_empty = bars + 9;
-    uint64_t* acc_full = bars + 10;   // [2] per tile slot
-    uint64_t* epi_done = bars + 12;   // [2]
-    uint64_t* f32_full = bars + 14;   // [2]
-    uint64_t* f32_empty = bars + 16;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* full = bars;            // [<=8]
+    uint64_t* empty = bars + 8;       // [<=8]
+    uint64_t* acc_full = bars + 16;   // [2] per tile slot
+    uint64_t* epi_done = bars + 18;   // [2]
+    uint64_t* f32_full = bars + 20;   // [2]
+    uint64_t* f32_empty = bars + 22;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_slots = A.m.counters ? A.m.counters[CNT_NSLOTS] : A.m.B;
@@ -973,8 +1008,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kPPMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(xa_full, 1);
-        mbar_init(xa_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&epi_done[i], kEpiWarps);
@@ -1006,9 +1039,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
 
     if (warp == kWarpProd) {
         // =========================== TMA producer ===========================
-        if (lane == 0) {
+        if (lane == 0 && A.nofetch < 4) {
             int stage = 0;
-            uint32_t phase = 0, xphase = 0, fph[2] = {0, 0};
+            uint32_t phase = 0, fph[2] = {0, 0};
             const uint32_t f32_bytes = (uint32_t)SL.f32_stride;
             for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
             const int64_t t0 = 2 * pr;
@@ -1032,21 +1065,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                         for (int sgi = 0; sgi < g.nseg; ++sgi) {
                             const int kseg = g.k[sgi];
                             if (g.src[sgi] != SRC_H) {
+                                // feature segment: 16 K-columns of weights + the same 16 K-columns of the tile's feature image
                                 const __half* xt = A.ximg + tiles[sl] * (int64_t)(P.kpe + P.kaux) * kTileM +
                                                    (g.src[sgi] == SRC_XAUX ? (int64_t)P.kpe * kTileM : 0);
-                                mbar_wait(xa_empty, xphase ^ 1);
-                                mbar_expect_tx(xa_full, (uint32_t)(kseg * kTileM * 2));
-                                bulk_g2s(XA, xt, (uint32_t)(kseg * kTileM * 2), xa_full);
-                                xphase ^= 1;
-                            }
-                            for (int k0 = 0; k0 < kseg; k0 += kPPSlabCols) {
-                                const int kc = min(kPPSlabCols, kseg - k0);
-                                const uint32_t bytes = (uint32_t)(kc * g.n * 2);
-                                mbar_wait(&empty[stage], phase ^ 1);
-                                mbar_expect_tx(&full[stage], bytes);
-                                bulk_g2s(ring + (size_t)stage * kPPStageBytes, wimg + (size_t)(kbase + k0) * g.n * 2, bytes,
-                                         &full[stage]);
-                                if (++stage == kPPStages) { stage = 0; phase ^= 1; }
+                                const uint32_t wbytes = (uint32_t)(kPPXCols * g.n * 2), xbytes = (uint32_t)(kPPXCols * kTileM * 2);
+                                for (int k0 = 0; k0 < kseg; k0 += kPPXCols) {
+                                    unsigned char* st_base = ring + (size_t)stage * kPPStageBytes;
+                                    mbar_wait(&empty[stage], phase ^ 1);
+                                    if (A.nofetch) { mbar_arrive(&full[stage]); if (++stage == kPPStages) { stage = 0; phase ^= 1; } continue; }
+                                    mbar_expect_tx(&full[stage], wbytes + xbytes);
+                                    bulk_g2s(st_base, wimg + (size_t)(kbase + k0) * g.n * 2, wbytes, &full[stage]);
+                                    bulk_g2s(st_base + kPPXOff, xt + (size_t)k0 * kTileM, xbytes, &full[stage]);
+                                    if (++stage == kPPStages) { stage = 0; phase ^= 1; }
+                                }
+                            } else {
+                                for (int k0 = 0; k0 < kseg; k0 += kPPSlabCols) {
+                                    const int kc = min(kPPSlabCols, kseg - k0);
+                                    const uint32_t bytes = (uint32_t)(kc * g.n * 2);
+                                    mbar_wait(&empty[stage], phase ^ 1);
+                                    if (A.nofetch) { mbar_arrive(&full[stage]); if (++stage == kPPStages) { stage = 0; phase ^= 1; } continue; }
+                                    mbar_expect_tx(&full[stage], bytes);
+                                    bulk_g2s(ring + (size_t)stage * kPPStageBytes, wimg + (size_t)(kbase + k0) * g.n * 2, bytes,
+                                             &full[stage]);
+                                    if (++stage == kPPStages) { stage = 0; phase ^= 1; }
+                                }
                             }
                             kbase += kseg;
                         }
@@ -1057,12 +1099,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     } else if (warp == kWarpMma) {
         // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
         int stage = 0;
-        uint32_t phase = 0, xphase = 0, eph0 = 0, eph1 = 0;
+        uint32_t phase = 0, eph0 = 0, eph1 = 0;
         bool started0 = false, started1 = false;
-        const uint32_t h_base = smem_u32(Hs), xa_base = smem_u32(XA), ring_base = smem_u32(ring);
+        const uint32_t h_base = smem_u32(Hs), ring_base = smem_u32(ring);
         const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
-        const uint32_t xa_full_a = smem_u32(xa_full), xa_empty_a = smem_u32(xa_empty);
         const uint32_t acc_full_a = smem_u32(acc_full), epi_done_a = smem_u32(epi_done);
+        const uint64_t xd0 = make_desc(ring_base + (uint32_t)kPPXOff, kTileM * 16, 128);
         const uint64_t a_step = (uint64_t)((2 * kTileM * 16) >> 4);
         const uint64_t st_step = (uint64_t)(kPPStageBytes >> 4);
         for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
@@ -1076,8 +1118,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                 for (int sl = 0; sl < 2; ++sl) {
                     if (sl == 1 && !valid1) continue;
                     // the previous GEMM of this tile slot has been drained from TMEM and its activations are in H[sl]
+                    if (A.nofetch < 2) {
                     if (sl == 0) { if (started0) { mbar_wait_a(epi_done_a, eph0); eph0 ^= 1; } started0 = true; }
                     else         { if (started1) { mbar_wait_a(epi_done_a + 8, eph1); eph1 ^= 1; } started1 = true; }
+                    }
                     tc_fence_after();
                     if (lane == 0) trace_ev(A.desc_swap, 0, 1, sl, gi);          // MMA: dependencies satisfied, start issuing
                     const uint32_t d_tmem = tmem_base + (uint32_t)sl * 256u;
@@ -1085,15 +1129,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                     for (int sgi = 0; sgi < g.nseg; ++sgi) {
                         int rem = g.k[sgi];
                         const bool from_x = g.src[sgi] != SRC_H;
-                        uint64_t ad = make_desc(from_x ? xa_base : h_base + (uint32_t)(sl * h_bytes), kTileM * 16, 128);
                         if (from_x) {
-                            mbar_wait_a(xa_full_a, xphase);
-                            xphase ^= 1;
+                            // one K=16 MMA per stage; the A operand (feature columns) sits in the stage itself
+                            for (; rem > 0; rem -= kPPXCols) {
+                                const uint64_t so = (uint64_t)stage * st_step;
+                                if (A.nofetch < 4) mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
+                                tc_fence_after();
+                                mma_stage(d_tmem, xd0 + so, bd0 + so, 0, 0, idesc, accum, 0u, empty_a + 8u * (uint32_t)stage);
+                                accum = 1;
+                                if (++stage == kPPStages) { stage = 0; phase ^= 1; }
+                            }
+                            continue;
                         }
+                        uint64_t ad = make_desc(h_base + (uint32_t)(sl * h_bytes), kTileM * 16, 128);
                         while (rem > 0) {
                             const uint32_t two = rem >= 32 ? 1u : 0u;
                             const uint64_t bd = bd0 + (uint64_t)stage * st_step;
-                            mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
+                            if (A.nofetch < 4) mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
                             tc_fence_after();
                             mma_stage(d_tmem, ad, bd, ad + a_step, bd + b_step, idesc, accum, two, empty_a + 8u * (uint32_t)stage);
                             accum = 1;
@@ -1101,14 +1153,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                             rem -= 32;
                             if (++stage == kPPStages) { stage = 0; phase ^= 1; }
                         }
-                        if (from_x) commit_elect(xa_empty_a);
                     }
                     commit_elect(acc_full_a + 8u * (uint32_t)sl);
                     if (lane == 0) trace_ev(A.desc_swap, 0, 2, sl, gi);          // MMA: all MMAs of this GEMM issued
                 }
             }
         }
-    } else {
+        if (A.nofetch >= 4) {   // debug: nobody consumed the accumulators; drain the tensor pipe before TMEM is freed
+            commit_elect(smem_u32(&f32_full[1]));
+            mbar_wait_a(smem_u32(&f32_full[1]), 0);
+        }
+    } else if (A.nofetch < 4) {
         // =========================== epilogue (16 warps) ===========================
         const int q = warp & 3;
         const int part = warp >> 2;
@@ -1147,26 +1202,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                     const float* Fb = fb_[sl];
                     const float* bias = Fb + g.bias_off;
                     const int64_t row = row_[sl], slot = slot_[sl];
-                    if (g.epi == EPI_RGB) {
+                    if (A.nofetch >= 3) {
+                    } else if (g.epi == EPI_RGB) {
                         if (part == 0) {
                             uint32_t v[32];
                             tmem_ld32(t_acc, v);
                             tmem_ld_wait();
-                            if (row >= 0) {
-                                const NetDims& nd = A.m.nd;
-                                const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
-                                const float w = A.m.slot_w ? A.m.slot_w[slot] : 1.0f;
-                                const float sigma = sigma_[sl];
-#pragma unroll
-                                for (int c = 0; c < 32; ++c) {
-                                    if (c < nd.rgb_dim) {
-                                        float x = __uint_as_float(v[c]) + bias[c];
-                                        if (nd.rgb_dim == 3) x = mn_sigmoid(x);
-                                        A.m.out[o + c] = A.m.slot_w ? x * w : x;
-                                    }
-                                }
-                                A.m.out[o + nd.rgb_dim] = A.m.slot_w ? sigma * w : sigma;
-                            }
+                            if (row >= 0) tc_emit_rgb(A.m, A.m.nd.affine ? sub_of(t0 + sl) : 0, row, slot, v, bias, sigma_[sl]);
                         }
                     } else {
                         const bool want_sigma = g.epi == EPI_RELU_SIGMA;
@@ -1223,10 +1265,33 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
 
 #include "mn_mlp_ts.cuh"
 #include "mn_mlp_c2.cuh"
+#include "mn_mlp_wide.cuh"
 
 }  // namespace
 
 // =================================================================================================
+// Tensor map over a buffer viewed as [rows][256 B] with boxes of box_rows rows.  cuTensorMapEncodeTiled is resolved
+// through the runtime so that the library does not link against libcuda (it must load on GPU-less hosts).
+static bool encode_rows256_map(void* base, uint64_t rows, uint32_t box_rows, void* out128) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+        enc = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t gdim[2] = {256, rows};
+    const cuuint64_t gstride[1] = {256};
+    const cuuint32_t estr[2] = {1, 1};
+    const cuuint32_t box[2] = {256, box_rows};
+    return enc(reinterpret_cast<CUtensorMap*>(out128), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 size_t mn_mlp_tc_workspace(const mn_model* m, int64_t n_tiles128, int precision) {
     TcPlan P;
     if (!build_plan(m->nd, &P)) return 0;
@@ -1244,34 +1309,19 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
     // [hi plane][lo plane][fp32 block, 256-aligned][half-major hi plane for the TS kernel]
     const size_t ts_off = (size_t)P.plane_bytes * 2 + (size_t)(((P.f32_floats * 4 + 255) / 256) * 256);
     const size_t c2_off = ts_off + (size_t)P.plane_bytes;      // [N-half of CTA 0][N-half of CTA 1] images for cta_group::2
-    const size_t sub_bytes = mn_align(c2_off + (size_t)P.plane_bytes, 256);
+    // 512-wide network: only the wide kernel runs it; its one image ([N half of 256][K/8][256][8]) lives in the hi plane
+    const bool wide = nd.L > 256;
+    const size_t sub_bytes = wide ? mn_align(ts_off, 256) : mn_align(c2_off + (size_t)P.plane_bytes, 256);
     if (!m->tc_packed) {
         MN_CUDA(ctx, cudaMalloc(&m->tc_packed, sub_bytes * m->d.n_sub));
         MN_CUDA(ctx, cudaMemsetAsync(m->tc_packed, 0, sub_bytes * m->d.n_sub, st));
         m->tc_sub_bytes = sub_bytes;
         // tensor maps for the cta_group::2 kernel (its TMA loads must be the .tensor form to signal the peer CTA's barrier)
-        const cuuint64_t rows = (cuuint64_t)(sub_bytes * m->d.n_sub / 256);
-        const cuuint64_t gdim[2] = {256, rows};
-        const cuuint64_t gstride[1] = {256};
-        const cuuint32_t estr[2] = {1, 1};
-        const cuuint32_t box_big[2] = {256, 64}, box_small[2] = {256, 8};
-        // resolved through the runtime so that the library does not link against libcuda (it must load on GPU-less hosts)
-        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        CUresult r1 = CUDA_ERROR_NOT_FOUND, r2 = CUDA_ERROR_NOT_FOUND;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn) {
-            EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
-            r1 = enc(reinterpret_cast<CUtensorMap*>(m->tmap_big), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, m->tc_packed, gdim, gstride, box_big, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            r2 = enc(reinterpret_cast<CUtensorMap*>(m->tmap_small), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, m->tc_packed, gdim, gstride, box_small, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        }
-        m->tmap_ready = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) ? 1 : 0;
+        const uint64_t rows = (uint64_t)(sub_bytes * m->d.n_sub / 256);
+        const uint32_t boxes[3] = {64, 32, 8};
+        m->tmap_ready = 1;
+        for (int b = 0; b < 3; ++b)
+            if (!encode_rows256_map(m->tc_packed, rows, boxes[b], m->tmap_w[b])) m->tmap_ready = 0;
     }
     unsigned char* base = (unsigned char*)m->tc_packed + (size_t)sub * sub_bytes;
     const float* Pk = m->packed + (size_t)sub * m->lay.total;
@@ -1282,6 +1332,13 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         const int64_t n = (int64_t)g.n * K;
         __half* hi = reinterpret_cast<__half*>(base + g.w_off);
         __half* lo = reinterpret_cast<__half*>(base + P.plane_bytes + g.w_off);
+        if (wide) {
+            tc_pack_half_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, g.n < 256 ? g.n : 256, k_real0, k_pad0, hi);
+            MN_LAUNCH_CHECK(ctx);
+            tc_pack_f32_kernel<<<(unsigned)mn_cdiv(P.bstride, 256), 256, 0, st>>>(bias, n_bias, f32 + g.bias_off, P.bstride);
+            MN_LAUNCH_CHECK(ctx);
+            return MN_OK;
+        }
         tc_pack_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, k_real0, k_pad0, hi, lo);
         MN_LAUNCH_CHECK(ctx);
         tc_pack_half_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, g.n < 128 ? g.n : 128, k_real0, k_pad0,
@@ -1320,8 +1377,11 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     TcArgs A{};
     if (!build_plan(a.nd, &A.plan) || !m->tc_ready)
         return mn_fail(ctx, MN_ERR_UNSUPPORTED,
-                       "tensor-core MLP path covers layer_dim <= 256 (multiple of 32), rgb_dim <= 32, no affine appearance; "
+                       "tensor-core MLP path covers layer_dim 64..256 (multiple of 64) or 512 and rgb_dim <= 32; "
                        "use precision 'fp32' for this model");
+    if (a.nd.L > 256 && precision == MN_PREC_TC_F16X3)
+        return mn_fail(ctx, MN_ERR_UNSUPPORTED,
+                       "precision 'tc_f16x3' covers layer_dim <= 256; use 'tc_f16' or 'fp32' for the 512-wide network");
     if (n_tiles128 <= 0) return MN_OK;
     TcPlan& P = A.plan;
     const int split = precision == MN_PREC_TC_F16X3 ? 1 : 0;
@@ -1336,6 +1396,12 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         desc_swap = (e && e[0] == '1') ? 1 : 0;
     }
     A.desc_swap = desc_swap;
+    static int nofetch = -1;
+    if (nofetch < 0) {
+        const char* e = getenv("MN_TC_NOFETCH");
+        nofetch = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 0;   // 2: MMAs also ignore epi_done; 3: and the epilogue is empty
+    }
+    A.nofetch = nofetch;
     A.n_tiles_cap = n_tiles128;
     const size_t need = mn_mlp_tc_workspace(m, n_tiles128, precision);
     if (ws_bytes < need || !ws) return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_mlp_tc_launch: workspace too small");
@@ -1355,6 +1421,44 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         tc_encode_kernel<<<(unsigned)n_tiles128, kTileM, enc_sm, st>>>(a, P.kpe, P.kaux, split, ximg, A.x_plane_halves);
     MN_LAUNCH_CHECK(ctx);
 
+    if (P.L > 256) {
+        const WLayout WL = w_layout(P);
+        if (WL.total > kSmemMax) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core MLP (512-wide): shared-memory budget exceeded");
+        // MN_TC_CLUSTER=2: clusters of two CTAs share one multicast weight stream (the router's bucket alignment
+        // guarantees that tiles 2p and 2p+1 belong to one sub-module).  Halves the L2 reads but measured 2-3 % SLOWER
+        // on B200 (the kernel is bound by shared-memory traffic, not by L2), so the default is one CTA per cluster.
+        static int cs = -1;
+        if (cs < 0) {
+            const char* e = getenv("MN_TC_CLUSTER");
+            cs = (e && e[0] == '2') ? 2 : 1;
+        }
+        mn_prof_begin(ctx, st);
+        if (cs == 2) {
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WL.total));
+            const int64_t groups = (n_tiles128 + 1) / 2;
+            const unsigned ncl = (unsigned)(groups < ctx->sm_count / 2 ? groups : ctx->sm_count / 2);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(2 * ncl);
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = (size_t)WL.total;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            MN_CUDA(ctx, cudaLaunchKernelEx(&cfg, tc_mlp_wide_kernel<2>, A));
+        } else {
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WL.total));
+            const unsigned grid_w = (unsigned)(n_tiles128 < ctx->sm_count ? n_tiles128 : ctx->sm_count);
+            tc_mlp_wide_kernel<1><<<grid_w, kThreads, WL.total, st>>>(A);
+        }
+        mn_prof_end(ctx, st);
+        MN_LAUNCH_CHECK(ctx);
+        return MN_OK;
+    }
     const SmemLayout SL = smem_layout(P, split != 0);
     const int total = SL.total;
     if (total > kSmemMax || SL.stages < 2) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core MLP: shared-memory budget exceeded");
@@ -1387,16 +1491,22 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         const PPLayout PL = pp_layout(P, bias_global != 0);
         const TsLayout TL = ts_layout(P);
         const C2Layout CL = c2_layout(P);
-        if (use_c2 && m->tmap_ready && CL.total <= kSmemMax && (n_tiles128 % 2) == 0) {
+        if (use_c2 && !a.nd.affine && P.L == 256 && m->tmap_ready && CL.total <= kSmemMax && CL.stages >= 3 && (n_tiles128 % 4) == 0) {
+            C2Maps maps;
+            memcpy(&maps.w64, m->tmap_w[0], 128);
+            memcpy(&maps.w32, m->tmap_w[1], 128);
+            memcpy(&maps.w8, m->tmap_w[2], 128);
+            const uint64_t xrows = (uint64_t)n_tiles128 * (uint64_t)(P.kpe + P.kaux);
+            if (!encode_rows256_map(ximg, xrows, 32, &maps.x32) || !encode_rows256_map(ximg, xrows, 16, &maps.x16))
+                return mn_fail(ctx, MN_ERR_CUDA, "cuTensorMapEncodeTiled failed for the feature tiles");
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL.total));
-            int64_t n_super = n_tiles128 / 2;
-            int64_t n_cl = (n_super + 1) / 2 < ctx->sm_count / 2 ? (n_super + 1) / 2 : ctx->sm_count / 2;
+            const int64_t n_quads = n_tiles128 / 4;
+            int64_t n_cl = n_quads < ctx->sm_count / 2 ? n_quads : ctx->sm_count / 2;
             if (n_cl < 1) n_cl = 1;
             mn_prof_begin(ctx, st);
-            tc_mlp_c2_kernel<<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A, *reinterpret_cast<const CUtensorMap*>(m->tmap_big),
-                                                                            *reinterpret_cast<const CUtensorMap*>(m->tmap_small));
+            tc_mlp_c2_kernel<<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A, maps);
         } else
-        if (use_ts && P.L % 128 == 0 && TL.stages >= 4) {
+        if (use_ts && !a.nd.affine && P.L % 128 == 0 && TL.stages >= 4) {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL.total));
             mn_prof_begin(ctx, st);
             tc_mlp_ts_kernel<<<grid, kTsThreads, TL.total, st>>>(A);

@@ -5,7 +5,7 @@
 #define MN_MAX_LAYERS 16
 #define MN_MAX_SUB 64
 #define MN_TILE 128     // rows of one tensor-core MLP tile
-#define MN_BUCKET 256   // slot-space bucket alignment: a CTA pair (cta_group::2, 2 x 128 rows) never mixes sub-modules
+#define MN_BUCKET 512   // slot-space bucket alignment: four consecutive 128-row tiles (two ping-pong slots of a CTA pair) never mix sub-modules
 
 // Offsets (in floats) of each packed tensor inside one sub-module's fp32 buffer.  All matrices are
 // stored K-major ("transposed": Wt[k][n] = W[n][k]) so that consecutive output channels are contiguous.
@@ -33,9 +33,8 @@ struct mn_model {
     void* tc_packed = nullptr;
     size_t tc_sub_bytes = 0;
     int tc_ready = 0;
-    // TMA tensor maps over tc_packed viewed as [rows][256 B] (boxes of 64 and 8 rows); CUtensorMap is 128 B, 64-B aligned
-    alignas(64) unsigned char tmap_big[128] = {0};
-    alignas(64) unsigned char tmap_small[128] = {0};
+    // TMA tensor maps over tc_packed viewed as [rows][256 B] (boxes of 64, 32 and 8 rows); CUtensorMap is 128 B, 64-B aligned
+    alignas(64) unsigned char tmap_w[3][128] = {{0}};
     int tmap_ready = 0;
 };
 

@@ -15,9 +15,10 @@ import cases as Cs
 from test_gpu_parity import product_net
 
 dev = torch.device('cuda:0')
-spec = O.NerfSpec()
+WIDTH = int(os.environ.get('TRACE_WIDTH', '256'))
+spec = O.NerfSpec(layer_dim=WIDTH)
 net = O.make_net('nerf', spec, seed=3)
-n = 148 * 128 * 8
+n = 148 * 128 * (8 if WIDTH == 256 else 4)
 x = Cs.nerf_rows(spec, n, 9).to(dev)
 p = product_net(net)
 M.set_precision('tc_f16')
@@ -45,3 +46,24 @@ st = [t for t, who, e, sl, gi in ev if e == 1 and sl == 0]
 if len(st) > 20:
     d = [b - a for a, b in zip(st[5:], st[6:])]
     print('median ns between consecutive slot-0 GEMM starts:', sorted(d)[len(d) // 2])
+
+# per (gemm, slot/half) medians over all recorded tiles: issue time, dependency stall before the next start, epilogue time
+import collections
+mma = [(t, e, sl, gi) for t, who, e, sl, gi in ev if who == 0]
+epi = [(t, e, sl, gi) for t, who, e, sl, gi in ev if who == 1]
+issue, stall, epit = collections.defaultdict(list), collections.defaultdict(list), collections.defaultdict(list)
+for (ta, ea, sa, ga), (tb, eb, sb, gb) in zip(mma, mma[1:]):
+    if ea == 1 and eb == 2 and (sa, ga) == (sb, gb):
+        issue[(ga, sa)].append(tb - ta)
+    if ea == 2 and eb == 1:
+        stall[(gb, sb)].append(tb - ta)
+for (ta, ea, sa, ga), (tb, eb, sb, gb) in zip(epi, epi[1:]):
+    if ea == 3 and eb == 4 and (sa, ga) == (sb, gb):
+        epit[(ga, sa)].append(tb - ta)
+med = lambda v: sorted(v)[len(v) // 2] if v else -1
+print('gemm slot/half | issue ns | stall-before ns | epilogue ns')
+tot_i = tot_s = 0
+for k in sorted(issue):
+    print(f'{k[0]:4d} {k[1]:2d} | {med(issue[k]):6d} | {med(stall[k]):6d} | {med(epit[k]):6d}')
+    tot_i += med(issue[k]); tot_s += max(med(stall[k]), 0)
+print('sum of medians: issue', tot_i, 'stall', tot_s)

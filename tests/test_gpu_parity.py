@@ -21,8 +21,9 @@ DEV = torch.device('cuda:0')
 MLP_TOL = {'fp32': 1e-5, 'tc_f16': 5e-4, 'tc_f16x3': 1e-5}
 RENDER_TOL = {'fp32': 1e-4, 'tc_f16': 2e-4, 'tc_f16x3': 1e-4}
 PRECS = ['fp32', 'tc_f16', 'tc_f16x3']
-TC_UNSUPPORTED_NERF = {'fg512', 'affine'}      # served by the fp32 kernel only
-TC_UNSUPPORTED_RENDER = {'c4_mega25_512'}
+# the 512-wide network runs on tensor cores in single-pass fp16 only (mn_mlp_wide.cuh); 'tc_f16x3' covers <= 256
+TC_UNSUPPORTED_NERF = {'tc_f16x3': {'fg512'}}
+TC_UNSUPPORTED_RENDER = {'tc_f16x3': {'c4_mega25_512'}}
 
 
 def M():
@@ -93,8 +94,8 @@ def test_nerf_variants(golden, vname, prec):
     assert C.net_checksum(net) == gd['wsum']
     p = product_net(net)
     tol = MLP_TOL[prec]
-    if prec != 'fp32' and vname in TC_UNSUPPORTED_NERF:
-        with pytest.raises(RuntimeError, match="use precision 'fp32'"):
+    if vname in TC_UNSUPPORTED_NERF.get(prec, ()):
+        with pytest.raises(RuntimeError, match="use 'tc_f16' or 'fp32'"):
             p(x.to(DEV))
         return
     assert relerr(p(x.to(DEV)), gd['out']) <= tol
@@ -117,13 +118,16 @@ def test_nerf_large_batch_matches_oracle():
 
 
 @pytest.mark.parametrize('prec', PRECS)
-def test_nerf_many_tiles_per_cta(prec):
+@pytest.mark.parametrize('width', [256, 512])
+def test_nerf_many_tiles_per_cta(prec, width):
     """More 128-row tiles than 3 x 148 SMs: exercises the persistent kernels' tile loop, barrier parities across
     tiles and the ragged last tile."""
+    if width == 512 and prec == 'tc_f16x3':
+        pytest.skip("512-wide: 'tc_f16' or 'fp32' only")
     M().set_precision(prec)
-    spec = O.NerfSpec()
+    spec = O.NerfSpec(layer_dim=width)
     net = O.make_net('nerf', spec, seed=4)
-    n = 148 * 128 * 3 + 77
+    n = 148 * 128 * (3 if width == 256 else 2) + 77
     x = C.nerf_rows(spec, n, 13)
     with torch.inference_mode():
         ref = O.nerf_forward(spec, net.weights[0], x)
@@ -344,8 +348,8 @@ def test_render_rays(golden, rname, prec):
     from argparse import Namespace
     m = M()
     m.set_precision(prec)
-    if prec != 'fp32' and rname in TC_UNSUPPORTED_RENDER:
-        pytest.skip('512-wide sub-modules run on the fp32 kernel in this round')
+    if rname in TC_UNSUPPORTED_RENDER.get(prec, ()):
+        pytest.skip("512-wide sub-modules: 'tc_f16' or 'fp32' only")
     net, bg_net, rays, idx, opts, center, radius = C.render_case(rname)
     gd = golden[f'render_{rname}']
     assert C.net_checksum(net) + (C.net_checksum(bg_net) if bg_net else 0.0) == gd['wsum']
