@@ -10,8 +10,8 @@
 // warps drain its own 128 TMEM lanes under the other tile's MMAs; feature columns ride in the weight ring.
 //
 // Cross-CTA signalling (all barriers live at identical offsets in both CTAs):
-//   full[s]            the LEADER's barrier counts both producers: each arrives with expect_tx and its tensor-map TMA
-//                      copies (.cta_group::2) complete_tx on the leader's barrier (shared::cluster address from mapa);
+//   full[s]            the LEADER's barrier: its producer arrives with expect_tx for the bytes of both CTAs, and both
+//                      CTAs' tensor-map TMA copies (.cta_group::2) complete_tx on it (shared::cluster address from mapa);
 //   empty[s], acc_full[slot]   tcgen05.commit ... multicast::cluster to both CTAs;
 //   epi_done[slot]     leader's barrier, 32 arrivals (16 epilogue warps per CTA, the peer's arrive remotely).
 #pragma once
@@ -168,7 +168,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const int xrows_tile = P.kpe + P.kaux;                           // 256-byte rows per feature tile image (one per K-column)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kC2MaxStages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kC2MaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&epi_done[i], 2 * kEpiWarps);
@@ -202,16 +202,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         // =========================== TMA producer (each CTA streams its N-half of every weight slab) ===========================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0, fph = 0;
+            uint32_t phase = 0, fph_e = 0;
+            int last_sub = -1;
             const uint32_t f32_bytes = (uint32_t)SL.f32_stride;
             const uint32_t full_l = mapa_u32(smem_u32(full), 0);          // the LEADER's full[] barriers count both halves
             const uint32_t ring_a = smem_u32(ring);
             for (int64_t q = cl; q < n_quads; q += ncl) {
-                const unsigned char* wsub = A.wpack + (size_t)sub_of(4 * q) * P.sub_bytes;
-                mbar_wait(f32_empty, fph ^ 1);
-                mbar_expect_tx(f32_full, f32_bytes);
-                bulk_g2s(reinterpret_cast<unsigned char*>(F32), wsub + (size_t)P.plane_bytes * 2, f32_bytes, f32_full);
-                fph ^= 1;
+                const int sub0 = sub_of(4 * q);
+                const unsigned char* wsub = A.wpack + (size_t)sub0 * P.sub_bytes;
+                if (sub0 != last_sub) {           // bias / sigma block: re-staged only when the sub-module changes
+                    if (last_sub >= 0) { mbar_wait(f32_empty, fph_e); fph_e ^= 1; }
+                    mbar_expect_tx(f32_full, f32_bytes);
+                    bulk_g2s(reinterpret_cast<unsigned char*>(F32), wsub + (size_t)P.plane_bytes * 2, f32_bytes, f32_full);
+                    last_sub = sub0;
+                }
                 for (int gi = 0; gi < n_gemm; ++gi) {
                     const TcGemm& g = P.g[gi];
                     const int nhalf = g.n >> 1;                                   // weight rows held by this CTA
@@ -232,7 +236,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                 const uint32_t bar = full_l + 8u * (uint32_t)stage;
                                 const uint32_t dst = ring_a + (uint32_t)stage * kC2StageBytes;
                                 mbar_wait(&empty[stage], phase ^ 1);
-                                mbar_expect_tx_cluster(bar, wbytes + xbytes);
+                                // the leader announces the bytes of BOTH CTAs (the streams are symmetric); the peer's copies
+                                // only complete_tx on the leader's barrier - no remote arrive on the critical path
+                                if (leader) mbar_expect_tx(&full[stage], 2u * (wbytes + xbytes));
                                 const int wrow0 = (int)((size_t)((wimg + (size_t)(kbase + k0) * nhalf * 2) - A.wpack) >> 8);
                                 c2_copy_rows(dst, wrow0, (int)(wbytes >> 8), bar, &TM.w64, 64, &TM.w32, 32, &TM.w8, 8);
                                 if (from_x) c2_copy_rows(dst + kC2XOff, xrow0 + k0, kc, bar, &TM.x32, 32, &TM.x16, 16, nullptr, 0);
@@ -268,6 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                         if (sl == 0) { if (started0) { mbar_wait_cluster(epi_done_a, eph0); eph0 ^= 1; } started0 = true; }
                         else         { if (started1) { mbar_wait_cluster(epi_done_a + 8, eph1); eph1 ^= 1; } started1 = true; }
                         tc_fence_after();
+                        if (lane == 0) trace_ev(A.desc_swap, 0, 1, sl, gi);
                         const uint32_t d_tmem = tmem_base + (uint32_t)sl * 256u;
                         uint32_t accum = 0;
                         for (int sgi = 0; sgi < g.nseg; ++sgi) {
@@ -288,6 +295,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                             }
                         }
                         c2_commit_both(acc_full_a + 8u * (uint32_t)sl);
+                        if (lane == 0) trace_ev(A.desc_swap, 0, 2, sl, gi);
                     }
                 }
             }
@@ -299,6 +307,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int r = q4 * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
         uint32_t aph0 = 0, aph1 = 0, fph = 0;
+        int last_sub = -1;
         const int L = P.L;
         const uint32_t epi_done_l = mapa_u32(smem_u32(epi_done), 0);      // leader's barrier (local address if we are the leader)
         for (int64_t q = cl; q < n_quads; q += ncl) {
@@ -308,9 +317,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 slot_[sl] = (4 * q + 2 * sl + rank) * kTileM + r;
                 if (slot_[sl] < n_slots) row_[sl] = A.m.slot_row ? (int64_t)A.m.slot_row[slot_[sl]] : slot_[sl];
             }
-            const int sub = A.m.nd.affine ? sub_of(4 * q) : 0;
-            mbar_wait(f32_full, fph);
-            fph ^= 1;
+            const int sub = sub_of(4 * q);
+            if (sub != last_sub) {
+                if (last_sub >= 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(f32_empty);
+                }
+                mbar_wait(f32_full, fph);
+                fph ^= 1;
+                last_sub = sub;
+            }
             for (int gi = 0; gi < n_gemm; ++gi) {
                 const TcGemm& g = P.g[gi];
 #pragma unroll
@@ -318,6 +334,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     if (sl == 0) { mbar_wait(&acc_full[0], aph0); aph0 ^= 1; }
                     else         { mbar_wait(&acc_full[1], aph1); aph1 ^= 1; }
                     tc_fence_after();
+                    if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 3, sl, gi);
                     const uint32_t t_acc = t_lane + (uint32_t)sl * 256u;
                     const float* bias = F32 + g.bias_off;
                     const int64_t row = row_[sl], slot = slot_[sl];
@@ -366,11 +383,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     }
                     tc_fence_before();
                     __syncwarp();
+                    if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 4, sl, gi);
                     if (lane == 0) mbar_arrive_cluster(epi_done_l + 8u * (uint32_t)sl);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(f32_empty);
         }
     }
     tc_fence_before();

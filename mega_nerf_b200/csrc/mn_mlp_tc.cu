@@ -1041,20 +1041,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
         // =========================== TMA producer ===========================
         if (lane == 0 && A.nofetch < 4) {
             int stage = 0;
-            uint32_t phase = 0, fph[2] = {0, 0};
+            uint32_t phase = 0, fph_e = 0;
+            int last_sub = -1;
             const uint32_t f32_bytes = (uint32_t)SL.f32_stride;
             for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
-            const int64_t t0 = 2 * pr;
+                const int64_t t0 = 2 * pr;
                 const int64_t tiles[2] = {t0, t0 + 1};
                 const unsigned char* wsub[2] = {nullptr, nullptr};
-                for (int sl = 0; sl < 2; ++sl) {
-                    if (tiles[sl] >= n_tiles) continue;
-                    wsub[sl] = A.wpack + (size_t)sub_of(tiles[sl]) * P.sub_bytes;
-                    if (kBiasGlobal || sl == 1) continue;
-                    mbar_wait(&f32_empty[0], fph[0] ^ 1);
+                const int sub0 = sub_of(t0);
+                for (int sl = 0; sl < 2; ++sl)
+                    if (tiles[sl] < n_tiles) wsub[sl] = A.wpack + (size_t)sub0 * P.sub_bytes;
+                if (!kBiasGlobal && sub0 != last_sub) {
+                    // the bias / sigma block is re-staged only when the sub-module changes (a handful of times per launch):
+                    // the weight stream of consecutive pairs is not interrupted by waiting for the epilogue
+                    if (last_sub >= 0) { mbar_wait(&f32_empty[0], fph_e); fph_e ^= 1; }
                     mbar_expect_tx(&f32_full[0], f32_bytes);
                     bulk_g2s(reinterpret_cast<unsigned char*>(F32), wsub[0] + (size_t)P.plane_bytes * 2, f32_bytes, &f32_full[0]);
-                    fph[0] ^= 1;
+                    last_sub = sub0;
                 }
                 for (int gi = 0; gi < n_gemm; ++gi) {
                     const TcGemm& g = P.g[gi];
@@ -1169,11 +1172,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
         const int part = warp >> 2;
         const int r = q * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t aph0 = 0, aph1 = 0, fph0 = 0, fph1 = 0;
+        uint32_t aph0 = 0, aph1 = 0, fph0 = 0;
+        int last_sub = -1;
         const int L = P.L;
         for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
             const int64_t t0 = 2 * pr;
             const bool valid1 = t0 + 1 < n_tiles;
+            if (!kBiasGlobal) {
+                const int sub0 = sub_of(t0);
+                if (sub0 != last_sub) {
+                    if (last_sub >= 0) {            // done with the previous sub-module's block
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&f32_empty[0]);
+                    }
+                    mbar_wait(&f32_full[0], fph0);
+                    fph0 ^= 1;
+                    last_sub = sub0;
+                }
+            }
             int64_t slot_[2], row_[2] = {-1, -1};
             float sigma_[2] = {0.0f, 0.0f};
             const float* fb_[2] = {nullptr, nullptr};
@@ -1186,7 +1202,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                                                              (size_t)P.plane_bytes * 2);
                 } else {
                     fb_[sl] = F32;
-                    if (sl == 0) { mbar_wait(&f32_full[0], fph0); fph0 ^= 1; }
                 }
             }
             for (int gi = 0; gi < n_gemm; ++gi) {
@@ -1252,8 +1267,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                     if (lane == 0) mbar_arrive(&epi_done[sl]);
                 }
             }
-            __syncwarp();
-            if (lane == 0 && !kBiasGlobal) mbar_arrive(&f32_empty[0]);
         }
     }
     tc_fence_before();
