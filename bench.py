@@ -196,6 +196,7 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('MN_B200_PRECISION', 'tc_f16'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-graph', action='store_true', help='issue every step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -231,16 +232,29 @@ def main():
     h = K.ctx(dev)
     L = K.lib()
 
-    def step_resident():
+    graphed = None      # the public CUDA-graph replay of render_rays (mega_nerf_b200/graph.py); set after the eager warm-up
+
+    def step_eager():
         res, _ = M.render_rays(model, None, rays_d, idx_d, hp, None, None, True, False, False)
         if world > 1:
             dist.all_gather_into_tensor(gather_buf, torch.cat([res['rgb_fine'], res['depth_fine'].unsqueeze(-1)], -1))
         return res
 
+    def step_resident():
+        if graphed is None:
+            return step_eager()
+        res = graphed(rays_d, idx_d)                 # device-resident inputs -> static buffers (D2D) -> graph replay
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, torch.cat([res['rgb_fine'], res['depth_fine'].unsqueeze(-1)], -1))
+        return res
+
     def step_e2e():
-        r = rays_pin.to(dev, non_blocking=True)
-        i = idx_pin.to(dev, non_blocking=True)
-        res, _ = M.render_rays(model, None, r, i, hp, None, None, True, False, False)
+        if graphed is None:
+            r = rays_pin.to(dev, non_blocking=True)
+            i = idx_pin.to(dev, non_blocking=True)
+            res, _ = M.render_rays(model, None, r, i, hp, None, None, True, False, False)
+        else:
+            res = graphed(rays_pin, idx_pin)         # pinned host inputs -> static device buffers (H2D) -> graph replay
         packed = torch.cat([res['rgb_fine'], res['depth_fine'].unsqueeze(-1)], -1)
         if world > 1:
             dist.all_gather_into_tensor(gather_buf, packed)
@@ -270,15 +284,28 @@ def main():
         step_resident()
         step_e2e()
     torch.cuda.synchronize()
-    log('warm-up done')
+    launches0 = L.mn_launch_count(h)
+    step_eager()
+    launches_per_step = L.mn_launch_count(h) - launches0      # kernels of ours per step (the graph replays the same list)
+    if not args.no_graph:
+        try:
+            graphed = M.GraphedRenderRays(model, hp, N_RAYS, dev, with_indices=True, get_depth=True)
+            graphed.capture(rays_d, idx_d)
+            for _ in range(args.warmup):
+                step_resident()
+                step_e2e()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            log(f'CUDA graph capture failed ({e!r}); running eagerly')
+            graphed = None
+    log(f'warm-up done (cuda graph: {graphed is not None})')
 
     # ---- device-resident throughput (the `value`) with clocks sampled during the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = L.mn_launch_count(h)
     ms_total = timed(step_resident, args.steps)
-    launches = L.mn_launch_count(h) - launches0
+    launches = launches_per_step * args.steps
     samples_per_step = N_RAYS * (COARSE + FINE) * world
     value = samples_per_step * args.steps / (ms_total * 1e-3)
 
@@ -291,7 +318,7 @@ def main():
     # ---- MLP kernel duration by CUDA events on the launching stream (roofline)
     nat = model._native()
     K.check(L.mn_profile_enable(h, 1), h)
-    timed(step_resident, args.steps)
+    timed(step_eager, args.steps)
     tot_ms, n_l = C.c_double(), C.c_longlong()
     K.check(L.mn_profile_read(h, C.byref(tot_ms), C.byref(n_l)), h)
     K.check(L.mn_profile_enable(h, 0), h)
@@ -339,7 +366,9 @@ def main():
             'config': {'workload': f'{WL["desc"]}, {N_RAYS} rays x ({COARSE} coarse + {FINE} fine) '
                                    f'per GPU, boundary_margin {MARGIN} (m = {mult:.3f} sub-modules/sample), random-init weights',
                        'parallelism': f'ray-sharded x{world}, weights replicated, 1 all-gather of [rays,4] per step' if world > 1 else 'single GPU',
-                       'precision': args.precision, 'l2': f'flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)',
+                       'precision': args.precision,
+                       'launch': 'one CUDA graph replay per step (mega_nerf_b200.GraphedRenderRays)' if graphed is not None else 'eager launches',
+                       'l2': f'flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)',
                        'rays_per_sec': value / (COARSE + FINE)},
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': rays_pin.numel() * 4 + idx_pin.numel() * 4, 'd2h_bytes_per_step': out_pin.numel() * 4},

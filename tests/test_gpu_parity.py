@@ -366,3 +366,24 @@ def test_render_rays(golden, rname, prec):
         assert res[k].shape == v.shape and res[k].dtype == torch.float32 and res[k].device.type == 'cuda'
         e = relerr(res[k], v)
         assert e <= (5 * tol if 'variance' in k else tol), (k, e)
+
+
+def test_graphed_render_rays_matches_eager():
+    """CUDA-graph replay (mega_nerf_b200/graph.py) returns exactly what the eager call returns, for fresh inputs too."""
+    from argparse import Namespace
+    m = M()
+    m.set_precision('tc_f16')
+    net, _, rays, idx, opts, _, _ = C.render_case('c2_mega8_blend')
+    pn = product_net(net)
+    hp = Namespace(**vars(opts))
+    g = m.GraphedRenderRays(pn, hp, rays.shape[0], DEV, with_indices=True, get_depth=True)
+    for shift in (0, 1):
+        r = rays.roll(shift, 0).to(DEV)
+        i = idx.roll(shift, 0).to(DEV)
+        want, _ = m.render_rays(pn, None, r, i, hp, None, None, True, False, False)
+        got = g(r, i)
+        assert set(got) == set(want)
+        for k in want:
+            assert torch.equal(got[k], want[k]), k
+    with pytest.raises(ValueError):
+        g(rays[:-1].to(DEV), idx[:-1].to(DEV))
