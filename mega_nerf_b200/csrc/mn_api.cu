@@ -242,6 +242,7 @@ size_t mn_model_workspace_bytes(const mn_model* m, int64_t B, int precision) {
     size_t bytes = 256;
     if (m->d.kind == 2) {
         bytes += mn_align((size_t)cap * sizeof(int));                                       // slot_row
+        bytes += mn_align(mn_route_scratch_bytes(m, B));                                    // routing decisions of the count pass
         if (m->d.boundary_margin > 1.0f) {
             bytes += mn_align((size_t)cap * sizeof(float));                                 // slot_w
             bytes += mn_align((size_t)B * m->d.n_sub * sizeof(int));                        // row_slots
@@ -330,6 +331,7 @@ int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, i
     float* slot_out = nullptr;
     if (d.kind == 2) {
         int* slot_row = (int*)carve((size_t)cap * sizeof(int));
+        void* route_scratch = carve(mn_route_scratch_bytes(m, B));
         float* slot_w = nullptr;
         const bool blend = d.boundary_margin > 1.0f;
         if (blend) {
@@ -337,7 +339,7 @@ int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, i
             row_slots = (int*)carve((size_t)B * d.n_sub * sizeof(int));
             slot_out = (float*)carve((size_t)cap * a.out_cols * sizeof(float));
         }
-        if ((rc = mn_route_build(ctx, m, src, B, cap, slot_row, slot_w, row_slots, st))) return rc;
+        if ((rc = mn_route_build(ctx, m, src, B, cap, slot_row, slot_w, row_slots, route_scratch, st))) return rc;
         a.slot_row = slot_row;
         a.slot_w = slot_w;
         a.counters = m->counters_d;

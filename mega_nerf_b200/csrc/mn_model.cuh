@@ -66,7 +66,8 @@ struct MlpArgs {
 };
 
 int mn_route_build(mn_ctx* ctx, mn_model* m, const RowSrc& src, int64_t B, int64_t cap, int* slot_row, float* slot_w,
-                   int* row_slots, cudaStream_t st);
+                   int* row_slots, void* scratch, cudaStream_t st);
+size_t mn_route_scratch_bytes(const mn_model* m, int64_t B);   // per-row active-set masks (+ blend weights [K][B])
 int mn_route_combine(mn_ctx* ctx, mn_model* m, int64_t B, const int* row_slots, const float* slot_out, int out_cols,
                      float* out, cudaStream_t st);
 int mn_mlp_simt_launch(mn_ctx* ctx, const MlpArgs& a, int64_t n_tiles128, cudaStream_t st);

@@ -74,9 +74,12 @@ __device__ __forceinline__ uint64_t route_row(const float* d, int K, float margi
     return mask;
 }
 
+// The routing decision (distances, threshold, normalised weights: ~2000 instructions per row with IEEE sqrt / div) is
+// made ONCE, here; the scatter pass re-reads the active-set mask [B] and the blend weights [K][B] (active entries only).
 template <int KMAX>
 __global__ void route_count_kernel(RowSrc src, int64_t B, const float* __restrict__ cent, int K, int s, float margin,
-                                   int direct, int* counters) {
+                                   int direct, int* counters, unsigned long long* __restrict__ mask_out,
+                                   float* __restrict__ w_out) {
     __shared__ int hist[MN_MAX_SUB];
     __shared__ float sc[MN_MAX_SUB * 3];
     for (int i = threadIdx.x; i < K * 3; i += blockDim.x) sc[i] = cent[i];
@@ -88,6 +91,12 @@ __global__ void route_count_kernel(RowSrc src, int64_t B, const float* __restric
         float d[KMAX], w[KMAX];
         distances<KMAX>(src, row, sc, K, s, direct, d);
         mask = route_row<KMAX>(d, K, margin, w);
+        mask_out[row] = mask;
+        if (w_out) {
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
+                if (k < K && ((mask >> k) & 1)) w_out[(int64_t)k * B + row] = w[k];
+        }
     }
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
@@ -117,21 +126,12 @@ __global__ void route_scan_kernel(int* counters, int K) {
 }
 
 template <int KMAX>
-__global__ void route_scatter_kernel(RowSrc src, int64_t B, const float* __restrict__ cent, int K, int s, float margin,
-                                     int direct, int* counters, int64_t cap, int* slot_row, float* slot_w,
-                                     int* row_slots, unsigned int* status) {
-    __shared__ float sc[MN_MAX_SUB * 3];
-    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) sc[i] = cent[i];
-    __syncthreads();
+__global__ void route_scatter_kernel(int64_t B, int K, int* counters, int64_t cap, const unsigned long long* __restrict__ mask_in,
+                                     const float* __restrict__ w_in, int* slot_row, float* slot_w, int* row_slots,
+                                     unsigned int* status) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    uint64_t mask = 0;
-    float w[KMAX];
-    if (row < B) {
-        float d[KMAX];
-        distances<KMAX>(src, row, sc, K, s, direct, d);
-        mask = route_row<KMAX>(d, K, margin, w);
-    }
+    const uint64_t mask = row < B ? mask_in[row] : 0ull;
     // one global atomic per (block, sub-module): warp ballots -> shared per-warp counts -> block prefix
     __shared__ int wcnt[8][KMAX];     // blockDim.x == 256
     const int warp = threadIdx.x >> 5;
@@ -169,7 +169,7 @@ __global__ void route_scatter_kernel(RowSrc src, int64_t B, const float* __restr
                 slot = -1;
             } else {
                 slot_row[slot] = (int)row;
-                if (slot_w) slot_w[slot] = w[k];
+                if (slot_w) slot_w[slot] = w_in[(int64_t)k * B + row];
             }
         }
         if (row < B && row_slots) row_slots[row * K + k] = slot;
@@ -209,8 +209,18 @@ __global__ void route_only_kernel(RowSrc src, int64_t B, const float* __restrict
 
 }  // namespace
 
+size_t mn_route_scratch_bytes(const mn_model* m, int64_t B) {
+    size_t n = mn_align((size_t)B * sizeof(unsigned long long));                                   // active-set masks
+    if (m->d.boundary_margin > 1.0f) n += mn_align((size_t)B * (size_t)m->d.n_sub * sizeof(float));   // blend weights [K][B]
+    return n;
+}
+
 int mn_route_build(mn_ctx* ctx, mn_model* m, const RowSrc& src, int64_t B, int64_t cap, int* slot_row, float* slot_w,
-                   int* row_slots, cudaStream_t st) {
+                   int* row_slots, void* scratch, cudaStream_t st) {
+    unsigned long long* mask_buf = reinterpret_cast<unsigned long long*>(scratch);
+    float* w_buf = m->d.boundary_margin > 1.0f
+                       ? reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + mn_align((size_t)B * sizeof(unsigned long long)))
+                       : nullptr;
     const int K = m->d.n_sub;
     const int direct = (B <= 25 && K <= 25) ? 1 : 0;
     MN_CUDA(ctx, cudaMemsetAsync(m->counters_d, 0, CNT_TOTAL * sizeof(int), st));
@@ -223,12 +233,12 @@ int mn_route_build(mn_ctx* ctx, mn_model* m, const RowSrc& src, int64_t B, int64
         else KERNEL<MN_MAX_SUB><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                 \
     } while (0)
     MN_ROUTE_DISPATCH(route_count_kernel, blocks, 256, src, B, m->centroids_d, K, m->d.cluster_dim_start, m->d.boundary_margin,
-                      direct, m->counters_d);
+                      direct, m->counters_d, mask_buf, w_buf);
     MN_LAUNCH_CHECK(ctx);
     route_scan_kernel<<<1, 32, 0, st>>>(m->counters_d, K);
     MN_LAUNCH_CHECK(ctx);
-    MN_ROUTE_DISPATCH(route_scatter_kernel, blocks, 256, src, B, m->centroids_d, K, m->d.cluster_dim_start, m->d.boundary_margin,
-                      direct, m->counters_d, cap, slot_row, slot_w, row_slots, ctx->status_d);
+    MN_ROUTE_DISPATCH(route_scatter_kernel, blocks, 256, B, K, m->counters_d, cap, mask_buf, w_buf, slot_row, slot_w, row_slots,
+                      ctx->status_d);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
 }
