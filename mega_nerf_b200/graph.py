@@ -57,7 +57,8 @@ class GraphedRenderRays:
         cur.wait_stream(side)
         torch.cuda.synchronize(self.rays.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads of the process (e.g. the NCCL watchdog polling its events) must not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
             self.results = self._run()
 
     def __call__(self, rays: torch.Tensor, image_indices: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
