@@ -378,8 +378,9 @@ def composite(rgbs: torch.Tensor, sigmas: torch.Tensor, z: torch.Tensor, last_de
     T = torch.cat((torch.ones_like(T[..., 0:1]), T[..., :-1]), dim=-1)
     weights = alphas * T
     rgb = (weights.unsqueeze(-1) * rgbs).sum(dim=1)
-    depth = (weights * (depth_real if depth_real is not None else z)).sum(dim=1)
-    var = (weights * (z - depth.unsqueeze(1)).square()).sum(axis=-1)
+    with torch.no_grad():                                   # rendering.py:381 (depth terms carry no gradient)
+        depth = (weights * (depth_real if depth_real is not None else z)).sum(dim=1)
+        var = (weights * (z - depth.unsqueeze(1)).square()).sum(axis=-1)
     return dict(weights=weights, rgb=rgb, depth=depth, depth_variance=var, bg_lambda=bg_lambda)
 
 
@@ -526,7 +527,7 @@ def _two_pass(net: Net, opts: RenderOpts, rays_d, image_indices, xyz_coarse, z, 
     if fine:
         mid = 0.5 * (z[:, :-1] + z[:, 1:])
         perturb = opts.perturb if net.training else 0
-        zf = sample_pdf(mid, res['weights_coarse'][:, 1:-1], opts.fine_samples // 2 if flip else opts.fine_samples,
+        zf = sample_pdf(mid, res['weights_coarse'][:, 1:-1].detach(), opts.fine_samples // 2 if flip else opts.fine_samples,
                         det=(perturb == 0))
         if opts.use_cascade:
             zf, _ = torch.sort(torch.cat([z, zf], -1), -1)
@@ -601,6 +602,68 @@ def render_rays(net: Net, bg_net: Optional[Net], rays: torch.Tensor, image_indic
                     res[f'fg_{name}'] = val
                     res[f'bg_{name}'] = torch.zeros_like(val)
     return res, bool(bg_net is not None and with_bg.shape[0] > 0)
+
+
+# --------------------------------------------------------------------------------------------
+# gradients: torch autograd over the restatement above, i.e. exactly what
+# `loss.backward()` does in the reference's training step (runner.py:346-378, :265) on CPU fp32.
+# Gradient flow mirrors the reference: resampling weights are detached (rendering.py:215), depth
+# terms are computed under no_grad (rendering.py:381), rays / sample positions carry no gradient.
+# --------------------------------------------------------------------------------------------
+
+def _leaf_copy(net: Optional[Net]):
+    """A Net whose weight tensors are fresh autograd leaves."""
+    if net is None:
+        return None
+    import dataclasses
+    ws = [{k: v.detach().clone().requires_grad_(True) for k, v in w.items()} for w in net.weights]
+    return dataclasses.replace(net, weights=ws)
+
+
+def _collect_grads(net: Optional[Net]):
+    if net is None:
+        return None
+    return [{k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in w.items()}
+            for w in net.weights]
+
+
+def net_forward_grads(net: Net, x: torch.Tensor, cotangent: torch.Tensor, use_coarse: bool = True,
+                      sigma_noise: Optional[torch.Tensor] = None):
+    """out = net(x);  (out * cotangent).sum().backward()  ->  (out, [per-sub-module grad dicts])."""
+    n2 = _leaf_copy(net)
+    out = net_forward(n2, x, use_coarse=use_coarse, sigma_noise=sigma_noise)
+    (out * cotangent).sum().backward()
+    return out.detach(), _collect_grads(n2)
+
+
+def composite_grads(rgbs: torch.Tensor, sigmas: torch.Tensor, z: torch.Tensor, last_delta: torch.Tensor, flip: bool,
+                    cot_rgb: torch.Tensor, cot_lambda: Optional[torch.Tensor] = None):
+    """Gradient of sum(rgb * cot_rgb) + sum(bg_lambda * cot_lambda) w.r.t. the per-sample (rgb, sigma)
+    (rendering.py:352-373)."""
+    r = rgbs.detach().clone().requires_grad_(True)
+    s = sigmas.detach().clone().requires_grad_(True)
+    c = composite(r, s, z, last_delta, flip)
+    loss = (c['rgb'] * cot_rgb).sum()
+    if cot_lambda is not None:
+        loss = loss + (c['bg_lambda'] * cot_lambda).sum()
+    loss.backward()
+    return r.grad, s.grad
+
+
+def render_grads(net: Net, bg_net: Optional[Net], rays: torch.Tensor, image_indices: Optional[torch.Tensor],
+                 opts: RenderOpts, sphere_center, sphere_radius, cotangents: Dict[str, torch.Tensor]):
+    """render_rays as the training step calls it (get_depth=False, get_depth_variance=True,
+    get_bg_fg_rgb=False; runner.py:349-358), then backward of sum_k sum(res[k] * cotangents[k]).
+    Returns (results, grads of net, grads of bg_net or None)."""
+    n2, b2 = _leaf_copy(net), _leaf_copy(bg_net)
+    res, _ = render_rays(n2, b2, rays, image_indices, opts, sphere_center, sphere_radius, False, True, False)
+    loss = None
+    for k, c in cotangents.items():
+        if k in res and res[k].requires_grad:
+            t = (res[k] * c).sum()
+            loss = t if loss is None else loss + t
+    loss.backward()
+    return {k: v.detach() for k, v in res.items()}, _collect_grads(n2), _collect_grads(b2)
 
 
 # --------------------------------------------------------------------------------------------

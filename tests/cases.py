@@ -127,13 +127,47 @@ RENDER_CASES: Dict[str, dict] = {
 }
 
 
+# ------------------------------------------------------------------------------------------
+# gradient cases: small networks so that the committed reference gradients stay small
+# ------------------------------------------------------------------------------------------
+_G = dict(layer_dim=64, appearance_count=10)
+GRAD_CASES: Dict[str, dict] = {
+    'g_single': dict(kind='nerf', spec=O.NerfSpec(**_G), rays=40, coarse=16, fine=32),
+    'g_coarse_only': dict(kind='cascade', spec=O.NerfSpec(**_G), rays=40, coarse=24, fine=0, cascade=True),
+    'g_cascade': dict(kind='cascade', spec=O.NerfSpec(**_G), rays=40, coarse=16, fine=16, cascade=True),
+    'g_mega_hard': dict(kind='mega', spec=O.NerfSpec(**_G), grid=(2, 2), margin=1.0, rays=40, coarse=16, fine=32),
+    'g_mega_blend': dict(kind='mega', spec=O.NerfSpec(**_G), grid=(2, 2), margin=1.15, rays=40, coarse=16, fine=32),
+    'g_sh2': dict(kind='nerf', spec=O.NerfSpec(pos_dir_dim=0, rgb_dim=27, **_G), rays=40, coarse=16, fine=32, sh_deg=2),
+    'g_affine': dict(kind='nerf', spec=O.NerfSpec(affine_appearance=True, **_G), rays=40, coarse=16, fine=32),
+    'g_noapp_q1': dict(kind='nerf', spec=O.NerfSpec(appearance_dim=0, layer_dim=64), rays=40, coarse=16, fine=32,
+                       idx=False),
+    # ReLU density head: the random-init head is dead (sigma == 0 everywhere), so lift its bias
+    'g_relu_sigma': dict(kind='nerf', spec=O.NerfSpec(shifted_softplus=False, **_G), rays=40, coarse=16, fine=32,
+                         sigma_bias=0.5),
+    'g_l128_skip2': dict(kind='nerf', spec=O.NerfSpec(layer_dim=128, layers=4, skip_layers=(2,), appearance_count=10),
+                         rays=24, coarse=16, fine=16),
+    'g_bg_single': dict(kind='nerf', spec=O.NerfSpec(**_G), rays=40, coarse=16, fine=16, bg='nerf'),
+    'g_bg_cascade': dict(kind='cascade', spec=O.NerfSpec(**_G), rays=40, coarse=16, fine=16, cascade=True, bg='cascade'),
+}
+GRAD_GOLDEN_PATH = os.path.join(ROOT, 'tests', 'golden', 'backward_v1.pt')
+
+
+def grad_cotangents(name: str, n_rays: int) -> Dict[str, torch.Tensor]:
+    """Seeded upstream gradients for the differentiable outputs (rgb_fine / rgb_coarse)."""
+    g = torch.Generator().manual_seed(977)
+    return {'rgb_fine': torch.randn(n_rays, 3, generator=g), 'rgb_coarse': torch.randn(n_rays, 3, generator=g)}
+
+
 def render_case(name: str):
     """-> (net, bg_net, rays, image_indices, opts, sphere_center, sphere_radius)."""
-    c = RENDER_CASES[name]
+    c = RENDER_CASES[name] if name in RENDER_CASES else GRAD_CASES[name]
     spec: O.NerfSpec = c['spec']
     cents = O.grid_centroids(*c['grid']) if 'grid' in c else None
     net = O.make_net(c['kind'], spec, seed=0, n_sub=0 if cents is None else cents.shape[0], centroids=cents,
                      boundary_margin=c.get('margin', 1.0), cluster_2d=True)
+    if 'sigma_bias' in c:
+        for w in net.weights:
+            w['sigma.bias'] = w['sigma.bias'] + c['sigma_bias']
     bg_net = None
     center = radius = None
     has_bg = 'bg' in c
