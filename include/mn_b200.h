@@ -201,6 +201,52 @@ int mn_model_route(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int
  * slots = routed (row, sub-module) pairs, tiles = 128-row MLP tiles. */
 int mn_model_last_stats(mn_ctx* ctx, mn_model* m, int64_t* slots, int64_t* tiles, void* stream);
 
+/* ---- training: gradients of the path ------------------------------------ SURVEY.md §8f-1 --------
+ * What `loss.backward()` computes through the hot path in the reference's training step
+ * (runner.py:346-378 -> :265).  Gradient flow is the reference's: per-sample (rgb, sigma) receive
+ * gradients from the composited colour and from bg_lambda; resampling weights are detached
+ * (rendering.py:215) and depth terms are computed under no_grad (rendering.py:381), so neither
+ * contributes; sample positions carry no gradient.  fp32 (CUDA-core) arithmetic only in this ABI
+ * version: the training forward always runs in MN_PREC_FP32.                                      */
+
+/* d(sum(rgb * grad_rgb) + sum(bg_lambda * grad_lambda)) / d raw   for mn_composite's inputs
+ * (rendering.py:336-373): same raw/z/raw2/z2/last_delta/flip as the forward call;
+ *   grad_rgb_d [N,3]; grad_lambda_d optional [N];
+ *   grad_raw_d [N,S,4] and (iff S2 > 0) grad_raw2_d [N,S2,4] receive d/d(r,g,b,sigma) per sample. */
+int mn_composite_backward(mn_ctx* ctx, const float* raw_d, const float* z_d, int S, const float* raw2_d,
+                          const float* z2_d, int S2, const float* last_delta_d, int64_t N, int flip,
+                          const float* grad_rgb_d, const float* grad_lambda_d, float* grad_raw_d, float* grad_raw2_d,
+                          void* stream);
+/* Backward of mn_sh_to_rgb (spherical_harmonics.py:55-106 + sigmoid, rendering.py:301-306):
+ *   grad_out_d [B,4] -> grad_coef_d [B, coef_stride] (all 3*(deg+1)^2 + 1 used columns written). */
+int mn_sh_to_rgb_backward(mn_ctx* ctx, int deg, const float* coef_d, int64_t coef_stride, const float* dirs_d,
+                          int64_t dir_stride, int dir_div, int64_t B, int apply_sigmoid, const float* grad_out_d,
+                          float* grad_coef_d, void* stream);
+
+/* Training forward of nn.Module.__call__ (nerf.py:115-160, cascade.py:13-18, mega_nerf.py:19-61): same
+ * result as mn_model_forward(precision = MN_PREC_FP32, sigma_only = 0) and, in addition, everything the
+ * backward pass needs (routing tables of this call, every layer's activations) is written to the
+ * caller-owned `tape_d` (mn_model_tape_bytes(m, B) bytes), which must stay untouched until
+ * mn_model_backward has consumed it.  workspace as for mn_model_forward(MN_PREC_FP32). */
+size_t mn_model_tape_bytes(const mn_model* m, int64_t B);
+int mn_model_forward_train(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int use_coarse,
+                           const float* sigma_noise_d, float* out_d, void* tape_d, size_t tape_bytes, void* workspace_d,
+                           size_t workspace_bytes, void* stream);
+/* Parameter gradients.  grad_out_d [B, rgb_dim+1] is dL/d(out) of the matching mn_model_forward_train
+ * call (same B / use_coarse / tape).  Gradients are ACCUMULATED (+=) into param_grads_d, a caller-zeroed
+ * fp32 block of mn_model_grad_floats(m) = n_sub * stride floats: sub-module s owns [s*stride, (s+1)*stride)
+ * and inside it every tensor sits at the offset mn_model_param_offsets reports, in the reference's
+ * state-dict layout (nn.Linear weight [out,in] row-major, embedding [count,dim]).
+ * mn_model_param_offsets fills out[0..MN_PARAM_OFFSETS): stride, xyz_encodings.{0..15}.0.weight,
+ * xyz_encodings.{0..15}.0.bias (-1 beyond `layers`), sigma.weight, sigma.bias, xyz_encoding_final.weight,
+ * .bias, dir_a_encoding.0.weight, .bias, rgb.weight, .bias, embedding_a.weight, affine.weight, affine.bias. */
+#define MN_PARAM_OFFSETS 44
+size_t mn_model_backward_workspace_bytes(const mn_model* m, int64_t B);
+int64_t mn_model_grad_floats(const mn_model* m);
+int mn_model_param_offsets(const mn_model* m, int64_t* out, int n);
+int mn_model_backward(mn_ctx* ctx, mn_model* m, int64_t B, int use_coarse, const float* grad_out_d, const void* tape_d,
+                      size_t tape_bytes, float* param_grads_d, void* workspace_d, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

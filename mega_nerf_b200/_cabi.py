@@ -76,7 +76,17 @@ SIGNATURES = {
     'mn_model_forward': (_I, [_P, _P, C.POINTER(Rows), _L, _I, _I, _P, _I, _P, _P, _Z, _P]),
     'mn_model_route': (_I, [_P, _P, C.POINTER(Rows), _L, _P, _P, _P]),
     'mn_model_last_stats': (_I, [_P, _P, C.POINTER(_L), C.POINTER(_L), _P]),
+    # training
+    'mn_composite_backward': (_I, [_P, _P, _P, _I, _P, _P, _I, _P, _L, _I, _P, _P, _P, _P, _P]),
+    'mn_sh_to_rgb_backward': (_I, [_P, _I, _P, _L, _P, _L, _I, _L, _I, _P, _P, _P]),
+    'mn_model_tape_bytes': (_Z, [_P, _L]),
+    'mn_model_forward_train': (_I, [_P, _P, C.POINTER(Rows), _L, _I, _P, _P, _P, _Z, _P, _Z, _P]),
+    'mn_model_backward_workspace_bytes': (_Z, [_P, _L]),
+    'mn_model_grad_floats': (_L, [_P]),
+    'mn_model_param_offsets': (_I, [_P, C.POINTER(_L), _I]),
+    'mn_model_backward': (_I, [_P, _P, _L, _I, _P, _P, _Z, _P, _P, _Z, _P]),
 }
+MN_PARAM_OFFSETS = 44
 
 _lib = None
 _lock = threading.Lock()

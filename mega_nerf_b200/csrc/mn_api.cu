@@ -20,6 +20,22 @@ int pack_T(mn_ctx* ctx, const float* src, int N, int K, float* dst, cudaStream_t
     return MN_OK;
 }
 
+__global__ void submatrix_kernel(const float* __restrict__ src, int N, int K, int koff, int kw, float* __restrict__ dst) {
+    // src [N][K] (nn.Linear weight) -> dst [N][kw] = src[:, koff : koff + kw]
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * kw) return;
+    const int n = (int)(i / kw), k = (int)(i % kw);
+    dst[i] = src[(int64_t)n * K + koff + k];
+}
+
+int pack_sub(mn_ctx* ctx, const float* src, int N, int K, int koff, int kw, float* dst, cudaStream_t st) {
+    const int64_t n = (int64_t)N * kw;
+    if (n == 0) return MN_OK;
+    submatrix_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(src, N, K, koff, kw, dst);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}
+
 int al4(int x) { return (x + 3) / 4 * 4; }
 
 void build_layout(mn_model* m) {
@@ -65,6 +81,37 @@ void build_layout(mn_model* m) {
     l.aff_w = take(nd.affine ? nd.app * 12 : 0);
     l.aff_b = take(nd.affine ? 12 : 0);
     l.total = off;
+
+    // training tapes (mn_model.cuh)
+    TapeLayout& t = m->tape;
+    int c = 0;
+    auto chan = [&](int n) { int o = c; c += n; return o; };
+    t.a_pe = chan(nd.in_xyz);
+    t.a_aux = chan(nd.aux);
+    t.a_h = chan(nd.layers * nd.L);
+    t.a_f = chan(nd.has_dir_a ? nd.L : 0);
+    t.a_g = chan(nd.has_dir_a ? nd.L / 2 : 0);
+    t.a_rgb = chan(nd.rgb_dim);
+    t.a_lin = chan(nd.affine ? 3 : 0);
+    t.a_sig = chan(1);
+    t.a_id = chan(nd.app > 0 ? 1 : 0);
+    t.a_total = c;
+    c = 0;
+    t.g_z = chan(nd.layers * nd.L);
+    t.g_final = chan(nd.has_dir_a ? nd.L : 0);
+    t.g_dira = chan(nd.has_dir_a ? nd.L / 2 : 0);
+    t.g_rgb = chan(nd.rgb_dim);
+    t.g_sig = chan(1);
+    t.g_total = c;
+
+    BwdLayout& bl = m->blay;
+    off = 0;
+    bl.w[0] = 0;
+    for (int i = 1; i < nd.layers; ++i) bl.w[i] = take(nd.L * nd.L);
+    bl.final_w = take(nd.has_dir_a ? nd.L * nd.L : 0);
+    bl.dira_f = take(nd.has_dir_a ? (nd.L / 2) * nd.L : 0);
+    bl.dira_e = take(nd.app_in_dira ? (nd.L / 2) * nd.app : 0);
+    bl.total = off > 0 ? off : 4;
 }
 
 }  // namespace
@@ -162,6 +209,8 @@ int mn_model_create(mn_ctx* ctx, const mn_model_desc* desc, mn_model** out) {
     *out = m;
     MN_CUDA(ctx, cudaMalloc(&m->packed, (size_t)d.n_sub * m->lay.total * sizeof(float)));
     MN_CUDA(ctx, cudaMemset(m->packed, 0, (size_t)d.n_sub * m->lay.total * sizeof(float)));
+    MN_CUDA(ctx, cudaMalloc(&m->packed_bwd, (size_t)d.n_sub * m->blay.total * sizeof(float)));
+    MN_CUDA(ctx, cudaMemset(m->packed_bwd, 0, (size_t)d.n_sub * m->blay.total * sizeof(float)));
     MN_CUDA(ctx, cudaMalloc(&m->centroids_d, (size_t)MN_MAX_SUB * 3 * sizeof(float)));
     MN_CUDA(ctx, cudaMalloc(&m->counters_d, CNT_TOTAL * sizeof(int)));
     MN_CUDA(ctx, cudaMemset(m->counters_d, 0, CNT_TOTAL * sizeof(int)));
@@ -171,6 +220,7 @@ int mn_model_create(mn_ctx* ctx, const mn_model_desc* desc, mn_model** out) {
 void mn_model_destroy(mn_model* m) {
     if (!m) return;
     if (m->packed) cudaFree(m->packed);
+    if (m->packed_bwd) cudaFree(m->packed_bwd);
     if (m->centroids_d) cudaFree(m->centroids_d);
     if (m->counters_d) cudaFree(m->counters_d);
     if (m->tc_packed) cudaFree(m->tc_packed);
@@ -228,6 +278,20 @@ int mn_model_set_weights(mn_model* m, int sub, const mn_nerf_weights* w, void* s
         if ((rc = pack_T(ctx, w->affine_w, 12, nd.app, P + l.aff_w, st))) return rc;
         if ((rc = copy(P + l.aff_b, w->affine_b, 12))) return rc;
     }
+    // data-gradient images (BwdLayout): the input columns that carry a gradient, in nn.Linear [out][in] order
+    {
+        const BwdLayout& bl = m->blay;
+        float* Q = m->packed_bwd + (size_t)sub * bl.total;
+        for (int i = 1; i < nd.layers; ++i)
+            if ((rc = pack_sub(ctx, w->xyz_w[i], nd.L, l.kin[i], l.kin[i] - nd.L, nd.L, Q + bl.w[i], st))) return rc;
+        if (nd.has_dir_a) {
+            if ((rc = pack_sub(ctx, w->final_w, nd.L, nd.L, 0, nd.L, Q + bl.final_w, st))) return rc;
+            if ((rc = pack_sub(ctx, w->dir_a_w, nd.L / 2, nd.L + nd.aux, 0, nd.L, Q + bl.dira_f, st))) return rc;
+            if (nd.app_in_dira)
+                if ((rc = pack_sub(ctx, w->dir_a_w, nd.L / 2, nd.L + nd.aux, nd.L + nd.in_dir, nd.app, Q + bl.dira_e, st)))
+                    return rc;
+        }
+    }
     return mn_mlp_tc_pack(ctx, m, sub, st);
 }
 
@@ -253,9 +317,13 @@ size_t mn_model_workspace_bytes(const mn_model* m, int64_t B, int precision) {
     return bytes;
 }
 
-int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int use_coarse, int sigma_only,
-                     const float* sigma_noise_d, int precision, float* out_d, void* workspace_d,
-                     size_t workspace_bytes, void* stream) {
+// Tape header: the routing counters of THIS forward call (the model's own counters are overwritten by the next call).
+#define MN_TAPE_HEADER 1024
+static_assert(CNT_TOTAL * sizeof(int) <= MN_TAPE_HEADER, "tape header too small");
+
+static int model_forward_impl(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int use_coarse, int sigma_only,
+                              const float* sigma_noise_d, int precision, float* out_d, void* workspace_d,
+                              size_t workspace_bytes, void* tape_d, size_t tape_bytes, void* stream) {
     if (!ctx || !m || !rows || B < 0) return MN_ERR_INVALID;
     const mn_model_desc& d = m->d;
     const NetDims& nd = m->nd;
@@ -325,6 +393,14 @@ int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, i
         return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_model_forward: workspace too small");
     char* ws = (char*)workspace_d;
     auto carve = [&](size_t n) { char* p = ws; ws += mn_align(n); return p; };
+    // training forward: the routing tables and the activations outlive the call inside the caller's tape
+    char* tp = (char*)tape_d;
+    auto tcarve = [&](size_t n) { char* p = tp; tp += mn_align(n); return p; };
+    int* tape_counters = nullptr;
+    if (tape_d) {
+        if (tape_bytes < mn_model_tape_bytes(m, B)) return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_model_forward_train: tape too small");
+        tape_counters = (int*)tcarve(MN_TAPE_HEADER);
+    }
 
     int rc;
     int* row_slots = nullptr;
@@ -339,7 +415,13 @@ int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, i
             row_slots = (int*)carve((size_t)B * d.n_sub * sizeof(int));
             slot_out = (float*)carve((size_t)cap * a.out_cols * sizeof(float));
         }
+        if (tape_d) {
+            slot_row = (int*)tcarve((size_t)cap * sizeof(int));
+            if (blend) slot_w = (float*)tcarve((size_t)cap * sizeof(float));
+        }
         if ((rc = mn_route_build(ctx, m, src, B, cap, slot_row, slot_w, row_slots, route_scratch, st))) return rc;
+        if (tape_d)
+            MN_CUDA(ctx, cudaMemcpyAsync(tape_counters, m->counters_d, CNT_TOTAL * sizeof(int), cudaMemcpyDeviceToDevice, st));
         a.slot_row = slot_row;
         a.slot_w = slot_w;
         a.counters = m->counters_d;
@@ -352,6 +434,10 @@ int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, i
     }
 
     const int64_t n_tiles = cap / MN_TILE;
+    if (tape_d) {
+        a.tape = (float*)tp;
+        a.tl = m->tape;
+    }
     if (precision == MN_PREC_FP32)
         rc = mn_mlp_simt_launch(ctx, a, n_tiles, st);
     else
@@ -359,6 +445,97 @@ int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, i
     if (rc) return rc;
     if (row_slots) return mn_route_combine(ctx, m, B, row_slots, slot_out, a.out_cols, out_d, st);
     return MN_OK;
+}
+
+int mn_model_forward(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int use_coarse, int sigma_only,
+                     const float* sigma_noise_d, int precision, float* out_d, void* workspace_d,
+                     size_t workspace_bytes, void* stream) {
+    return model_forward_impl(ctx, m, rows, B, use_coarse, sigma_only, sigma_noise_d, precision, out_d, workspace_d,
+                              workspace_bytes, nullptr, 0, stream);
+}
+
+// ---- training --------------------------------------------------------------------
+size_t mn_model_tape_bytes(const mn_model* m, int64_t B) {
+    if (!m) return 0;
+    const int64_t cap = slot_capacity(m, B);
+    const int TM = mn_tape_tm(m->nd.L);
+    size_t bytes = MN_TAPE_HEADER;
+    if (m->d.kind == 2) {
+        bytes += mn_align((size_t)cap * sizeof(int));
+        if (m->d.boundary_margin > 1.0f) bytes += mn_align((size_t)cap * sizeof(float));
+    }
+    bytes += mn_align((size_t)(cap / TM) * m->tape.a_total * TM * sizeof(float));
+    return bytes;
+}
+
+int mn_model_forward_train(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int use_coarse,
+                           const float* sigma_noise_d, float* out_d, void* tape_d, size_t tape_bytes, void* workspace_d,
+                           size_t workspace_bytes, void* stream) {
+    if (!tape_d) return mn_fail(ctx, MN_ERR_INVALID, "mn_model_forward_train: tape is NULL");
+    return model_forward_impl(ctx, m, rows, B, use_coarse, 0, sigma_noise_d, MN_PREC_FP32, out_d, workspace_d,
+                              workspace_bytes, tape_d, tape_bytes, stream);
+}
+
+size_t mn_model_backward_workspace_bytes(const mn_model* m, int64_t B) {
+    if (!m) return 0;
+    const int64_t cap = slot_capacity(m, B);
+    const int TM = mn_tape_tm(m->nd.L);
+    return 256 + mn_align((size_t)(cap / TM) * m->tape.g_total * TM * sizeof(float));
+}
+
+int64_t mn_model_grad_floats(const mn_model* m) { return m ? (int64_t)m->d.n_sub * m->lay.total : 0; }
+
+int mn_model_param_offsets(const mn_model* m, int64_t* out, int n) {
+    if (!m || !out || n < MN_PARAM_OFFSETS) return MN_ERR_INVALID;
+    const PackedLayout& l = m->lay;
+    int k = 0;
+    out[k++] = l.total;
+    for (int i = 0; i < MN_MAX_LAYERS; ++i) out[k++] = i < m->nd.layers ? l.w[i] : -1;
+    for (int i = 0; i < MN_MAX_LAYERS; ++i) out[k++] = i < m->nd.layers ? l.b[i] : -1;
+    out[k++] = l.sigma_w; out[k++] = l.sigma_b;
+    out[k++] = l.final_w; out[k++] = l.final_b;
+    out[k++] = l.dira_w; out[k++] = l.dira_b;
+    out[k++] = l.rgb_w; out[k++] = l.rgb_b;
+    out[k++] = l.emb; out[k++] = l.aff_w; out[k++] = l.aff_b;
+    return MN_OK;
+}
+
+int mn_model_backward(mn_ctx* ctx, mn_model* m, int64_t B, int use_coarse, const float* grad_out_d, const void* tape_d,
+                      size_t tape_bytes, float* param_grads_d, void* workspace_d, size_t workspace_bytes, void* stream) {
+    if (!ctx || !m || B < 0 || !grad_out_d || !tape_d || !param_grads_d) return MN_ERR_INVALID;
+    if (B == 0) return MN_OK;
+    const mn_model_desc& d = m->d;
+    if (tape_bytes < mn_model_tape_bytes(m, B)) return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_model_backward: tape too small");
+    if (!workspace_d || workspace_bytes < mn_model_backward_workspace_bytes(m, B))
+        return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_model_backward: workspace too small");
+    const int64_t cap = slot_capacity(m, B);
+    const char* tp = (const char*)tape_d;
+    auto tcarve = [&](size_t n) { const char* p = tp; tp += mn_align(n); return p; };
+    const int* counters = (const int*)tcarve(MN_TAPE_HEADER);
+
+    BwdArgs a{};
+    a.nd = m->nd;
+    a.lay = m->lay;
+    a.blay = m->blay;
+    a.tl = m->tape;
+    a.packed = m->packed;
+    a.packed_bwd = m->packed_bwd;
+    a.n_sub = d.n_sub;
+    a.B = B;
+    a.grad_out = grad_out_d;
+    a.out_cols = m->nd.rgb_dim + 1;
+    a.gw = param_grads_d;
+    if (d.kind == 2) {
+        a.slot_row = (const int*)tcarve((size_t)cap * sizeof(int));
+        if (d.boundary_margin > 1.0f) a.slot_w = (const float*)tcarve((size_t)cap * sizeof(float));
+        a.counters = counters;
+        a.B = cap;
+    } else {
+        a.fixed_sub = (d.kind == 1) ? (use_coarse ? 0 : 1) : 0;
+    }
+    a.act = (const float*)tp;
+    a.grad = (float*)workspace_d;
+    return mn_mlp_bwd_launch(ctx, a, cap / MN_TILE, (cudaStream_t)stream);
 }
 
 int mn_model_last_stats(mn_ctx* ctx, mn_model* m, int64_t* slots, int64_t* tiles, void* stream) {

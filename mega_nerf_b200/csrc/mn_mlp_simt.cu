@@ -12,7 +12,7 @@ namespace {
 template <int TM>
 __device__ __forceinline__ void gemm_layer(const float* __restrict__ Wt, const float* __restrict__ bias, int N,
                                            const float* s0, int k0, const float* s1, int k1, float* dst,
-                                           bool relu) {
+                                           bool relu, float* __restrict__ gdst = nullptr) {
     constexpr int RM = TM / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int cb = 0; cb < N; cb += 256) {
@@ -57,15 +57,19 @@ __device__ __forceinline__ void gemm_layer(const float* __restrict__ Wt, const f
                 float v = acc[i][j];
                 if (relu) v = fmaxf(v, 0.0f);
                 dst[(n0 + j) * TM + lane + 32 * i] = v;
+                if (gdst) gdst[(n0 + j) * TM + lane + 32 * i] = v;   // activation tape (training forward)
             }
     }
 }
 
-template <int TM>
+// SAVE = training forward: every value the backward pass needs is also written to the activation tape
+// (TapeLayout, mn_model.cuh); the arithmetic is the same instruction stream either way.
+template <int TM, bool SAVE>
 __global__ void __launch_bounds__(256, 1) mlp_simt_kernel(const MlpArgs a) {
     extern __shared__ float smem[];
     const NetDims& nd = a.nd;
     const int L = nd.L;
+    float* const T = SAVE ? a.tape + (size_t)blockIdx.x * a.tl.a_total * TM : nullptr;
     float* PE = smem;                    // [in_xyz][TM]
     float* AUX = PE + nd.in_xyz * TM;    // [aux][TM]  = dir encoding | appearance embedding
     float* H0 = AUX + nd.aux * TM;       // [L][TM]
@@ -148,6 +152,16 @@ __global__ void __launch_bounds__(256, 1) mlp_simt_kernel(const MlpArgs a) {
         }
     }
     __syncthreads();
+    if (SAVE) {
+        // PE and AUX are contiguous [channels][TM] blocks in shared memory, same layout as the tape
+        for (int it = tid; it < nd.in_xyz * TM; it += 256) T[a.tl.a_pe * TM + it] = PE[it];
+        for (int it = tid; it < nd.aux * TM; it += 256) T[a.tl.a_aux * TM + it] = AUX[it];
+        if (tid < TM && nd.app > 0) {
+            int id = (int)XIN[tid * 8 + 7];
+            id = min(max(id, 0), nd.app_count - 1);
+            T[a.tl.a_id * TM + tid] = (float)id;
+        }
+    }
 
     // trunk (nerf.py:126-130)
     float* cur = nullptr;
@@ -155,12 +169,13 @@ __global__ void __launch_bounds__(256, 1) mlp_simt_kernel(const MlpArgs a) {
         float* dst = (i & 1) ? H1 : H0;
         const float* W = P + a.lay.w[i];
         const float* Bv = P + a.lay.b[i];
+        float* gd = SAVE ? T + (size_t)(a.tl.a_h + i * L) * TM : nullptr;
         if (i == 0)
-            gemm_layer<TM>(W, Bv, L, PE, nd.in_xyz, nullptr, 0, dst, true);
+            gemm_layer<TM>(W, Bv, L, PE, nd.in_xyz, nullptr, 0, dst, true, gd);
         else if ((nd.skip_mask >> i) & 1)
-            gemm_layer<TM>(W, Bv, L, PE, nd.in_xyz, cur, L, dst, true);   // cat[PE, h]  (nerf.py:129)
+            gemm_layer<TM>(W, Bv, L, PE, nd.in_xyz, cur, L, dst, true, gd);   // cat[PE, h]  (nerf.py:129)
         else
-            gemm_layer<TM>(W, Bv, L, cur, L, nullptr, 0, dst, true);
+            gemm_layer<TM>(W, Bv, L, cur, L, nullptr, 0, dst, true, gd);
         cur = dst;
         __syncthreads();
     }
@@ -173,6 +188,7 @@ __global__ void __launch_bounds__(256, 1) mlp_simt_kernel(const MlpArgs a) {
         for (int k = 0; k < L; ++k) acc = fmaf(cur[k * TM + tid], __ldg(ws + k), acc);
         const int row = ROW[tid];
         if (a.sigma_noise && row >= 0) acc = acc + a.sigma_noise[row];
+        if (SAVE) T[a.tl.a_sig * TM + tid] = acc;   // pre-activation (noise included)
         SIG[tid] = nd.softplus ? mn_softplus_shifted(acc) : fmaxf(acc, 0.0f);
     }
     __syncthreads();
@@ -193,9 +209,11 @@ __global__ void __launch_bounds__(256, 1) mlp_simt_kernel(const MlpArgs a) {
     const float* rgb_src = cur;
     if (nd.has_dir_a) {
         // xyz_encoding_final (no activation) then dir_a_encoding + ReLU (nerf.py:141-151)
-        gemm_layer<TM>(P + a.lay.final_w, P + a.lay.final_b, L, cur, L, nullptr, 0, other, false);
+        gemm_layer<TM>(P + a.lay.final_w, P + a.lay.final_b, L, cur, L, nullptr, 0, other, false,
+                       SAVE ? T + (size_t)a.tl.a_f * TM : nullptr);
         __syncthreads();
-        gemm_layer<TM>(P + a.lay.dira_w, P + a.lay.dira_b, L / 2, other, L, AUX, nd.aux, cur, true);
+        gemm_layer<TM>(P + a.lay.dira_w, P + a.lay.dira_b, L / 2, other, L, AUX, nd.aux, cur, true,
+                       SAVE ? T + (size_t)a.tl.a_g * TM : nullptr);
         __syncthreads();
         rgb_src = cur;
     }
@@ -212,8 +230,15 @@ __global__ void __launch_bounds__(256, 1) mlp_simt_kernel(const MlpArgs a) {
         }
     }
     __syncthreads();
+    if (SAVE && tid < TM) {
+        // values the backward pass needs: the Linear output of the rgb head (affine models) ...
+        if (nd.affine && nd.app > 0)
+            for (int c = 0; c < 3; ++c) T[(a.tl.a_lin + c) * TM + tid] = OUTS[c * TM + tid];
+    }
     if (tid < TM) {
         const int row = ROW[tid];
+        if (SAVE && row < 0)
+            for (int c = 0; c < nd.rgb_dim; ++c) T[(a.tl.a_rgb + c) * TM + tid] = 0.0f;
         if (row >= 0) {
             float rgb[3] = {0, 0, 0};
             if (nd.affine && nd.app > 0) {
@@ -240,6 +265,7 @@ __global__ void __launch_bounds__(256, 1) mlp_simt_kernel(const MlpArgs a) {
             for (int c = 0; c < nd.rgb_dim; ++c) {
                 float v = OUTS[c * TM + tid];
                 if (nd.rgb_dim == 3) v = mn_sigmoid(v);
+                if (SAVE) T[(a.tl.a_rgb + c) * TM + tid] = v;   // ... and the head's output before blending
                 a.out[o + c] = a.slot_w ? v * w : v;
             }
             const float s = SIG[tid];
@@ -261,15 +287,20 @@ int mn_mlp_simt_launch(mn_ctx* ctx, const MlpArgs& a, int64_t n_tiles128, cudaSt
         return mn_fail(ctx, MN_ERR_UNSUPPORTED, "fp32 MLP kernel supports layer_dim in {64,...,512} (multiple of 64)");
     if (n_tiles128 <= 0) return MN_OK;
     mn_prof_begin(ctx, st);
+    if (a.tape && a.sigma_only) return mn_fail(ctx, MN_ERR_INVALID, "training forward has no sigma_only mode");
+#define MN_SIMT_LAUNCH(TM_, SAVE_, MULT_)                                                                            \
+    do {                                                                                                             \
+        const size_t sm = simt_smem_bytes<TM_>(nd);                                                                  \
+        MN_CUDA(ctx, cudaFuncSetAttribute(mlp_simt_kernel<TM_, SAVE_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          (int)sm));                                                                 \
+        mlp_simt_kernel<TM_, SAVE_><<<(unsigned)(n_tiles128 * MULT_), 256, sm, st>>>(a);                             \
+    } while (0)
     if (nd.L <= 256) {
-        const size_t sm = simt_smem_bytes<64>(nd);
-        MN_CUDA(ctx, cudaFuncSetAttribute(mlp_simt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        mlp_simt_kernel<64><<<(unsigned)(n_tiles128 * 2), 256, sm, st>>>(a);
+        if (a.tape) MN_SIMT_LAUNCH(64, true, 2); else MN_SIMT_LAUNCH(64, false, 2);
     } else {
-        const size_t sm = simt_smem_bytes<32>(nd);
-        MN_CUDA(ctx, cudaFuncSetAttribute(mlp_simt_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        mlp_simt_kernel<32><<<(unsigned)(n_tiles128 * 4), 256, sm, st>>>(a);
+        if (a.tape) MN_SIMT_LAUNCH(32, true, 4); else MN_SIMT_LAUNCH(32, false, 4);
     }
+#undef MN_SIMT_LAUNCH
     mn_prof_end(ctx, st);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;

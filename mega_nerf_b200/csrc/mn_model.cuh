@@ -20,12 +20,41 @@ struct NetDims {
         softplus, skip_mask, app_count, app_in_dira;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Training tapes.  Both are tiled like the fp32 MLP kernel: tile t holds TM slots
+// (TM = mn_tape_tm(L)), channel-major, i.e. value (channel c, slot r of tile t) lives at
+// base[(t * C + c) * TM + r].  The ACTIVATION tape is written by the forward pass in training mode,
+// the GRADIENT tape (dL/d pre-activation of every Linear) by the data-gradient kernel; the weight-
+// gradient kernel contracts one against the other over the slots of each sub-module.
+// ------------------------------------------------------------------------------------------------
+struct TapeLayout {
+    // activation tape channels
+    int a_pe, a_aux, a_h, a_f, a_g, a_rgb, a_lin, a_sig, a_id, a_total;
+    // gradient tape channels
+    int g_z, g_final, g_dira, g_rgb, g_sig, g_total;
+};
+
+// Sub-matrices of the weights in the layout the data-gradient pass streams them: [n (reduce)][k (out)],
+// i.e. the nn.Linear [out,in] storage restricted to the input columns that carry a gradient.
+struct BwdLayout {
+    int w[MN_MAX_LAYERS];   // [L][L]    layer i >= 1, columns of the hidden part (after the PE block on skip layers)
+    int final_w;            // [L][L]
+    int dira_f;             // [L/2][L]  dir_a_encoding columns 0..L-1 (the xyz_encoding_final features)
+    int dira_e;             // [L/2][app] dir_a_encoding columns of the appearance embedding
+    int total;
+};
+
+static inline int mn_tape_tm(int L) { return L <= 256 ? 64 : 32; }
+
 struct mn_model {
     mn_ctx* ctx = nullptr;
     mn_model_desc d{};
     NetDims nd{};
     PackedLayout lay{};
+    TapeLayout tape{};
+    BwdLayout blay{};
     float* packed = nullptr;          // [n_sub * lay.total] fp32
+    float* packed_bwd = nullptr;      // [n_sub * blay.total] fp32, see BwdLayout
     float* centroids_d = nullptr;     // [n_sub, 3]
     int* counters_d = nullptr;        // routing scratch: see mn_route.cu
     int max_multiplicity = 0;         // slot capacity per row for blended routing
@@ -63,6 +92,29 @@ struct MlpArgs {
     float* out;               // [*, out_cols]
     int out_cols;
     int scatter;              // 1: out index = row, 0: out index = slot
+    float* tape;              // activation tape (training forward) or NULL
+    TapeLayout tl;
+};
+
+// Arguments of the backward kernels (csrc/mn_backward.cu).
+struct BwdArgs {
+    NetDims nd;
+    PackedLayout lay;
+    BwdLayout blay;
+    TapeLayout tl;
+    const float* packed;       // forward weights (K-major), small heads are read from here
+    const float* packed_bwd;   // see BwdLayout
+    const int* slot_row;       // slot -> row, -1 = padding; NULL = identity
+    const float* slot_w;       // slot -> blend weight; NULL = 1
+    const int* counters;       // routing counters SAVED by the forward pass, or NULL
+    int n_sub;
+    int fixed_sub;
+    int64_t B;                 // rows (identity mode) / slot capacity (routed mode)
+    const float* grad_out;     // [rows, out_cols]
+    int out_cols;
+    const float* act;          // activation tape
+    float* grad;               // gradient tape
+    float* gw;                 // parameter gradients, [n_sub * lay.total], matrices stored [out][in] (nn.Linear layout)
 };
 
 int mn_route_build(mn_ctx* ctx, mn_model* m, const RowSrc& src, int64_t B, int64_t cap, int* slot_row, float* slot_w,
@@ -71,6 +123,7 @@ size_t mn_route_scratch_bytes(const mn_model* m, int64_t B);   // per-row active
 int mn_route_combine(mn_ctx* ctx, mn_model* m, int64_t B, const int* row_slots, const float* slot_out, int out_cols,
                      float* out, cudaStream_t st);
 int mn_mlp_simt_launch(mn_ctx* ctx, const MlpArgs& a, int64_t n_tiles128, cudaStream_t st);
+int mn_mlp_bwd_launch(mn_ctx* ctx, const BwdArgs& a, int64_t n_tiles128, cudaStream_t st);
 int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles128, int precision, void* ws,
                      size_t ws_bytes, cudaStream_t st);
 size_t mn_mlp_tc_workspace(const mn_model* m, int64_t n_tiles128, int precision);

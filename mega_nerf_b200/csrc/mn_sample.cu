@@ -544,6 +544,225 @@ __global__ void embed_kernel(const float* __restrict__ x, int64_t B, int dim, in
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// backward of merge + composite                       (rendering.py:336-373)
+// ------------------------------------------------------------------------------------------------
+// With x_j = 1 - alpha_j + 1e-8, T_j = prod_{k<j} x_k, w_j = alpha_j T_j, rgb = sum_j w_j c_j,
+// lambda = prod_j x_j and upstream gradients g (rgb) and gl (lambda):
+//     dL/dc_j     = w_j g
+//     dL/dalpha_j = T_j (g.c_j) - ( sum_{i>j} w_i (g.c_i) + lambda gl ) / x_j
+//     dL/dsigma_j = dL/dalpha_j * delta_j * exp(-delta_j sigma_j)
+// The merged order is rebuilt exactly like composite_kernel does (same total order on ties), T comes from
+// the same fp64 prefix product rounded to fp32, the suffix sum runs in fp64.
+struct CompositeBwdArgs {
+    const float* raw; const float* z; int S;
+    const float* raw2; const float* z2; int S2;
+    const float* last_delta;
+    int64_t N;
+    int flip;
+    const float* grad_rgb;      // [N,3]
+    const float* grad_lambda;   // [N] or null
+    float* grad_raw;            // [N,S,4]
+    float* grad_raw2;           // [N,S2,4]
+    int npad;
+};
+
+__device__ __forceinline__ double warp_incl_suffix_add(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v = v + u;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(128) composite_bwd_kernel(const CompositeBwdArgs a) {
+    extern __shared__ unsigned char sm_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ray = (int64_t)blockIdx.x * 4 + warp;
+    if (ray >= a.N) return;
+    const int n = a.S + a.S2;
+    float* zs = reinterpret_cast<float*>(sm_raw) + (size_t)warp * a.npad * 2;
+    float* ts = zs + a.npad;   // merge scratch first, then T (exclusive transmittance) per merged position
+    unsigned short* ids = reinterpret_cast<unsigned short*>(reinterpret_cast<float*>(sm_raw) + (size_t)4 * a.npad * 2) +
+                          (size_t)warp * a.npad;
+
+    float zmax = -INFINITY;
+    for (int i = lane; i < a.S; i += 32) {
+        const float v = a.z[ray * a.S + i];
+        zs[i] = v;
+        ids[i] = (unsigned short)i;
+        zmax = fmaxf(zmax, v);
+    }
+    zmax = warp_max(zmax);
+    if (a.S2 > 0) {
+        for (int i = lane; i < a.S2; i += 32) {
+            zs[a.S + i] = a.z2[ray * a.S2 + i];
+            ids[a.S + i] = (unsigned short)(a.S + i);
+        }
+        __syncwarp();
+        bool ordered = true;
+        for (int i = lane; i + 1 < a.S; i += 32) ordered &= a.flip ? (zs[i] >= zs[i + 1]) : (zs[i] <= zs[i + 1]);
+        for (int i = lane; i + 1 < a.S2; i += 32)
+            ordered &= a.flip ? (zs[a.S + i] >= zs[a.S + i + 1]) : (zs[a.S + i] <= zs[a.S + i + 1]);
+        ordered = __all_sync(0xffffffffu, ordered);
+        if (ordered) {
+            float* zm = ts;
+            unsigned short* idm = ids + a.npad * 4;
+            for (int i = lane; i < n; i += 32) {
+                const bool own = i < a.S;
+                const float v = zs[i];
+                const float* other = own ? zs + a.S : zs;
+                const int m = own ? a.S2 : a.S;
+                int lo = 0, hi = m;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const float o = other[mid];
+                    const bool before = a.flip ? (own ? o > v : o >= v) : (own ? o < v : o <= v);
+                    if (before) lo = mid + 1; else hi = mid;
+                }
+                const int pos = (own ? i : i - a.S) + lo;
+                zm[pos] = v;
+                idm[pos] = (unsigned short)i;
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) { const float v = zm[i]; const unsigned short id = idm[i]; zs[i] = v; ids[i] = id; }
+        } else {
+            const float pad = a.flip ? -INFINITY : INFINITY;
+            for (int i = n + lane; i < a.npad; i += 32) { zs[i] = pad; ids[i] = 0xFFFF; }
+            __syncwarp();
+            warp_bitonic(zs, ids, a.npad, a.flip != 0, lane);
+        }
+    }
+    __syncwarp();
+
+    float ld = a.last_delta[ray];
+    if (ld < 1e10f) ld = ld - zmax;
+
+    // forward sweep: exclusive transmittance T (fp32-rounded fp64 prefix product, as composite_kernel)
+    double carry = 1.0;
+    float carry_f = 1.0f;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int p = c0 + lane;
+        const bool ok = p < n;
+        float x = 1.0f;
+        if (ok) {
+            const int id = ids[p];
+            const float sg = (id < a.S) ? a.raw[(ray * a.S + id) * 4 + 3] : a.raw2[(ray * a.S2 + (id - a.S)) * 4 + 3];
+            const float zz = zs[p];
+            const float znext = (p + 1 < n) ? zs[p + 1] : 0.0f;
+            float delta = a.flip ? (zz - znext) : (znext - zz);
+            if (p + 1 == n) delta = ld;
+            const float alpha = 1.0f - expf(-delta * sg);
+            x = (1.0f - alpha) + 1e-8f;
+        }
+        const double incl = warp_incl_scan_mul((double)x, lane);
+        const double Pd = carry * incl;
+        const float Tf = (float)Pd;
+        float Tprev = __shfl_up_sync(0xffffffffu, Tf, 1);
+        if (lane == 0) Tprev = carry_f;
+        if (ok) ts[p] = Tprev;
+        const int last = min(31, n - 1 - c0);
+        carry = __shfl_sync(0xffffffffu, Pd, last);
+        carry_f = __shfl_sync(0xffffffffu, Tf, last);
+    }
+    __syncwarp();
+    const float g0 = a.grad_rgb[ray * 3 + 0], g1 = a.grad_rgb[ray * 3 + 1], g2 = a.grad_rgb[ray * 3 + 2];
+    const double lam_term = a.grad_lambda ? (double)carry_f * (double)a.grad_lambda[ray] : 0.0;
+
+    // backward sweep, last chunk first
+    double tail = 0.0;   // sum of w_i (g.c_i) over all later chunks
+    for (int c0 = ((n - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
+        const int p = c0 + lane;
+        const bool ok = p < n;
+        double wG = 0.0, G = 0.0;
+        float w = 0.0f, x = 1.0f, delta = 0.0f, ex = 0.0f, Tp = 0.0f;
+        int id = 0;
+        if (ok) {
+            id = ids[p];
+            const float* rw = (id < a.S) ? a.raw + (ray * a.S + id) * 4 : a.raw2 + (ray * a.S2 + (id - a.S)) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(rw);
+            const float zz = zs[p];
+            const float znext = (p + 1 < n) ? zs[p + 1] : 0.0f;
+            delta = a.flip ? (zz - znext) : (znext - zz);
+            if (p + 1 == n) delta = ld;
+            ex = expf(-delta * v.w);
+            const float alpha = 1.0f - ex;
+            x = (1.0f - alpha) + 1e-8f;
+            Tp = ts[p];
+            w = alpha * Tp;
+            G = (double)g0 * (double)v.x + (double)g1 * (double)v.y + (double)g2 * (double)v.z;
+            wG = (double)w * G;
+        }
+        const double sfx = warp_incl_suffix_add(wG, lane);          // sum over lanes >= this one
+        const double later = (sfx - wG) + tail;                      // strictly later samples
+        if (ok) {
+            const double d_alpha = (double)Tp * G - (later + lam_term) / (double)x;
+            const float d_sigma = (float)(d_alpha * (double)delta * (double)ex);
+            float* out = (id < a.S) ? a.grad_raw + (ray * a.S + id) * 4 : a.grad_raw2 + (ray * a.S2 + (id - a.S)) * 4;
+            *reinterpret_cast<float4*>(out) = make_float4(w * g0, w * g1, w * g2, d_sigma);
+        }
+        tail += __shfl_sync(0xffffffffu, sfx, 0);
+    }
+}
+
+// Real SH basis values with the constants folded in: sh_eval(deg, s, d) == sum_k Y[k] * s[k].
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float* Y) {
+    Y[0] = 0.28209479177387814f;
+    if (deg < 1) return;
+    const float C1 = 0.4886025119029199f;
+    Y[1] = -(C1 * y); Y[2] = C1 * z; Y[3] = -(C1 * x);
+    if (deg < 2) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    Y[4] = 1.0925484305920792f * xy;
+    Y[5] = -1.0925484305920792f * yz;
+    Y[6] = 0.31539156525252005f * ((2.0f * zz - xx) - yy);
+    Y[7] = -1.0925484305920792f * xz;
+    Y[8] = 0.5462742152960396f * (xx - yy);
+    if (deg < 3) return;
+    Y[9] = (-0.5900435899266435f * y) * (3 * xx - yy);
+    Y[10] = (2.890611442640554f * xy) * z;
+    Y[11] = (-0.4570457994644658f * y) * ((4 * zz - xx) - yy);
+    Y[12] = (0.3731763325901154f * z) * ((2 * zz - 3 * xx) - 3 * yy);
+    Y[13] = (-0.4570457994644658f * x) * ((4 * zz - xx) - yy);
+    Y[14] = (1.445305721320277f * z) * (xx - yy);
+    Y[15] = (-0.5900435899266435f * x) * (xx - 3 * yy);
+    if (deg < 4) return;
+    Y[16] = (2.5033429417967046f * xy) * (xx - yy);
+    Y[17] = (-1.7701307697799304f * yz) * (3 * xx - yy);
+    Y[18] = (0.9461746957575601f * xy) * (7 * zz - 1);
+    Y[19] = (-0.6690465435572892f * yz) * (7 * zz - 3);
+    Y[20] = 0.10578554691520431f * (zz * (35 * zz - 30) + 3);
+    Y[21] = (-0.6690465435572892f * xz) * (7 * zz - 3);
+    Y[22] = (0.47308734787878004f * (xx - yy)) * (7 * zz - 1);
+    Y[23] = (-1.7701307697799304f * xz) * (xx - 3 * yy);
+    Y[24] = 0.6258357354491761f * (xx * (xx - 3 * yy) - yy * (3 * xx - yy));
+}
+
+__global__ void sh_to_rgb_bwd_kernel(int deg, const float* __restrict__ coef, int64_t cstride, const float* __restrict__ dirs,
+                                     int64_t dstride, int ddiv, int64_t B, int sig, const float* __restrict__ gout,
+                                     float* __restrict__ gcoef) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nc = (deg + 1) * (deg + 1);
+    const float* c = coef + b * cstride;
+    const float* d = dirs + (b / ddiv) * dstride;
+    float* gc = gcoef + b * cstride;
+    float Y[25], s[25];
+    sh_basis(deg, d[0], d[1], d[2], Y);
+    for (int ch = 0; ch < 3; ++ch) {
+        float g = gout[b * 4 + ch];
+        if (sig) {
+            for (int k = 0; k < nc; ++k) s[k] = c[ch * nc + k];
+            const float o = mn_sigmoid(sh_eval(deg, s, d[0], d[1], d[2]));
+            g = (g * (1.0f - o)) * o;
+        }
+        for (int k = 0; k < nc; ++k) gc[ch * nc + k] = g * Y[k];
+    }
+    gc[3 * nc] = gout[b * 4 + 3];
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -651,6 +870,38 @@ int mn_composite(mn_ctx* ctx, const float* raw_d, const float* z_d, const float*
     const size_t sm = (size_t)4 * a.npad * (2 * sizeof(float) + 2 * sizeof(unsigned short));
     MN_CUDA(ctx, cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     composite_kernel<<<(unsigned)mn_cdiv(N, 4), 128, sm, (cudaStream_t)stream>>>(a);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}
+
+int mn_composite_backward(mn_ctx* ctx, const float* raw_d, const float* z_d, int S, const float* raw2_d, const float* z2_d,
+                          int S2, const float* last_delta_d, int64_t N, int flip, const float* grad_rgb_d,
+                          const float* grad_lambda_d, float* grad_raw_d, float* grad_raw2_d, void* stream) {
+    if (!ctx || !raw_d || !z_d || !last_delta_d || !grad_rgb_d || !grad_raw_d || S < 1 || S2 < 0) return MN_ERR_INVALID;
+    if (S2 > 0 && (!raw2_d || !z2_d || !grad_raw2_d)) return MN_ERR_INVALID;
+    if (N == 0) return MN_OK;
+    CompositeBwdArgs a{};
+    a.raw = raw_d; a.z = z_d; a.S = S;
+    a.raw2 = raw2_d; a.z2 = z2_d; a.S2 = S2;
+    a.last_delta = last_delta_d; a.N = N; a.flip = flip;
+    a.grad_rgb = grad_rgb_d; a.grad_lambda = grad_lambda_d;
+    a.grad_raw = grad_raw_d; a.grad_raw2 = grad_raw2_d;
+    a.npad = S2 > 0 ? pow2_at_least(S + S2) : (S + 31) / 32 * 32;
+    if (a.npad > 4096) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "mn_composite_backward: more than 4096 samples per ray");
+    const size_t sm = (size_t)4 * a.npad * (2 * sizeof(float) + 2 * sizeof(unsigned short));
+    MN_CUDA(ctx, cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    composite_bwd_kernel<<<(unsigned)mn_cdiv(N, 4), 128, sm, (cudaStream_t)stream>>>(a);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}
+
+int mn_sh_to_rgb_backward(mn_ctx* ctx, int deg, const float* coef_d, int64_t coef_stride, const float* dirs_d,
+                          int64_t dir_stride, int dir_div, int64_t B, int apply_sigmoid, const float* grad_out_d,
+                          float* grad_coef_d, void* stream) {
+    if (!ctx || !coef_d || !dirs_d || !grad_out_d || !grad_coef_d || deg < 0 || deg > 4 || dir_div < 1) return MN_ERR_INVALID;
+    if (B == 0) return MN_OK;
+    sh_to_rgb_bwd_kernel<<<(unsigned)mn_cdiv(B, 256), 256, 0, (cudaStream_t)stream>>>(
+        deg, coef_d, coef_stride, dirs_d, dir_stride, dir_div, B, apply_sigmoid, grad_out_d, grad_coef_d);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
 }

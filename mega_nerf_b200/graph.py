@@ -35,7 +35,8 @@ class GraphedRenderRays:
         self.warmup = warmup
 
     def _run(self) -> Dict[str, torch.Tensor]:
-        res, _ = render_rays(self.nerf, None, self.rays, self.indices, self.hparams, None, None, *self.flags)
+        with torch.no_grad():      # inference path only (a recording call would switch to the fp32 training kernels)
+            res, _ = render_rays(self.nerf, None, self.rays, self.indices, self.hparams, None, None, *self.flags)
         return res
 
     def _load(self, rays: torch.Tensor, image_indices: Optional[torch.Tensor]) -> None:

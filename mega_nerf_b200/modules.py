@@ -5,7 +5,9 @@ Same constructor arguments, parameter names and shapes as the reference (so its 
   MegaNeRF  <- mega_nerf/models/mega_nerf.py:7-61
   Cascade   <- mega_nerf/models/cascade.py:7-18
   get_nerf / get_bg_nerf <- mega_nerf/models/model_utils.py:12-69
-Forward-only in this round (SURVEY.md §8f-1 lists backward as the next row).
+Training: when autograd is recording and a parameter requires grad, the call runs the fp32 kernels in
+training mode (activation tape) and returns a tensor whose backward is mn_model_backward
+(mega_nerf_b200/autograd.py).
 """
 from __future__ import annotations
 
@@ -184,6 +186,71 @@ class _Native:
                                    prec, K.ptr(out), K.ptr(ws), ws.numel(), K.stream_of(device)), h)
         return out
 
+    # ---- training (SURVEY.md §8f-1) -------------------------------------------------------------
+    PARAM_KEYS = ('sigma.weight', 'sigma.bias', 'xyz_encoding_final.weight', 'xyz_encoding_final.bias',
+                  'dir_a_encoding.0.weight', 'dir_a_encoding.0.bias', 'rgb.weight', 'rgb.bias', 'embedding_a.weight',
+                  'affine.weight', 'affine.bias')
+
+    def needs_grad(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for sub in self.subs for p in sub.parameters())
+
+    def param_list(self):
+        """[(sub index, state-dict key, parameter)] in a fixed order (the autograd.Function's tensor inputs)."""
+        out = []
+        for i, sub in enumerate(self.subs):
+            named = dict(sub.named_parameters())
+            for k in sorted(named):
+                out.append((i, k, named[k]))
+        return out
+
+    def _offsets(self):
+        L = K.lib()
+        buf = (C.c_int64 * K.MN_PARAM_OFFSETS)()
+        K.check(L.mn_model_param_offsets(self.handle, buf, K.MN_PARAM_OFFSETS), K.ctx(self.device))
+        v = list(buf)
+        off = {'stride': v[0]}
+        for li in range(K.MN_MAX_LAYERS):
+            off[f'xyz_encodings.{li}.0.weight'] = v[1 + li]
+            off[f'xyz_encodings.{li}.0.bias'] = v[1 + K.MN_MAX_LAYERS + li]
+        for j, k in enumerate(self.PARAM_KEYS):
+            off[k] = v[1 + 2 * K.MN_MAX_LAYERS + j]
+        return off
+
+    def forward_train(self, rows: K.Rows, B: int, device: torch.device, use_coarse: bool,
+                      sigma_noise: Optional[torch.Tensor], out_cols: int):
+        """-> (out [B, out_cols], tape).  The tape holds this call's routing tables and activations."""
+        L = K.lib()
+        h = self.sync(device)
+        out = torch.empty(B, out_cols, device=device, dtype=torch.float32)
+        ws = torch.empty(max(int(L.mn_model_workspace_bytes(self.handle, B, K.PREC_FP32)), 256), device=device, dtype=torch.uint8)
+        tape = torch.empty(max(int(L.mn_model_tape_bytes(self.handle, B)), 256), device=device, dtype=torch.uint8)
+        noise = K.f32c(sigma_noise).view(-1) if sigma_noise is not None else None
+        K.check(L.mn_model_forward_train(h, self.handle, C.byref(rows), B, int(use_coarse), K.ptr(noise), K.ptr(out),
+                                         K.ptr(tape), tape.numel(), K.ptr(ws), ws.numel(), K.stream_of(device)), h)
+        return out, tape
+
+    def backward(self, B: int, device: torch.device, use_coarse: bool, grad_out: torch.Tensor, tape: torch.Tensor,
+                 params):
+        """Parameter gradients for `params` (a param_list()): list of tensors shaped like the parameters."""
+        L = K.lib()
+        h = K.ctx(device)
+        n = int(L.mn_model_grad_floats(self.handle))
+        gbuf = torch.zeros(n, device=device, dtype=torch.float32)
+        ws = torch.empty(max(int(L.mn_model_backward_workspace_bytes(self.handle, B)), 256), device=device, dtype=torch.uint8)
+        g = K.f32c(grad_out)
+        K.check(L.mn_model_backward(h, self.handle, B, int(use_coarse), K.ptr(g), K.ptr(tape), tape.numel(), K.ptr(gbuf),
+                                    K.ptr(ws), ws.numel(), K.stream_of(device)), h)
+        off = self._offsets()
+        stride = off['stride']
+        grads = []
+        for i, k, p in params:
+            o = off.get(k, -1)
+            if o < 0:
+                raise RuntimeError(f'libmn_b200: no gradient slot for parameter {k!r}')
+            a = i * stride + o
+            grads.append(gbuf[a:a + p.numel()].view(p.shape))
+        return grads
+
     def stats(self, device):
         L = K.lib()
         h = K.ctx(device)
@@ -199,6 +266,48 @@ def _rows_matrix(x: torch.Tensor) -> tuple:
     r.x_d = xin.data_ptr()
     r.cols = xin.shape[1]
     return r, xin
+
+
+class RayRows:
+    """Ray-structured model input (mn_rows mode 1): xyz [B, cols] plus per-ray directions / image indices, i.e.
+    what the reference materialises with repeat + cat (rendering.py:275-292,311-319).  render_rays hands this to
+    `nerf(...)` instead of a row matrix, THROUGH any wrapper (DistributedDataParallel) so that the wrapper's own
+    forward bookkeeping runs as it does in the reference."""
+
+    def __init__(self, xyz: torch.Tensor, samples_per_ray: int, dirs: Optional[torch.Tensor], idx: Optional[torch.Tensor]):
+        self.xyz, self.samples_per_ray, self.dirs, self.idx = xyz, samples_per_ray, dirs, idx
+
+    def rows(self) -> tuple:
+        r = K.Rows()
+        r.mode = 1
+        r.x_d = self.xyz.data_ptr()
+        r.cols = self.xyz.shape[-1]
+        r.samples_per_ray = self.samples_per_ray
+        if self.dirs is not None:
+            r.dirs_d = self.dirs.data_ptr()
+            r.dir_stride = self.dirs.stride(0)
+        if self.idx is not None:
+            r.idx_d = self.idx.data_ptr()
+        return r, (self.xyz, self.dirs, self.idx)
+
+
+def _module_forward(native: _Native, x, use_coarse: bool, sigma_only: bool, sigma_noise: Optional[torch.Tensor],
+                    rgb_dim: int) -> torch.Tensor:
+    """nn.Module.__call__ body shared by NeRF / MegaNeRF / Cascade."""
+    if isinstance(x, RayRows):
+        rows, keep = x.rows()
+        B, device = x.xyz.numel() // x.xyz.shape[-1], x.xyz.device
+    else:
+        rows, xin = _rows_matrix(x)
+        keep = (xin,)
+        B, device = xin.shape[0], x.device
+    out_cols = 1 if sigma_only else rgb_dim + 1
+    if native.needs_grad():
+        if sigma_only:
+            raise RuntimeError('mega_nerf_b200: sigma_only queries are inference-only (wrap them in torch.no_grad())')
+        from .autograd import model_apply
+        return model_apply(native, rows, B, device, use_coarse, sigma_noise, out_cols, keep)
+    return native.forward(rows, B, device, use_coarse, sigma_only, sigma_noise, out_cols, keep)
 
 
 class NeRF(nn.Module):
@@ -259,10 +368,8 @@ class NeRF(nn.Module):
             object.__setattr__(self, '_native_obj', _Native(self, 0, [self], None, 1.0, False, 0))
         return self._native_obj
 
-    def forward(self, x: torch.Tensor, sigma_only: bool = False, sigma_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
-        rows, xin = _rows_matrix(x)
-        return self._native().forward(rows, xin.shape[0], x.device, True, sigma_only, sigma_noise,
-                                      1 if sigma_only else self.rgb_dim + 1, (xin,))
+    def forward(self, x, sigma_only: bool = False, sigma_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return _module_forward(self._native(), x, True, sigma_only, sigma_noise, self.rgb_dim)
 
 
 class MegaNeRF(nn.Module):
@@ -288,11 +395,8 @@ class MegaNeRF(nn.Module):
         self._native_obj.centroids = self.centroids
         return self._native_obj
 
-    def forward(self, x: torch.Tensor, sigma_only: bool = False, sigma_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
-        rows, xin = _rows_matrix(x)
-        sub = self.sub_modules[0]
-        return self._native().forward(rows, xin.shape[0], x.device, True, sigma_only, sigma_noise,
-                                      1 if sigma_only else sub.rgb_dim + 1, (xin,))
+    def forward(self, x, sigma_only: bool = False, sigma_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return _module_forward(self._native(), x, True, sigma_only, sigma_noise, self.sub_modules[0].rgb_dim)
 
 
 class Cascade(nn.Module):
@@ -309,11 +413,9 @@ class Cascade(nn.Module):
             object.__setattr__(self, '_native_obj', _Native(self, 1, [self.coarse, self.fine], None, 1.0, False, 0))
         return self._native_obj
 
-    def forward(self, use_coarse: bool, x: torch.Tensor, sigma_only: bool = False,
+    def forward(self, use_coarse: bool, x, sigma_only: bool = False,
                 sigma_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
-        rows, xin = _rows_matrix(x)
-        return self._native().forward(rows, xin.shape[0], x.device, use_coarse, sigma_only, sigma_noise,
-                                      1 if sigma_only else self.coarse.rgb_dim + 1, (xin,))
+        return _module_forward(self._native(), x, use_coarse, sigma_only, sigma_noise, self.coarse.rgb_dim)
 
 
 # --------------------------------------------------------------------------------------------------

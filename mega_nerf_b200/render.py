@@ -2,7 +2,10 @@
 orchestrating the sm_100a kernels of libmn_b200.so.  Host syncs happen only where the reference has
 them too (sphere check :412, background ray selection :37).
 
-Forward only in this round; results carry no autograd graph.
+When autograd is recording and a network parameter requires grad (the reference's training step,
+runner.py:346-378), the model queries and the compositing go through mega_nerf_b200/autograd.py and the
+returned rgb_* / bg_lambda_* carry a graph whose backward runs mn_composite_backward / mn_model_backward
+(SURVEY.md §8f-1).  Otherwise nothing is recorded.
 """
 from __future__ import annotations
 
@@ -15,7 +18,8 @@ import torch
 from torch import nn
 
 from . import _cabi as K
-from .modules import NeRF, MegaNeRF, Cascade
+from . import autograd as AG
+from .modules import NeRF, MegaNeRF, Cascade, RayRows
 
 TO_COMPOSITE = ('rgb', 'depth')
 
@@ -112,38 +116,36 @@ class _Stage:
 
 
 def _query(sg: _Stage, net: nn.Module, hparams: Namespace, typ: str, xyz: torch.Tensor, dirs: torch.Tensor,
-           idx: Optional[torch.Tensor]) -> torch.Tensor:
-    """Model query for [n,S,C] points -> raw [n,S,4] = (rgb, sigma).  rendering.py:275-334."""
+           idx: Optional[torch.Tensor], call: Optional[nn.Module] = None) -> torch.Tensor:
+    """Model query for [n,S,C] points -> raw [n,S,4] = (rgb, sigma).  rendering.py:275-334.
+    `call` is the module as the caller handed it in (e.g. DistributedDataParallel around `net`)."""
     n, S, Cc = xyz.shape
     B = n * S
     native = net._native()
     first = native.subs[0]
-    rows = K.Rows()
-    rows.mode = 1
-    rows.x_d = xyz.data_ptr()
-    rows.cols = Cc
-    rows.samples_per_ray = S
     use_dirs = hparams.pos_dir_dim != 0
-    if use_dirs:
-        rows.dirs_d = dirs.data_ptr()
-        rows.dir_stride = dirs.stride(0)
-    if idx is not None:
-        rows.idx_d = idx.data_ptr()
     noise = None
     if net.training:
         # same draw order / shapes as the reference's per-chunk torch.rand (rendering.py:294,321)
         ch = hparams.model_chunk_size
         noise = torch.cat([torch.rand(min(ch, B - a), 1, device=xyz.device) for a in range(0, B, ch)], 0)
-    out = native.forward(rows, B, xyz.device, typ == 'coarse', False, noise, first.rgb_dim + 1)
+    rr = RayRows(xyz, S, dirs if use_dirs else None, idx)
+    target = call if call is not None else net
+    if native.needs_grad():
+        # through the wrapper's __call__, like `nerf(x)` in the reference (rendering.py:296-299)
+        out = target(typ == 'coarse', rr, sigma_noise=noise) if isinstance(net, Cascade) else target(rr, sigma_noise=noise)
+    else:
+        rows, keep = rr.rows()
+        out = native.forward(rows, B, xyz.device, typ == 'coarse', False, noise, first.rgb_dim + 1, keep)
     if hparams.pos_dir_dim == 0 and hparams.sh_deg is not None:
-        out = sg.sh_to_rgb(hparams.sh_deg, out, dirs, S)
+        out = AG.sh_apply(sg, hparams.sh_deg, out, dirs, S) if out.requires_grad else sg.sh_to_rgb(hparams.sh_deg, out, dirs, S)
     return out.view(n, S, 4)
 
 
 def _two_pass(sg: _Stage, net: nn.Module, hparams: Namespace, dirs: torch.Tensor, idx: Optional[torch.Tensor],
               xyz_coarse: torch.Tensor, z: torch.Tensor, last_delta: torch.Tensor, get_depth: bool,
               get_depth_variance: bool, get_bg_lambda: bool, flip: bool, depth_real: Optional[torch.Tensor],
-              xyz_fine_fn: Callable) -> Dict[str, torch.Tensor]:
+              xyz_fine_fn: Callable, call: Optional[nn.Module] = None) -> Dict[str, torch.Tensor]:
     """coarse -> resample -> fine  (rendering.py:176-248 with _inference :251-393 inlined)."""
     res: Dict[str, torch.Tensor] = {}
     fine = hparams.fine_samples > 0
@@ -155,12 +157,39 @@ def _two_pass(sg: _Stage, net: nn.Module, hparams: Namespace, dirs: torch.Tensor
     if flip:
         xyz_c = torch.flip(xyz_coarse, dims=[-2]).contiguous()
         z_c = torch.flip(z, dims=[-1]).contiguous()
-    raw_c = _query(sg, net, hparams, 'coarse', xyz_c, dirs, idx)
-    w, rgb, depth, var, lam = sg.composite(raw_c, z_c, depth_real, None, None, None, last_delta, flip,
-                                           want_w=fine, want_rgb=cascade,
-                                           want_depth=(not fine) and (get_depth or get_depth_variance),
-                                           want_var=(not fine) and get_depth_variance,
-                                           want_lambda=get_bg_lambda and cascade)
+    raw_c = _query(sg, net, hparams, 'coarse', xyz_c, dirs, idx, call)
+    grad = raw_c.requires_grad
+
+    def composite(raw, zz, dreal, raw2, z2, dreal2, want_depth, want_var, want_lambda):
+        """rgb (+ depth, variance, bg_lambda) of one pass; recorded for backward iff the queries were."""
+        if grad:
+            return AG.composite_apply(sg, raw, zz, dreal, raw2, z2, dreal2, last_delta, flip, want_depth, want_var, want_lambda)
+        return sg.composite(raw, zz, dreal, raw2, z2, dreal2, last_delta, flip, False, True, want_depth, want_var,
+                            want_lambda)[1:]
+
+    if not grad:
+        w, rgb, depth, var, lam = sg.composite(raw_c, z_c, depth_real, None, None, None, last_delta, flip,
+                                               want_w=fine, want_rgb=cascade,
+                                               want_depth=(not fine) and (get_depth or get_depth_variance),
+                                               want_var=(not fine) and get_depth_variance,
+                                               want_lambda=get_bg_lambda and cascade)
+    else:
+        w = rgb = depth = var = lam = None
+        if cascade:
+            rgb, depth, var, lam = composite(raw_c, z_c, depth_real, None, None, None,
+                                             (not fine) and (get_depth or get_depth_variance),
+                                             (not fine) and get_depth_variance, get_bg_lambda)
+        if fine or not cascade:
+            # resampling weights (detached in the reference, rendering.py:215) and, for a coarse-only non-cascade
+            # call, the depth terms (no_grad, rendering.py:381): nothing here carries a gradient
+            with torch.no_grad():
+                w, _, d2, v2, _ = sg.composite(raw_c.detach(), z_c, depth_real, None, None, None, last_delta, flip,
+                                               want_w=fine, want_rgb=False,
+                                               want_depth=(not cascade) and (not fine) and (get_depth or get_depth_variance),
+                                               want_var=(not cascade) and (not fine) and get_depth_variance,
+                                               want_lambda=False)
+            if not cascade:
+                depth, var = d2, v2
     if lam is not None:
         res['bg_lambda_coarse'] = lam
     if rgb is not None:
@@ -190,14 +219,13 @@ def _two_pass(sg: _Stage, net: nn.Module, hparams: Namespace, dirs: torch.Tensor
         if flip:
             xyz_f = torch.flip(xyz_f, dims=[-2]).contiguous()
             z_f = torch.flip(z_f, dims=[-1]).contiguous()
-        raw_f = _query(sg, net, hparams, 'fine', xyz_f, dirs, idx)
-        _, rgb, depth, var, lam = sg.composite(raw_f, z_f, dreal_f, None, None, None, last_delta, flip, False, True,
-                                               get_depth or get_depth_variance, get_depth_variance, get_bg_lambda)
+        raw_f = _query(sg, net, hparams, 'fine', xyz_f, dirs, idx, call)
+        rgb, depth, var, lam = composite(raw_f, z_f, dreal_f, None, None, None, get_depth or get_depth_variance,
+                                         get_depth_variance, get_bg_lambda)
     else:
-        raw_f = _query(sg, net, hparams, 'fine', xyz_f, dirs, idx)
-        _, rgb, depth, var, lam = sg.composite(raw_f, z_f, dreal_f, raw_c, z_c, depth_real if dreal_f is not None else None,
-                                               last_delta, flip, False, True, get_depth or get_depth_variance,
-                                               get_depth_variance, get_bg_lambda)
+        raw_f = _query(sg, net, hparams, 'fine', xyz_f, dirs, idx, call)
+        rgb, depth, var, lam = composite(raw_f, z_f, dreal_f, raw_c, z_c, depth_real if dreal_f is not None else None,
+                                         get_depth or get_depth_variance, get_depth_variance, get_bg_lambda)
     res['rgb_fine'] = rgb
     if lam is not None:
         res['bg_lambda_fine'] = lam
@@ -222,13 +250,18 @@ def render_rays(nerf: nn.Module,
     bg = _unwrap(bg_nerf)
     if not isinstance(net, (NeRF, MegaNeRF, Cascade)) or (bg is not None and not isinstance(bg, (NeRF, MegaNeRF, Cascade))):
         raise TypeError('mega_nerf_b200.render_rays needs mega_nerf_b200 modules (use get_nerf / install())')
+    recording = net._native().needs_grad() or (bg is not None and bg._native().needs_grad())
+    if recording:
+        # training step (runner.py:346-358): queries and compositing are recorded, see mega_nerf_b200/autograd.py
+        return _render(net, bg, rays.detach(), image_indices, hparams, sphere_center, sphere_radius, get_depth,
+                       get_depth_variance, get_bg_fg_rgb, nerf, bg_nerf)
     with torch.no_grad():
         return _render(net, bg, rays, image_indices, hparams, sphere_center, sphere_radius, get_depth,
                        get_depth_variance, get_bg_fg_rgb)
 
 
 def _render(net, bg, rays, image_indices, hparams, sphere_center, sphere_radius, get_depth, get_depth_variance,
-            get_bg_fg_rgb):
+            get_bg_fg_rgb, call_net=None, call_bg=None):
     dev = rays.device
     sg = _Stage(dev)
     rays = K.f32c(rays)
@@ -266,13 +299,13 @@ def _render(net, bg, rays, image_indices, hparams, sphere_center, sphere_radius,
             bg_idx = idx[with_bg].contiguous() if idx is not None else None
             bg_res = _two_pass(sg, bg, hparams, bg_dirs, bg_idx, bpts, bz,
                                torch.full((nb,), 1e10, device=dev, dtype=torch.float32), get_depth,
-                               get_depth_variance, False, True, breal, mk)
+                               get_depth_variance, False, True, breal, mk, call_bg)
 
     steps = torch.linspace(0, 1, S, device=dev)
     rnd = torch.rand(N, S, device=dev) if perturb > 0 else None
     z, xyz = sg.sample_coarse(rays, far_override, steps, rnd, perturb, N, S)
     res = _two_pass(sg, net, hparams, dirs, idx, xyz, z, last_delta, get_depth, get_depth_variance, bg is not None,
-                    False, None, lambda zz: (sg.points_from_z(rays, zz), None))
+                    False, None, lambda zz: (sg.points_from_z(rays, zz), None), call_net)
 
     if bg is not None:
         types = ['fine' if hparams.fine_samples > 0 else 'coarse']
@@ -296,4 +329,12 @@ def _render(net, bg, rays, image_indices, hparams, sphere_center, sphere_radius,
                     res[f'fg_{name}'] = val
                     res[f'bg_{name}'] = torch.zeros_like(val)
     present = bool(bg is not None and with_bg.shape[0] > 0)
+    if bg is not None and not present and 'RANK' in os.environ and net.training and bg._native().needs_grad():
+        # Distributed training with no background ray in this batch: the reference renders one dummy background
+        # ray and adds 0 x its colour (rendering.py:143-171) so that every bg parameter still takes part in the
+        # backward pass (all-zero gradients) and the optimiser steps on every rank.  Same effect, without the render:
+        key = f'rgb_{"fine" if hparams.fine_samples > 0 else "coarse"}'
+        touch = sum(p.sum() for p in bg.parameters() if p.requires_grad)
+        res[key] = res[key] + 0 * touch
+        present = True
     return res, present

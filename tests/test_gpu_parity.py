@@ -55,7 +55,9 @@ def product_net(net: O.Net):
         out = m.Cascade(subs[0], subs[1])
     else:
         out = m.MegaNeRF(subs, net.centroids.clone(), net.boundary_margin, net.xyz_real, net.cluster_2d)
-    return out.to(DEV).eval()
+    # inference parity: frozen parameters, so that calls outside no_grad are not recorded for backward (the
+    # recording path always runs the fp32 kernels, tests/test_gpu_zz_backward.py)
+    return out.to(DEV).eval().requires_grad_(False)
 
 
 # ------------------------------------------------------------------------------------------------
