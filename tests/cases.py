@@ -158,6 +158,29 @@ def grad_cotangents(name: str, n_rays: int) -> Dict[str, torch.Tensor]:
     return {'rgb_fine': torch.randn(n_rays, 3, generator=g), 'rgb_coarse': torch.randn(n_rays, 3, generator=g)}
 
 
+CONTAINER_PATH = os.path.join(ROOT, 'tests', 'golden', 'container_v1.pt')
+
+
+def container_nets():
+    """Foreground / background mixtures stored in tests/golden/container_v1.pt (tests/golden/make_container.py)."""
+    cents = O.grid_centroids(2, 2)
+    spec = O.NerfSpec(layer_dim=64, appearance_count=10)
+    bspec = O.NerfSpec(layer_dim=64, appearance_count=10, xyz_dim=4)
+    fg = O.make_net('mega', spec, seed=31, n_sub=4, centroids=cents, boundary_margin=1.15, cluster_2d=True)
+    bg = O.make_net('mega', bspec, seed=32, n_sub=4, centroids=cents, boundary_margin=1.15, xyz_real=True, cluster_2d=True)
+    return fg, bg, cents
+
+
+def container_hparams(**over):
+    """The hparams fields model_utils.py reads (mega_nerf/opts.py defaults, small widths)."""
+    from argparse import Namespace
+    hp = dict(pos_xyz_dim=12, pos_dir_dim=4, layers=8, skip_layers=[4], layer_dim=64, bg_layer_dim=64, appearance_dim=48,
+              affine_appearance=False, sh_deg=None, shifted_softplus=True, use_cascade=False, container_path=None,
+              ckpt_path=None, train_mega_nerf=None, boundary_margin=1.15)
+    hp.update(over)
+    return Namespace(**hp)
+
+
 def render_case(name: str):
     """-> (net, bg_net, rays, image_indices, opts, sphere_center, sphere_radius)."""
     c = RENDER_CASES[name] if name in RENDER_CASES else GRAD_CASES[name]
