@@ -185,6 +185,98 @@ def log(msg):
         print(f'[bench {time.strftime("%H:%M:%S")}] {msg}', file=sys.stderr, flush=True)
 
 
+def run_train(args, rank, local_rank, world):
+    """One training step of the reference (runner.py:346-378, :244-274 without AMP): render_rays(get_depth=False,
+    get_depth_variance=True) in train() mode, photometric MSE, backward, Adam step.  Rank-sharded rays, gradients
+    all-reduced by DistributedDataParallel semantics are NOT part of this diagnostic (N = 1 only)."""
+    import mega_nerf_b200 as M
+    from mega_nerf_b200 import _cabi as K
+    from test_gpu_parity import product_net
+    if world != 1:
+        raise SystemExit('--mode train is a single-GPU diagnostic')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    spec, net, rays_h, idx_h, opts = workload()
+    hp = Namespace(**vars(opts))
+    model = product_net(net).requires_grad_(True).train()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    rgbs_h = torch.rand(N_RAYS, 3, generator=torch.Generator().manual_seed(9))
+    rays_pin, idx_pin, rgbs_pin = rays_h.pin_memory(), idx_h.pin_memory(), rgbs_h.pin_memory()
+    loss_pin = torch.empty(1).pin_memory()
+    rays_d, idx_d, rgbs_d = rays_h.to(dev), idx_h.to(dev), rgbs_h.to(dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    h, L = K.ctx(dev), K.lib()
+
+    def step(r, i, t):
+        res, _ = M.render_rays(model, None, r, i, hp, None, None, False, True, False)
+        loss = torch.nn.functional.mse_loss(res['rgb_fine'], t)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_resident():
+        step(rays_d, idx_d, rgbs_d)
+
+    def step_e2e():
+        loss = step(rays_pin.to(dev, non_blocking=True), idx_pin.to(dev, non_blocking=True), rgbs_pin.to(dev, non_blocking=True))
+        loss_pin.copy_(loss.detach().view(1), non_blocking=True)
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        for a, b in evs:
+            flush.fill_(1)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    for _ in range(args.warmup):
+        step_resident()
+        step_e2e()
+    torch.cuda.synchronize()
+    l0 = L.mn_launch_count(h)
+    step_resident()
+    launches_per_step = L.mn_launch_count(h) - l0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(step_resident, args.steps)
+    ms_e2e = timed(step_e2e, args.steps)
+    K.check(L.mn_profile_enable(h, 1), h)
+    timed(step_resident, args.steps)
+    tot_ms, n_l = C.c_double(), C.c_longlong()
+    K.check(L.mn_profile_read(h, C.byref(tot_ms), C.byref(n_l)), h)
+    K.check(L.mn_profile_enable(h, 0), h)
+    clocks = sampler.stop()
+    slots, _ = model._native().stats(dev)
+    mult = slots / (N_RAYS * FINE)
+    pk = peaks()
+    samples = N_RAYS * (COARSE + FINE)
+    flops_step = 3 * samples * mult * flops_per_row(spec)          # forward + data gradients + weight gradients
+    kms = tot_ms.value / args.steps
+    achieved = flops_step / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+    line = {
+        'metric': 'training ray-samples/sec (forward + backward + Adam)', 'value': samples * args.steps / (ms * 1e-3),
+        'unit': 'samples/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{WL["desc"]}, {N_RAYS} rays x ({COARSE} coarse + {FINE} fine), train() mode (jitter, density '
+                               f'noise, random resampling), boundary_margin {MARGIN} (m = {mult:.3f}), MSE vs random colours, Adam',
+                   'parallelism': 'single GPU', 'precision': 'fp32 (CUDA-core kernels; the only backward arithmetic so far)',
+                   'launch': 'eager', 'l2': f'flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)'},
+        'e2e': {'value': samples * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e2e / args.steps,
+                'h2d_bytes_per_step': (rays_pin.numel() + idx_pin.numel() + rgbs_pin.numel()) * 4, 'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches_per_step * args.steps),
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'mlp_simt_kernel<SAVE> + mlp_bwd_data_kernel + mlp_bwd_weight_kernel',
+                     'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
+                     'peak_source': pk['src'], 'traffic': None, 'kernel_ms_per_step': kms,
+                     'note': 'GEMM-shaped work still on the fp32 FMA pipe: the fraction is against the tensor-core peak on purpose'},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     import faulthandler
     faulthandler.dump_traceback_later(240, repeat=True, file=sys.stderr)
@@ -197,6 +289,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true', help='issue every step eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--mode', default='render', choices=['render', 'train'],
+                    help="'render' = the graded line; 'train' = one optimisation step (forward + backward + Adam) of the same "
+                         "workload through the recording path (SURVEY.md §8f-1), diagnostics only")
     args = ap.parse_args()
     select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -206,6 +301,9 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
         run_reference(args, rank)
+        return
+    if args.mode == 'train':
+        run_train(args, rank, local_rank, world)
         return
 
     import torch.distributed as dist

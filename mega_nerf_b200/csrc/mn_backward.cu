@@ -359,6 +359,7 @@ int mn_mlp_bwd_launch(mn_ctx* ctx, const BwdArgs& a, int64_t n_tiles128, cudaStr
     const int TM = mn_tape_tm(nd.L);
     const int64_t n_tiles = n_tiles128 * (MN_TILE / TM);
 
+    mn_prof_begin(ctx, st);   // bench.py --mode train: data + weight gradient kernels timed as one span
     // ---- data gradients
     if (TM == 64) {
         const size_t sm = bwd_smem_bytes<64>(nd, a.out_cols);
@@ -419,6 +420,7 @@ int mn_mlp_bwd_launch(mn_ctx* ctx, const BwdArgs& a, int64_t n_tiles128, cudaStr
         mlp_bwd_weight_kernel<64><<<grid, 256, 0, st>>>(w);
     else
         mlp_bwd_weight_kernel<32><<<grid, 256, 0, st>>>(w);
+    mn_prof_end(ctx, st);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
 }
