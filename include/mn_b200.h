@@ -201,6 +201,17 @@ int mn_model_route(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int
  * slots = routed (row, sub-module) pairs, tiles = 128-row MLP tiles. */
 int mn_model_last_stats(mn_ctx* ctx, mn_model* m, int64_t* slots, int64_t* tiles, void* stream);
 
+/* ---- cluster masks ------------------------------------------- scripts/create_cluster_masks.py ----
+ * The per-image hot loop of create_cluster_masks.py:155-201: for every ray, the minimum over
+ * its S samples (z = near(1-t) + far t, t = z_steps_d [S] = torch.linspace(0,1,S) passed in) of
+ * d(sample, centroid_k) / (min_j d(sample, centroid_j) + 1e-8), distances over (y,z) only iff cluster_2d.
+ *   rays_d [N,8]; centroids_d [K,3];  ratios_out_d optional [N,K];
+ *   mask_out_d optional uint8 [K,N] = (ratio <= boundary_margin), i.e. one [H,W] pixel mask per cluster
+ *   (create_cluster_masks.py:199-201).  At least one output must be given. */
+int mn_cluster_min_dist_ratios(mn_ctx* ctx, const float* rays_d, int64_t N, const float* z_steps_d, int S,
+                               const float* centroids_d, int K, int cluster_2d, float boundary_margin,
+                               float* ratios_out_d, unsigned char* mask_out_d, void* stream);
+
 /* ---- training: gradients of the path ------------------------------------ SURVEY.md §8f-1 --------
  * What `loss.backward()` computes through the hot path in the reference's training step
  * (runner.py:346-378 -> :265).  Gradient flow is the reference's: per-sample (rgb, sigma) receive

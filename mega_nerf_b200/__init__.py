@@ -10,3 +10,4 @@ from .graph import GraphedRenderRays  # noqa: F401
 from .raygen import get_ray_directions, get_rays, get_rays_batch  # noqa: F401
 from .sh import eval_sh  # noqa: F401
 from .install import install  # noqa: F401
+from . import cluster_masks  # noqa: F401

@@ -207,6 +207,77 @@ __global__ void route_only_kernel(RowSrc src, int64_t B, const float* __restrict
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Cluster masks (scripts/create_cluster_masks.py:155-201): for every ray the minimum over
+// its S samples of d(sample, centroid_k) / (min_j d(sample, centroid_j) + 1e-8), without materialising
+// the reference's [rays, S, K] distance tensor.  One warp per ray, lanes stride the samples, running
+// minima in registers, one shuffle reduction at the end.  Arithmetic = the torch ops, separately rounded:
+// z = near (1 - t) + far t;  xyz = o + d z;  cdist's matmul path (FMA chain, see distances<> above).
+// ------------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(128) cluster_ratio_kernel(const float* __restrict__ rays, int64_t N,
+                                                            const float* __restrict__ z_steps, int S,
+                                                            const float* __restrict__ cent, int K, int s, float margin,
+                                                            float* __restrict__ ratios, unsigned char* __restrict__ mask) {
+    __shared__ float sc[MN_MAX_SUB * 3];
+    __shared__ float scn[MN_MAX_SUB];
+    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) sc[i] = cent[i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float cn = sc[k * 3 + s] * sc[k * 3 + s];
+        for (int j = s + 1; j < 3; ++j) cn = cn + sc[k * 3 + j] * sc[k * 3 + j];
+        scn[k] = cn;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ray = (int64_t)blockIdx.x * 4 + warp;
+    if (ray >= N) return;
+    const float* r = rays + ray * 8;
+    const float o[3] = {r[0], r[1], r[2]}, dir[3] = {r[3], r[4], r[5]};
+    const float near = r[6], far = r[7];
+    float best[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) best[k] = INFINITY;
+    for (int i = lane; i < S; i += 32) {
+        const float t = z_steps[i];
+        const float z = near * (1.0f - t) + far * t;
+        float x[3];
+        for (int j = 0; j < 3; ++j) x[j] = o[j] + dir[j] * z;
+        float xn = x[s] * x[s];
+        for (int j = s + 1; j < 3; ++j) xn = xn + x[j] * x[j];
+        float d[KMAX];
+        float dmin = INFINITY;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                float acc = 0.0f;
+                for (int j = s; j < 3; ++j) acc = fmaf(-2.0f * x[j], sc[k * 3 + j], acc);
+                acc = fmaf(xn, 1.0f, acc);
+                acc = fmaf(1.0f, scn[k], acc);
+                d[k] = sqrtf(fmaxf(acc, 0.0f));
+                dmin = fminf(dmin, d[k]);
+            }
+        }
+        const float den = dmin + 1e-8f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) best[k] = fminf(best[k], d[k] / den);
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+            float v = best[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, off));
+            if (lane == 0) {
+                if (ratios) ratios[ray * K + k] = v;
+                if (mask) mask[(int64_t)k * N + ray] = v <= margin ? 1 : 0;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 size_t mn_route_scratch_bytes(const mn_model* m, int64_t B) {
@@ -265,6 +336,21 @@ extern "C" int mn_model_route(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int
     cudaStream_t st = (cudaStream_t)stream;
     MN_ROUTE_DISPATCH(route_only_kernel, (unsigned)mn_cdiv(B, 128), 128, src, B, m->centroids_d, K, m->d.cluster_dim_start,
                       m->d.boundary_margin, direct, assign_out_d, weights_out_d);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}
+
+extern "C" int mn_cluster_min_dist_ratios(mn_ctx* ctx, const float* rays_d, int64_t N, const float* z_steps_d, int S,
+                                          const float* centroids_d, int K, int cluster_2d, float boundary_margin,
+                                          float* ratios_out_d, unsigned char* mask_out_d, void* stream) {
+    if (!ctx || !rays_d || !z_steps_d || !centroids_d || N < 0 || S < 1 || K < 1 || K > MN_MAX_SUB) return MN_ERR_INVALID;
+    if (!ratios_out_d && !mask_out_d) return MN_ERR_INVALID;
+    if (N == 0) return MN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)mn_cdiv(N, 4);
+    const int s = cluster_2d ? 1 : 0;
+    MN_ROUTE_DISPATCH(cluster_ratio_kernel, blocks, 128, rays_d, N, z_steps_d, S, centroids_d, K, s, boundary_margin,
+                      ratios_out_d, mask_out_d);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
 }

@@ -605,6 +605,58 @@ def render_rays(net: Net, bg_net: Optional[Net], rays: torch.Tensor, image_indic
 
 
 # --------------------------------------------------------------------------------------------
+# cluster masks                                    (scripts/create_cluster_masks.py:104-213)
+# --------------------------------------------------------------------------------------------
+
+def grid_centroids_from_cameras(camera_positions: torch.Tensor, grid_dim) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Cell centres of a grid_dim[0] x grid_dim[1] grid over the cameras' (y, z) extent, altitude ignored.
+    create_cluster_masks.py:66-80.  -> (centroids [K,3], min_position, max_position)."""
+    min_position = camera_positions.min(dim=0)[0]
+    max_position = camera_positions.max(dim=0)[0]
+    ranges = max_position[1:] - min_position[1:]
+    offsets = [torch.arange(s) * ranges[i] / s + ranges[i] / (s * 2) for i, s in enumerate(grid_dim)]
+    cent = torch.stack((torch.zeros(grid_dim[0], grid_dim[1]),
+                        torch.ones(grid_dim[0], grid_dim[1]) * min_position[1],
+                        torch.ones(grid_dim[0], grid_dim[1]) * min_position[2])).permute(1, 2, 0)
+    cent[:, :, 1] += offsets[0].unsqueeze(1)
+    cent[:, :, 2] += offsets[1]
+    return cent.reshape(-1, 3), min_position, max_position
+
+
+def cluster_min_dist_ratios(rays: torch.Tensor, z_steps: torch.Tensor, centroids: torch.Tensor, cluster_2d: bool,
+                            ray_chunk_size: int = 48 * 1024, dist_chunk_size: int = 64 * 1024 * 1024) -> torch.Tensor:
+    """For every ray the minimum over its samples of d(sample, centroid_k) / (min_j d(sample, centroid_j) + 1e-8).
+    rays [N,8] -> [N,K].  create_cluster_masks.py:155-185 (same chunking: torch.cdist switches algorithm on tiny batches)."""
+    s = 1 if cluster_2d else 0
+    out = []
+    for j in range(0, rays.shape[0], ray_chunk_size):
+        o = rays[j:j + ray_chunk_size, :3]
+        d = rays[j:j + ray_chunk_size, 3:6]
+        near, far = rays[j:j + ray_chunk_size, 6:7], rays[j:j + ray_chunk_size, 7:8]
+        z = near * (1 - z_steps) + far * z_steps
+        xyz = (o.unsqueeze(1) + d.unsqueeze(1) * z.unsqueeze(-1)).view(-1, 3)
+        dist, dmin = [], []
+        for k in range(0, xyz.shape[0], dist_chunk_size):
+            dd = torch.cdist(xyz[k:k + dist_chunk_size, s:], centroids[:, s:])
+            dist.append(dd)
+            dmin.append(dd.min(dim=1)[0])
+        dist = torch.cat(dist).view(o.shape[0], -1, centroids.shape[0])
+        dmin = torch.cat(dmin).view(o.shape[0], -1)
+        out.append((dist / (dmin.unsqueeze(-1) + 1e-8)).min(dim=1)[0])
+    return torch.cat(out)
+
+
+def image_cluster_masks(W: int, H: int, intrinsics, c2w: torch.Tensor, near: float, far: float, ray_altitude_range,
+                        center_pixels: bool, z_steps: torch.Tensor, centroids: torch.Tensor, cluster_2d: bool,
+                        boundary_margin: float, ray_chunk_size: int = 48 * 1024) -> torch.Tensor:
+    """Per-cluster pixel masks of one image, [K,H,W] bool.  create_cluster_masks.py:139-201."""
+    dirs = ray_directions(W, H, intrinsics[0], intrinsics[1], intrinsics[2], intrinsics[3], center_pixels)
+    rays = rays_from_pose(dirs, c2w, near, far, ray_altitude_range).view(-1, 8)
+    ratios = cluster_min_dist_ratios(rays, z_steps, centroids, cluster_2d, ray_chunk_size).view(H, W, centroids.shape[0])
+    return (ratios <= boundary_margin).permute(2, 0, 1)
+
+
+# --------------------------------------------------------------------------------------------
 # gradients (SURVEY.md §8f-1): torch autograd over the restatement above, i.e. exactly what
 # `loss.backward()` does in the reference's training step (runner.py:346-378, :265) on CPU fp32.
 # Gradient flow mirrors the reference: resampling weights are detached (rendering.py:215), depth

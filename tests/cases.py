@@ -158,6 +158,21 @@ def grad_cotangents(name: str, n_rays: int) -> Dict[str, torch.Tensor]:
     return {'rgb_fine': torch.randn(n_rays, 3, generator=g), 'rgb_coarse': torch.randn(n_rays, 3, generator=g)}
 
 
+CLUSTER_GOLDEN_PATH = os.path.join(ROOT, 'tests', 'golden', 'cluster_masks_v1.pt')
+
+
+def cluster_mask_case() -> dict:
+    """Tiny synthetic dataset for scripts/create_cluster_masks.py: 4 downward-looking cameras over a 2 x 2 grid."""
+    g = torch.Generator().manual_seed(123)
+    images = []
+    for i in range(4):
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g) * 0.15 + torch.tensor([[0.0, 0.0, -1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0]]))
+        pos = torch.tensor([-0.5 + 0.05 * i, -0.4 + 0.27 * (i % 2) + 0.1 * i, 0.3 - 0.22 * i])
+        images.append(dict(c2w=torch.cat([q, pos.unsqueeze(-1)], -1), intrinsics=[20.0 + i, 19.0, 12.3, 8.1], W=24, H=16))
+    return dict(images=images, grid_dim=[2, 2], ray_samples=64, ray_chunk_size=100, ray_altitude_range=[-0.45, 0.1],
+                near=0.05, far=1.5, cluster_2d=True, boundary_margin=1.15, center_pixels=True)
+
+
 CONTAINER_PATH = os.path.join(ROOT, 'tests', 'golden', 'container_v1.pt')
 
 
