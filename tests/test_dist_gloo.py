@@ -81,3 +81,65 @@ def test_shard_bounds_cover():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# training: the recording path under DistributedDataParallel (runner.py:121, rendering.py:296-299)
+# ------------------------------------------------------------------------------------------------
+class _StandInFn(torch.autograd.Function):
+    """Same contract as mega_nerf_b200.autograd._ModelFn: non-tensor arguments first, parameters as tensor inputs,
+    gradients returned positionally."""
+
+    @staticmethod
+    def forward(ctx, rr, weight):
+        ctx.save_for_backward(rr.xyz, weight)
+        return rr.xyz @ weight.t()
+
+    @staticmethod
+    def backward(ctx, g):
+        xyz, weight = ctx.saved_tensors
+        return None, g.t() @ xyz
+
+
+class _StandIn(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.lin = torch.nn.Linear(3, 4, bias=False)
+
+    def forward(self, x, sigma_noise=None):
+        from mega_nerf_b200.modules import RayRows
+        assert isinstance(x, RayRows), type(x)          # DDP.__call__ must hand the object through untouched
+        return _StandInFn.apply(x, self.lin.weight)
+
+
+def ddp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from mega_nerf_b200.modules import RayRows
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = _StandIn()
+    ddp = torch.nn.parallel.DistributedDataParallel(net)
+    xyz = torch.rand(50, 3, generator=torch.Generator().manual_seed(10 + rank))
+    out = ddp(RayRows(xyz, 5, None, None), sigma_noise=None)
+    out.sum().backward()
+    q.put((rank, net.lin.weight.grad.tolist(), xyz.sum(0).tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_hands_rayrows_through_and_reduces_gradients():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = free_port()
+    ps = [ctx.Process(target=ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    mean = (torch.tensor(out[0][2]) + torch.tensor(out[1][2])) / 2    # d(sum(xyz W^T))/dW[n] = sum_rows xyz, averaged over ranks
+    for _, g, _ in out:
+        assert torch.allclose(torch.tensor(g), mean.expand(4, 3), atol=1e-5)
