@@ -180,6 +180,41 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+def gpu_incumbent(O, net, rays_d, idx_d, opts, dev, steps: int = 5):
+    """SURVEY.md §8d "GPU incumbent": the reference algorithm as PyTorch eager ops on the SAME B200 (the oracle
+    restatement moved to CUDA: cuBLAS GEMMs + ~10^3 elementwise launches per step) in the three precisions the
+    reference can run in - fp32, TF32, and autocast fp16 (its default, runner.py:243).  A baseline leg like
+    cpu_baseline: reported next to the product's number, never on the product path.  Any failure is reported, not raised."""
+    out = {'kind': 'port (oracle restatement under torch-CUDA eager, same GPU)', 'unit': 'samples/s', 'steps': steps}
+    try:
+        netd = O.net_to(net, dev)
+        n = rays_d.shape[0]
+        samples = n * (opts.coarse_samples + opts.fine_samples)
+        saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        for name, tf32, amp in (('fp32', False, False), ('tf32', True, False), ('amp_fp16', True, True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+
+            def step():
+                with torch.inference_mode(), torch.autocast('cuda', dtype=torch.float16, enabled=amp):
+                    O.render_rays(netd, None, rays_d, idx_d, opts, None, None, True, False, False)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                step()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / steps
+            out[name] = {'value': samples / (ms * 1e-3), 'ms_per_step': ms}
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    except Exception as e:  # noqa: BLE001
+        out['error'] = repr(e)[:300]
+    return out
+
+
 def log(msg):
     if os.environ.get('MN_BENCH_VERBOSE', '1') == '1':
         print(f'[bench {time.strftime("%H:%M:%S")}] {msg}', file=sys.stderr, flush=True)
@@ -287,6 +322,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('MN_B200_PRECISION', 'tc_f16'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-incumbent', action='store_true', help='skip timing the restatement under torch-CUDA eager')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true', help='issue every step eagerly instead of replaying a CUDA graph')
     ap.add_argument('--mode', default='render', choices=['render', 'train'],
@@ -489,6 +525,9 @@ def main():
         }
         if cpu is not None:
             line['cpu_baseline'] = cpu
+        if world == 1 and not args.no_gpu_incumbent:
+            line['gpu_incumbent'] = gpu_incumbent(O, net, rays_d, idx_d, opts, dev)
+            log(f'gpu incumbent: {line["gpu_incumbent"]}')
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -227,6 +227,15 @@ class Net:
         return 1 if self.cluster_2d else 0
 
 
+def net_to(net: Optional[Net], device) -> Optional[Net]:
+    """The same network with its tensors on `device` (bench.py: the restatement under torch-CUDA as the GPU incumbent)."""
+    if net is None:
+        return None
+    import dataclasses
+    return dataclasses.replace(net, weights=[{k: v.to(device) for k, v in w.items()} for w in net.weights],
+                               centroids=net.centroids.to(device) if net.centroids is not None else None)
+
+
 def route(net: Net, x: torch.Tensor):
     """Spatial routing.  models/mega_nerf.py:21-30.  Returns (assign or None, weights or None)."""
     s = net.cluster_dim_start
@@ -243,7 +252,7 @@ def mega_forward(net: Net, x: torch.Tensor, sigma_only: bool = False,
                  sigma_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Nearest-centroid routing or inverse-distance blending.  models/mega_nerf.py:19-61."""
     assign, wts = route(net, x)
-    out = torch.empty(0)
+    out = torch.empty(0, device=x.device)
     for i, w in enumerate(net.weights):
         mask = (assign == i) if wts is None else (wts[:, i] > 0)
         sub_x = x[mask, 3:] if net.xyz_real else x[mask]
@@ -251,7 +260,7 @@ def mega_forward(net: Net, x: torch.Tensor, sigma_only: bool = False,
             continue
         r = nerf_forward(net.spec, w, sub_x, sigma_only, sigma_noise[mask] if sigma_noise is not None else None)
         if out.shape[0] == 0:
-            out = torch.zeros(x.shape[0], r.shape[1], dtype=r.dtype)
+            out = torch.zeros(x.shape[0], r.shape[1], dtype=r.dtype, device=r.device)
         if wts is None:
             out[mask] = r
         else:
@@ -342,7 +351,8 @@ def sample_cdf(bins: torch.Tensor, cdf: torch.Tensor, n_fine: int, det: bool,
     n_rays, n_bins = cdf.shape
     cdf = torch.cat([torch.zeros_like(cdf[:, :1]), cdf], -1)
     if u is None:
-        u = torch.linspace(0, 1, n_fine).expand(n_rays, n_fine) if det else torch.rand(n_rays, n_fine)
+        u = (torch.linspace(0, 1, n_fine, device=cdf.device).expand(n_rays, n_fine) if det
+             else torch.rand(n_rays, n_fine, device=cdf.device))
     u = u.contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
     lo = torch.clamp_min(inds - 1, 0)
@@ -466,7 +476,7 @@ def _query(net: Net, opts: RenderOpts, typ: str, xyz: torch.Tensor, rays_d: torc
         if idx is not None:
             cols.append(idx[a:a + C])
         xin = torch.cat(cols, 1) if len(cols) > 1 else cols[0]
-        noise = torch.rand(len(xin), 1) if net.training else None
+        noise = torch.rand(len(xin), 1, device=xin.device) if net.training else None
         o = net_forward(net, xin, use_coarse=(typ == 'coarse'), sigma_noise=noise)
         if opts.pos_dir_dim == 0 and opts.sh_deg is not None:
             nc = (opts.sh_deg + 1) ** 2
@@ -554,28 +564,29 @@ def render_rays(net: Net, bg_net: Optional[Net], rays: torch.Tensor, image_indic
     if image_indices is not None:
         image_indices = image_indices.unsqueeze(-1).unsqueeze(-1)
     perturb = opts.perturb if net.training else 0
-    last_delta = 1e10 * torch.ones(n, 1)
+    dev = rays.device
+    last_delta = 1e10 * torch.ones(n, 1, device=dev)
     with_bg = None
     if bg_net is not None:
         fg_far = intersect_sphere(o, d, sphere_center, sphere_radius)
         fg_far = torch.maximum(fg_far, near.squeeze())
-        with_bg = torch.arange(n)[far.squeeze() > fg_far]
+        with_bg = torch.arange(n, device=dev)[far.squeeze() > fg_far]
     o = o.view(n, 1, 3)
     d = d.view(n, 1, 3)
     if bg_net is not None and with_bg.shape[0] > 0:
         last_delta[with_bg, 0] = fg_far[with_bg]
         far = torch.minimum(far.squeeze(), fg_far).unsqueeze(-1)
         half = opts.coarse_samples // 2
-        bz = stratify(torch.linspace(0, 1, half), half, perturb, with_bg.shape[0])
+        bz = stratify(torch.linspace(0, 1, half, device=dev), half, perturb, with_bg.shape[0])
         xyz_real = opts.container_path is not None or opts.train_mega_nerf is not None
         c2d = xyz_real and net.cluster_dim_start == 1
         mk = lambda zz: points_outside(o[with_bg], d[with_bg], zz, sphere_center, sphere_radius, xyz_real, c2d)
         bpts, breal = mk(bz)
         bg_res = _two_pass(bg_net, opts, d[with_bg],
                            image_indices[with_bg] if image_indices is not None else None,
-                           bpts, bz, 1e10 * torch.ones(with_bg.shape[0], 1), get_depth, get_depth_variance,
+                           bpts, bz, 1e10 * torch.ones(with_bg.shape[0], 1, device=dev), get_depth, get_depth_variance,
                            False, True, breal, mk)
-    t = torch.linspace(0, 1, opts.coarse_samples)
+    t = torch.linspace(0, 1, opts.coarse_samples, device=dev)
     z = stratify(near * (1 - t) + far * t, opts.coarse_samples, perturb, n)
     xyz = o + d * z.unsqueeze(-1)
     res = _two_pass(net, opts, d, image_indices, xyz, z, last_delta, get_depth, get_depth_variance,
