@@ -312,6 +312,78 @@ def run_train(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_cluster(args, local_rank):
+    """scripts/create_cluster_masks.py:155-201 on its default chunk (ray_chunk_size 48k rays, ray_samples 1000) with the 8
+    centroids of the C2 grid: rays/s of mn_cluster_min_dist_ratios, device-timed, next to the restatement on the host cores
+    (bounded sample).  The kernel reads 32 B/ray and writes (4K + K) B/ray, so HBM is irrelevant (a few GB/s): the work is
+    S x K distance evaluations per ray (sqrt + div each), i.e. it is bound by the fp32 / SFU issue rate; `roofline`
+    reports distance evaluations per second against 148 SMs x 128 lanes x clock / ~12 issue slots per evaluation."""
+    import mega_nerf_b200 as M  # noqa: F401
+    from mega_nerf_b200 import cluster_masks as CM
+    from oracle import mn_oracle as O
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    n, S = 48 * 1024, 1000
+    rays_h = O.synthetic_rays(n, seed=0, far=1.2)
+    cent = O.grid_centroids(2, 4)
+    zs = torch.linspace(0, 1, S)
+    rays_d, cent_d, zs_d = rays_h.to(dev), cent.to(dev), zs.to(dev)
+    rays_pin = rays_h.pin_memory()
+    mask_pin = torch.empty(8, n, dtype=torch.uint8).pin_memory()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        for a, b in evs:
+            flush.fill_(1)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    def resident():
+        CM.min_dist_ratios(rays_d, zs_d, cent_d, True, MARGIN)
+
+    def e2e():
+        _, m = CM.min_dist_ratios(rays_pin.to(dev, non_blocking=True), zs_d, cent_d, True, MARGIN)
+        mask_pin.copy_(m, non_blocking=True)
+
+    for _ in range(args.warmup):
+        resident()
+        e2e()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(resident, args.steps) / args.steps
+    ms_e2e = timed(e2e, args.steps) / args.steps
+    clocks = sampler.stop()
+    torch.set_num_threads(usable_cpus())
+    n_cpu = 2048
+    with torch.inference_mode():
+        t0 = time.perf_counter()
+        O.cluster_min_dist_ratios(rays_h[:n_cpu], zs, cent, True)
+        dt = time.perf_counter() - t0
+    evals = n * S * 8
+    sm_mhz = clocks.get('sm_mhz') or 1965.0
+    peak = 148 * 128 * sm_mhz * 1e6 / 12.0
+    line = {'metric': 'cluster-mask rays/sec (1000 samples x 8 centroids per ray)', 'value': n / (ms * 1e-3), 'unit': 'rays/s',
+            'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'create_cluster_masks.py default chunk: {n} rays x {S} samples, 2x4 centroid grid, cluster_2d, margin {MARGIN}',
+                       'l2': f'flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)'},
+            'e2e': {'value': n / (ms_e2e * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': rays_pin.numel() * 4,
+                    'd2h_bytes_per_step': mask_pin.numel()},
+            'gpu_launches': args.steps, 'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'note': 'HBM traffic is ~2 MB per launch; the kernel is issue-bound (sqrt + div per distance)',
+                         'achieved': (n * 32 + n * 8 * 5) / (ms * 1e-3) / 1e9, 'peak': peaks()['hbm'], 'unit': 'GB/s',
+                         'frac': (n * 32 + n * 8 * 5) / (ms * 1e-3) / 1e9 / peaks()['hbm'], 'traffic': None,
+                         'distance_evals_per_s': evals / (ms * 1e-3), 'issue_bound_estimate_evals_per_s': peak},
+            'cpu_baseline': {'value': n_cpu / dt, 'unit': 'rays/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                             'sample': f'first {n_cpu} rays of the same chunk ({dt:.1f} s)'}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     import faulthandler
     faulthandler.dump_traceback_later(240, repeat=True, file=sys.stderr)
@@ -325,9 +397,10 @@ def main():
     ap.add_argument('--no-gpu-incumbent', action='store_true', help='skip timing the restatement under torch-CUDA eager')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true', help='issue every step eagerly instead of replaying a CUDA graph')
-    ap.add_argument('--mode', default='render', choices=['render', 'train'],
+    ap.add_argument('--mode', default='render', choices=['render', 'train', 'cluster'],
                     help="'render' = the graded line; 'train' = one optimisation step (forward + backward + Adam) of the same "
-                         "workload through the recording path (SURVEY.md §8f-1), diagnostics only")
+                         "workload through the recording path (SURVEY.md §8f-1); 'cluster' = the cluster-mask kernel on one "
+                         "48k-ray chunk x 1000 samples (SURVEY.md §8f-3); both diagnostics only")
     args = ap.parse_args()
     select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -340,6 +413,9 @@ def main():
         return
     if args.mode == 'train':
         run_train(args, rank, local_rank, world)
+        return
+    if args.mode == 'cluster':
+        run_cluster(args, local_rank)
         return
 
     import torch.distributed as dist
