@@ -2,7 +2,7 @@
 activation masks which gradient, which weight sub-matrix each data-gradient step streams, where the sigma
 head joins, the affine-appearance and embedding gathers, the compositing suffix sums) restated step by step
 with plain tensor algebra and checked against the oracle's autograd.  Guards the derivation; the CUDA
-kernels themselves are checked on the GPU by tests/test_gpu_zz_backward.py."""
+kernels themselves are checked on the GPU by tests/test_gpu_zc_backward.py."""
 import pytest
 import torch
 import torch.nn.functional as F

@@ -56,7 +56,7 @@ def product_net(net: O.Net):
     else:
         out = m.MegaNeRF(subs, net.centroids.clone(), net.boundary_margin, net.xyz_real, net.cluster_2d)
     # inference parity: frozen parameters, so that calls outside no_grad are not recorded for backward (the
-    # recording path always runs the fp32 kernels, tests/test_gpu_zz_backward.py)
+    # recording path always runs the fp32 kernels, tests/test_gpu_zc_backward.py)
     return out.to(DEV).eval().requires_grad_(False)
 
 

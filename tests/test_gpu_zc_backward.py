@@ -18,7 +18,8 @@ Tolerances.
          first layer's weight gradient.
    Measured on B200 (first version): worst per-tensor deviation 1.5e-3 (layer-0 weights of g_mega_*), typical 3-9e-4.
    Wiring errors (a wrong mask, sub-matrix, blend weight, sample order) show up as O(1) deviations.
-Named test_gpu_zz_* so that it runs after the forward parity suite.
+Files test_gpu_z{b,c,d,e}_* run after the forward parity suite, most-verified first (the driver uses `pytest -x`);
+inside this file the end-to-end cases come last for the same reason.
 """
 import os
 from argparse import Namespace
@@ -235,6 +236,48 @@ def test_gradients_accumulate_and_repack():
     assert relerr(pn(x.to(DEV)), want_out) <= 1e-5
 
 
+def test_training_step_reduces_loss():
+    """train() mode (stratified jitter, density noise, random resampling), Adam on a fixed batch: the photometric loss
+    falls, every parameter receives a finite gradient and inference afterwards sees the updated weights."""
+    m = M()
+    torch.manual_seed(0)
+    spec = O.NerfSpec(layer_dim=64, appearance_count=10)
+    net = O.make_net('nerf', spec, seed=12)
+    rays = O.synthetic_rays(256, seed=2).to(DEV)
+    idx = O.synthetic_indices(256, 10).to(DEV)
+    target = torch.tensor([0.9, 0.1, 0.5], device=DEV).expand(256, 3)
+    hp = Namespace(**vars(O.RenderOpts(coarse_samples=16, fine_samples=32, perturb=1.0)))
+    pn = trainable(net).train()
+    opt = torch.optim.Adam(pn.parameters(), lr=2e-3)
+    losses = []
+    for it in range(50):
+        res, _ = m.render_rays(pn, None, rays, idx, hp, None, None, False, True, False)
+        loss = torch.nn.functional.mse_loss(res['rgb_fine'], target)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        for k, p in pn.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        opt.step()
+        losses.append(float(loss))
+    assert sum(losses[-5:]) < 0.8 * sum(losses[:5]), losses
+    with torch.no_grad():
+        pn.eval()
+        res, _ = m.render_rays(pn, None, rays, idx, hp, None, None, False, False, False)
+        assert float(torch.nn.functional.mse_loss(res['rgb_fine'], target)) < losses[0]
+
+
+def test_inference_is_not_recorded():
+    m = M()
+    net, _, rays, idx, opts, _, _ = C.render_case('g_single')
+    pn = trainable(net)
+    hp = Namespace(**vars(opts))
+    with torch.no_grad():
+        res, _ = m.render_rays(pn, None, rays.to(DEV), idx.to(DEV), hp, None, None, True, True, False)
+    assert not any(v.requires_grad for v in res.values())
+    with pytest.raises(RuntimeError, match='inference-only'):
+        pn(C.nerf_rows(net.spec, 8, 1, sigma_only=True).to(DEV), sigma_only=True)
+
+
 # ------------------------------------------------------------------------------------------------
 # render_rays end to end, as the training step calls it (runner.py:349-358)
 # ------------------------------------------------------------------------------------------------
@@ -295,45 +338,3 @@ def test_render_rays_backward_c2_shape():
     loss.backward()
     check_param_grads(pn, net, want, 'c2_mega8_blend', E2E_TOL)
     assert global_rel_l2(pn, net, want) <= E2E_L2
-
-
-def test_training_step_reduces_loss():
-    """train() mode (stratified jitter, density noise, random resampling), Adam on a fixed batch: the photometric loss
-    falls, every parameter receives a finite gradient and inference afterwards sees the updated weights."""
-    m = M()
-    torch.manual_seed(0)
-    spec = O.NerfSpec(layer_dim=64, appearance_count=10)
-    net = O.make_net('nerf', spec, seed=12)
-    rays = O.synthetic_rays(256, seed=2).to(DEV)
-    idx = O.synthetic_indices(256, 10).to(DEV)
-    target = torch.tensor([0.9, 0.1, 0.5], device=DEV).expand(256, 3)
-    hp = Namespace(**vars(O.RenderOpts(coarse_samples=16, fine_samples=32, perturb=1.0)))
-    pn = trainable(net).train()
-    opt = torch.optim.Adam(pn.parameters(), lr=2e-3)
-    losses = []
-    for it in range(50):
-        res, _ = m.render_rays(pn, None, rays, idx, hp, None, None, False, True, False)
-        loss = torch.nn.functional.mse_loss(res['rgb_fine'], target)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        for k, p in pn.named_parameters():
-            assert p.grad is not None and torch.isfinite(p.grad).all(), k
-        opt.step()
-        losses.append(float(loss))
-    assert sum(losses[-5:]) < 0.8 * sum(losses[:5]), losses
-    with torch.no_grad():
-        pn.eval()
-        res, _ = m.render_rays(pn, None, rays, idx, hp, None, None, False, False, False)
-        assert float(torch.nn.functional.mse_loss(res['rgb_fine'], target)) < losses[0]
-
-
-def test_inference_is_not_recorded():
-    m = M()
-    net, _, rays, idx, opts, _, _ = C.render_case('g_single')
-    pn = trainable(net)
-    hp = Namespace(**vars(opts))
-    with torch.no_grad():
-        res, _ = m.render_rays(pn, None, rays.to(DEV), idx.to(DEV), hp, None, None, True, True, False)
-    assert not any(v.requires_grad for v in res.values())
-    with pytest.raises(RuntimeError, match='inference-only'):
-        pn(C.nerf_rows(net.spec, 8, 1, sigma_only=True).to(DEV), sigma_only=True)
