@@ -131,7 +131,17 @@ def _query(sg: _Stage, net: nn.Module, hparams: Namespace, typ: str, xyz: torch.
         noise = torch.cat([torch.rand(min(ch, B - a), 1, device=xyz.device) for a in range(0, B, ch)], 0)
     rr = RayRows(xyz, S, dirs if use_dirs else None, idx)
     target = call if call is not None else net
-    if native.needs_grad():
+    ep = getattr(net, '_ep', None)
+    if ep is not None:
+        # owner-computes execution over the process group (mega_nerf_b200/expert_parallel.py): the rows travel, so
+        # they are materialised like the reference does (rendering.py:275-292,311-319)
+        cols = [xyz.reshape(B, Cc)]
+        if use_dirs:
+            cols.append(dirs.unsqueeze(1).expand(n, S, 3).reshape(B, 3))
+        if idx is not None:
+            cols.append(idx.view(n, 1, 1).expand(n, S, 1).reshape(B, 1))
+        out = ep.forward(torch.cat(cols, 1) if len(cols) > 1 else cols[0], noise)
+    elif native.needs_grad():
         # through the wrapper's __call__, like `nerf(x)` in the reference (rendering.py:296-299)
         out = target(typ == 'coarse', rr, sigma_noise=noise) if isinstance(net, Cascade) else target(rr, sigma_noise=noise)
     else:

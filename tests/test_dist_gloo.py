@@ -143,3 +143,78 @@ def test_ddp_hands_rayrows_through_and_reduces_gradients():
     mean = (torch.tensor(out[0][2]) + torch.tensor(out[1][2])) / 2    # d(sum(xyz W^T))/dW[n] = sum_rows xyz, averaged over ranks
     for _, g, _ in out:
         assert torch.allclose(torch.tensor(g), mean.expand(4, 3), atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# owner-computes ("one centroid per GPU") execution of a MegaNeRF: dispatch / return / accumulate
+# ------------------------------------------------------------------------------------------------
+def ep_worker(rank, world, port, mname, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import types
+    import cases as C
+    from oracle import mn_oracle as O
+    from mega_nerf_b200.expert_parallel import ExpertParallel, plan_dispatch, owner_of
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    net = C.mega_net(mname)
+    K_ = len(net.weights)
+    x = C.mega_rows(net, 300 + 37 * rank, 51 + rank)            # every rank routes its own (differently sized) rows
+    calls = []
+
+    def sub_fn(k, rows, noise):
+        assert owner_of(k, world) == rank, (k, rank)             # only owned sub-modules are ever evaluated here
+        calls.append((k, rows.shape[0]))
+        return O.nerf_forward(net.spec, net.weights[k], rows, sigma_noise=noise)
+
+    mega = types.SimpleNamespace(sub_modules=[types.SimpleNamespace(rgb_dim=net.spec.rgb_dim)] * K_, xyz_real=net.xyz_real,
+                                 parameters=lambda: iter(()))
+    ep = ExpertParallel(mega, None, route_fn=lambda xx: O.route(net, xx), sub_fn=sub_fn)
+    g = torch.Generator().manual_seed(5 + rank)
+    noise = torch.rand(x.shape[0], 1, generator=g)
+    with torch.inference_mode():
+        got = ep.forward(x)
+        got_n = ep.forward(x, noise)
+        want = O.mega_forward(net, x)
+        want_n = O.mega_forward(net, x, sigma_noise=noise)
+    err = float((got - want).abs().max() / want.abs().max())
+    err_n = float((got_n - want_n).abs().max() / want_n.abs().max())
+    total = torch.tensor([ep.last_pairs, ep.last_owned])
+    dist.all_reduce(total)
+    q.put((rank, err, err_n, sorted(set(k for k, _ in calls)), int(total[0]), int(total[1])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_ep(mname):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = free_port()
+    ps = [ctx.Process(target=ep_worker, args=(r, 2, port, mname, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted([q.get(timeout=180) for _ in ps])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return out
+
+
+def test_expert_parallel_matches_single_device_mixture():
+    for mname in ('hard2d', 'blend2d', 'hard3d_bgreal', 'blend25'):
+        out = run_ep(mname)
+        for rank, err, err_n, ks, sent, owned in out:
+            assert err <= 1e-6 and err_n <= 1e-6, (mname, rank, err, err_n)
+            assert all(k % 2 == rank for k in ks), (mname, rank, ks)
+            assert sent == owned                                   # every dispatched pair was computed exactly once
+
+
+def test_plan_dispatch_order_and_counts():
+    from mega_nerf_b200.expert_parallel import plan_dispatch
+    w = torch.tensor([[0.5, 0.0, 0.5, 0.0], [0.0, 1.0, 0.0, 0.0], [0.2, 0.3, 0.0, 0.5]])
+    rows, subs, ww, counts = plan_dispatch(None, w, 4, 2)
+    assert subs.tolist() == [0, 0, 2, 1, 1, 3] and rows.tolist() == [0, 2, 0, 1, 2, 2] and counts.tolist() == [3, 3]
+    assert torch.allclose(ww, torch.tensor([0.5, 0.2, 0.5, 1.0, 0.3, 0.5]))
+    rows, subs, ww, counts = plan_dispatch(torch.tensor([3, 0, 1, 1]), None, 4, 3)
+    assert subs.tolist() == [0, 3, 1, 1] and rows.tolist() == [1, 0, 2, 3] and ww is None and counts.tolist() == [2, 2, 0]
