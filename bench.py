@@ -397,6 +397,9 @@ def main():
     ap.add_argument('--no-gpu-incumbent', action='store_true', help='skip timing the restatement under torch-CUDA eager')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true', help='issue every step eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--parallelism', default='rays', choices=['rays', 'experts'],
+                    help="N > 1: 'rays' = ray-sharded with replicated weights (default, graded); 'experts' = additionally "
+                         "owner-computes sub-modules (sub-module k on rank k mod N, two all-to-alls per model query; eager launches)")
     ap.add_argument('--mode', default='render', choices=['render', 'train', 'cluster'],
                     help="'render' = the graded line; 'train' = one optimisation step (forward + backward + Adam) of the same "
                          "workload through the recording path (SURVEY.md §8f-1); 'cluster' = the cluster-mask kernel on one "
@@ -434,6 +437,11 @@ def main():
     hp = Namespace(**vars(opts))
     model = product_net(net).to(dev).eval()
     M.set_precision(args.precision)
+    experts = args.parallelism == 'experts' and world > 1
+    if experts:
+        from mega_nerf_b200 import expert_parallel as EP
+        EP.enable(model)
+        args.no_graph = True                      # host-sized all-to-alls are not graph-capturable
     rays_d, idx_d = rays_h.to(dev), idx_h.to(dev)
     rays_pin, idx_pin = rays_h.pin_memory(), idx_h.pin_memory()
     out_pin = torch.empty(N_RAYS, 4).pin_memory()
@@ -533,7 +541,7 @@ def main():
     K.check(L.mn_profile_read(h, C.byref(tot_ms), C.byref(n_l)), h)
     K.check(L.mn_profile_enable(h, 0), h)
     clocks = sampler.stop() if rank == 0 else None      # sampled over the resident, e2e and kernel-timing sections
-    slots, tiles = nat.stats(dev)                # of the last (fine) pass
+    slots, tiles = (model._ep.last_pairs, 0) if experts else nat.stats(dev)                # of the last (fine) pass
     rows_fine = N_RAYS * FINE
     mult = slots / rows_fine
     pk = peaks()
@@ -575,7 +583,9 @@ def main():
             'data': 'synthetic',
             'config': {'workload': f'{WL["desc"]}, {N_RAYS} rays x ({COARSE} coarse + {FINE} fine) '
                                    f'per GPU, boundary_margin {MARGIN} (m = {mult:.3f} sub-modules/sample), random-init weights',
-                       'parallelism': f'ray-sharded x{world}, weights replicated, 1 all-gather of [rays,4] per step' if world > 1 else 'single GPU',
+                       'parallelism': (f'ray-sharded x{world} + owner-computes sub-modules (k mod {world}), 2 all-to-alls per query, '
+                                       f'1 all-gather of [rays,4] per step' if experts else
+                                       f'ray-sharded x{world}, weights replicated, 1 all-gather of [rays,4] per step') if world > 1 else 'single GPU',
                        'precision': args.precision,
                        'launch': 'one CUDA graph replay per step (mega_nerf_b200.GraphedRenderRays)' if graphed is not None else 'eager launches',
                        'l2': f'flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)',
