@@ -553,6 +553,8 @@ def main():
     passes = {'fp32': 1, 'tc_f16': 1, 'tc_f16x3': 3}[args.precision]
 
     log(f'mlp kernel: {kernel_ms_per_step:.3f} ms/step, m={mult:.3f}')
+    if experts:
+        EP.disable(model)          # the parity sample below runs on rank 0 alone: no collectives allowed there
     if rank == 0:
         # parity sample against the oracle (not timed): 256 rays
         torch.set_num_threads(usable_cpus())
