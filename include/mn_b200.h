@@ -201,6 +201,23 @@ int mn_model_route(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int
  * slots = routed (row, sub-module) pairs, tiles = 128-row MLP tiles. */
 int mn_model_last_stats(mn_ctx* ctx, mn_model* m, int64_t* slots, int64_t* tiles, void* stream);
 
+/* ---- the whole foreground path in one call ------------------------------ mega_nerf/rendering.py:15-248 ----
+ * render_rays(nerf, bg_nerf=None, ...) in eval mode (no jitter, no density noise): coarse depths -> query -> weights ->
+ * inverse-CDF resampling -> fine query -> merge + volume rendering, sequenced on `stream` from the caller's workspace
+ * (mn_render_rays_workspace_bytes) with no allocation and no host sync.  Same results as the stage entry points called
+ * one by one (that is what it does).
+ *   rays_d [N,8]; image_indices_d [N] fp32 (required iff the model has an appearance embedding);
+ *   z_steps_d [coarse_samples] and u_fine_d [fine_samples] = torch.linspace(0,1,.) passed in;
+ *   use_cascade must match the model kind (Cascade <-> 1); sh_deg = -1 for a plain rgb head;
+ *   outputs: rgb_out_d [N,3] = rgb_fine (rgb_coarse when fine_samples == 0); depth_out_d / depth_var_out_d optional [N];
+ *   rgb_coarse_out_d optional [N,3], written under use_cascade with fine_samples > 0 (rendering.py:199). */
+size_t mn_render_rays_workspace_bytes(const mn_model* m, int64_t N, int coarse_samples, int fine_samples, int use_cascade,
+                                      int sh_deg, int precision);
+int mn_render_rays(mn_ctx* ctx, mn_model* m, const float* rays_d, const float* image_indices_d, int64_t N,
+                   const float* z_steps_d, int coarse_samples, const float* u_fine_d, int fine_samples, int use_cascade,
+                   int sh_deg, int precision, float* rgb_out_d, float* depth_out_d, float* depth_var_out_d,
+                   float* rgb_coarse_out_d, void* workspace_d, size_t workspace_bytes, void* stream);
+
 /* ---- cluster masks ------------------------------------------- scripts/create_cluster_masks.py ----
  * The per-image hot loop of create_cluster_masks.py:155-201: for every ray, the minimum over
  * its S samples (z = near(1-t) + far t, t = z_steps_d [S] = torch.linspace(0,1,S) passed in) of

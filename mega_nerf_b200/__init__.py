@@ -5,7 +5,7 @@ of libmn_b200.so (hand-written sm_100a CUDA behind the C ABI in include/mn_b200.
 """
 from .modules import (Embedding, ShiftedSoftplus, NeRF, MegaNeRF, Cascade, get_nerf, get_bg_nerf,  # noqa: F401
                       set_precision, get_precision)
-from .render import render_rays  # noqa: F401
+from .render import render_rays, render_rays_fused  # noqa: F401
 from .graph import GraphedRenderRays  # noqa: F401
 from .raygen import get_ray_directions, get_rays, get_rays_batch  # noqa: F401
 from .sh import eval_sh  # noqa: F401

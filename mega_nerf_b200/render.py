@@ -348,3 +348,48 @@ def _render(net, bg, rays, image_indices, hparams, sphere_center, sphere_radius,
         res[key] = res[key] + 0 * touch
         present = True
     return res, present
+
+
+def render_rays_fused(nerf: nn.Module, rays: torch.Tensor, image_indices: Optional[torch.Tensor], hparams: Namespace,
+                      get_depth: bool, get_depth_variance: bool) -> Dict[str, torch.Tensor]:
+    """The foreground inference path of `render_rays(nerf, None, ...)` as ONE library call (`mn_render_rays`): the same
+    kernels in the same order, sequenced in C on the current stream instead of from Python.  Eval mode, no background
+    network; returns the same keys and values as `render_rays(...)[0]` for that case."""
+    net = _unwrap(nerf)
+    if not isinstance(net, (NeRF, MegaNeRF, Cascade)):
+        raise TypeError('mega_nerf_b200.render_rays_fused needs mega_nerf_b200 modules (use get_nerf / install())')
+    if net.training:
+        raise ValueError('render_rays_fused is the inference path; call nerf.eval() first')
+    if bool(hparams.use_cascade) != isinstance(net, Cascade):
+        raise ValueError('hparams.use_cascade does not match the network')
+    from .modules import get_precision
+    dev = rays.device
+    L, h = K.lib(), K.ctx(dev)
+    native = net._native()
+    native.sync(dev)
+    rays = K.f32c(rays)
+    N = rays.shape[0]
+    idx = K.f32c(image_indices.to(dev)).view(-1) if image_indices is not None else None
+    Sc, Sf = hparams.coarse_samples, hparams.fine_samples
+    sh_deg = hparams.sh_deg if (hparams.pos_dir_dim == 0 and hparams.sh_deg is not None) else -1
+    prec = K.PRECISIONS[get_precision()]
+    steps = torch.linspace(0, 1, Sc, device=dev)
+    u = torch.linspace(0, 1, Sf, device=dev) if Sf > 0 else None
+    typ = 'fine' if Sf > 0 else 'coarse'
+    rgb = torch.empty(N, 3, device=dev, dtype=torch.float32)
+    depth = torch.empty(N, device=dev, dtype=torch.float32) if get_depth else None
+    var = torch.empty(N, device=dev, dtype=torch.float32) if get_depth_variance else None
+    rgb_c = torch.empty(N, 3, device=dev, dtype=torch.float32) if (hparams.use_cascade and Sf > 0) else None
+    nbytes = int(L.mn_render_rays_workspace_bytes(native.handle, N, Sc, Sf, int(hparams.use_cascade), sh_deg, prec))
+    ws = torch.empty(max(nbytes, 256), device=dev, dtype=torch.uint8)
+    K.check(L.mn_render_rays(h, native.handle, K.ptr(rays), K.ptr(idx), N, K.ptr(steps), Sc, K.ptr(u), Sf, int(hparams.use_cascade),
+                             sh_deg, prec, K.ptr(rgb), K.ptr(depth), K.ptr(var), K.ptr(rgb_c), K.ptr(ws), ws.numel(),
+                             K.stream_of(dev)), h)
+    res = {f'rgb_{typ}': rgb}
+    if depth is not None:
+        res[f'depth_{typ}'] = depth
+    if var is not None:
+        res[f'depth_variance_{typ}'] = var
+    if rgb_c is not None:
+        res['rgb_coarse'] = rgb_c
+    return res
