@@ -400,6 +400,9 @@ def main():
     ap.add_argument('--parallelism', default='rays', choices=['rays', 'experts'],
                     help="N > 1: 'rays' = ray-sharded with replicated weights (default, graded); 'experts' = additionally "
                          "owner-computes sub-modules (sub-module k on rank k mod N, two all-to-alls per model query; eager launches)")
+    ap.add_argument('--gather', default='nccl', choices=['nccl', 'peer'],
+                    help="N > 1: how the per-ray results are exchanged: 'nccl' = torch.cat + all_gather_into_tensor (default, graded); "
+                         "'peer' = one kernel of ours storing into every rank's symmetric buffer over NVLink (mega_nerf_b200.dist.PeerGather)")
     ap.add_argument('--mode', default='render', choices=['render', 'train', 'cluster'],
                     help="'render' = the graded line; 'train' = one optimisation step (forward + backward + Adam) of the same "
                          "workload through the recording path (SURVEY.md §8f-1); 'cluster' = the cluster-mask kernel on one "
@@ -447,6 +450,19 @@ def main():
     out_pin = torch.empty(N_RAYS, 4).pin_memory()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     gather_buf = torch.empty(world * N_RAYS, 4, device=dev) if world > 1 else None
+    pg = None
+    if world > 1 and args.gather == 'peer':
+        from mega_nerf_b200.dist import PeerGather
+        pg = PeerGather(world * N_RAYS, dev)
+
+    def exchange(res):
+        """every rank ends up with all ranks' (rgb, depth) rows"""
+        if world == 1:
+            return
+        if pg is not None:
+            pg.gather(res['rgb_fine'], res['depth_fine'], rank * N_RAYS)
+        else:
+            dist.all_gather_into_tensor(gather_buf, torch.cat([res['rgb_fine'], res['depth_fine'].unsqueeze(-1)], -1))
     h = K.ctx(dev)
     L = K.lib()
 
@@ -454,16 +470,14 @@ def main():
 
     def step_eager():
         res, _ = M.render_rays(model, None, rays_d, idx_d, hp, None, None, True, False, False)
-        if world > 1:
-            dist.all_gather_into_tensor(gather_buf, torch.cat([res['rgb_fine'], res['depth_fine'].unsqueeze(-1)], -1))
+        exchange(res)
         return res
 
     def step_resident():
         if graphed is None:
             return step_eager()
         res = graphed(rays_d, idx_d)                 # device-resident inputs -> static buffers (D2D) -> graph replay
-        if world > 1:
-            dist.all_gather_into_tensor(gather_buf, torch.cat([res['rgb_fine'], res['depth_fine'].unsqueeze(-1)], -1))
+        exchange(res)
         return res
 
     def step_e2e():
@@ -475,7 +489,10 @@ def main():
             res = graphed(rays_pin, idx_pin)         # pinned host inputs -> static device buffers (H2D) -> graph replay
         packed = torch.cat([res['rgb_fine'], res['depth_fine'].unsqueeze(-1)], -1)
         if world > 1:
-            dist.all_gather_into_tensor(gather_buf, packed)
+            if pg is not None:
+                pg.gather(res['rgb_fine'], res['depth_fine'], rank * N_RAYS)
+            else:
+                dist.all_gather_into_tensor(gather_buf, packed)
         out_pin.copy_(packed, non_blocking=True)
 
     def timed(fn, steps):
@@ -587,7 +604,8 @@ def main():
                                    f'per GPU, boundary_margin {MARGIN} (m = {mult:.3f} sub-modules/sample), random-init weights',
                        'parallelism': (f'ray-sharded x{world} + owner-computes sub-modules (k mod {world}), 2 all-to-alls per query, '
                                        f'1 all-gather of [rays,4] per step' if experts else
-                                       f'ray-sharded x{world}, weights replicated, 1 all-gather of [rays,4] per step') if world > 1 else 'single GPU',
+                                       f'ray-sharded x{world}, weights replicated, 1 all-gather of [rays,4] per step'
+                                       + (' as peer-memory stores (PeerGather)' if pg is not None else '')) if world > 1 else 'single GPU',
                        'precision': args.precision,
                        'launch': 'one CUDA graph replay per step (mega_nerf_b200.GraphedRenderRays)' if graphed is not None else 'eager launches',
                        'l2': f'flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)',

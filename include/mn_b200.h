@@ -218,6 +218,13 @@ int mn_render_rays(mn_ctx* ctx, mn_model* m, const float* rays_d, const float* i
                    int sh_deg, int precision, float* rgb_out_d, float* depth_out_d, float* depth_var_out_d,
                    float* rgb_coarse_out_d, void* workspace_d, size_t workspace_bytes, void* stream);
 
+/* Fused per-ray all-gather over peer memory: stores this rank's (rgb, depth) rows [row0, row0+n) into
+ * every buffer of peer_bufs[0..n_peers) - HOST array of device pointers to [n_total, 4] fp32 buffers, one per rank,
+ * peer-mapped into this process (e.g. torch symmetric memory) - with 16-byte P2P stores.  Cross-rank ordering (nobody
+ * still reads the previous contents; everybody's stores have landed) is the caller's: a barrier before and after. */
+int mn_peer_gather_store(mn_ctx* ctx, const float* rgb_d, const float* depth_d, int64_t n, int64_t row0,
+                         const void* const* peer_bufs, int n_peers, void* stream);
+
 /* ---- cluster masks ------------------------------------------- scripts/create_cluster_masks.py ----
  * The per-image hot loop of create_cluster_masks.py:155-201: for every ray, the minimum over
  * its S samples (z = near(1-t) + far t, t = z_steps_d [S] = torch.linspace(0,1,S) passed in) of

@@ -78,6 +78,7 @@ SIGNATURES = {
     'mn_model_last_stats': (_I, [_P, _P, C.POINTER(_L), C.POINTER(_L), _P]),
     'mn_render_rays_workspace_bytes': (_Z, [_P, _L, _I, _I, _I, _I, _I]),
     'mn_render_rays': (_I, [_P, _P, _P, _P, _L, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    'mn_peer_gather_store': (_I, [_P, _P, _P, _L, _L, C.POINTER(C.c_void_p), _I, _P]),
     'mn_cluster_min_dist_ratios': (_I, [_P, _P, _L, _P, _I, _P, _I, _I, _F, _P, _P, _P]),
     # training
     'mn_composite_backward': (_I, [_P, _P, _P, _I, _P, _P, _I, _P, _L, _I, _P, _P, _P, _P, _P]),

@@ -130,3 +130,36 @@ int mn_render_rays(mn_ctx* ctx, mn_model* m, const float* rays_d, const float* i
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Fused per-ray all-gather ("fused form"): every rank stores its rays' (rgb, depth) rows straight into
+// EVERY rank's result buffer through peer-mapped pointers (NVLink / NVSwitch P2P stores), instead of packing them and
+// calling a collective.  The buffers are symmetric allocations exchanged by the host (torch symmetric memory in the
+// Python mirror); ordering between ranks is the caller's barrier pair (see mega_nerf_b200/dist.py::PeerGather).
+// ------------------------------------------------------------------------------------------------
+#define MN_MAX_PEERS 16
+struct PeerBufs {
+    float* p[MN_MAX_PEERS];
+};
+
+__global__ void peer_gather_store_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int64_t n, int64_t row0,
+                                         PeerBufs bufs, int G) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = make_float4(rgb[i * 3 + 0], rgb[i * 3 + 1], rgb[i * 3 + 2], depth ? depth[i] : 0.0f);
+    for (int g = 0; g < G; ++g) reinterpret_cast<float4*>(bufs.p[g])[row0 + i] = v;   // 16-byte store per peer
+}
+
+extern "C" int mn_peer_gather_store(mn_ctx* ctx, const float* rgb_d, const float* depth_d, int64_t n, int64_t row0,
+                                    const void* const* peer_bufs, int n_peers, void* stream) {
+    if (!ctx || !rgb_d || !peer_bufs || n < 0 || row0 < 0 || n_peers < 1 || n_peers > MN_MAX_PEERS) return MN_ERR_INVALID;
+    if (n == 0) return MN_OK;
+    PeerBufs b{};
+    for (int g = 0; g < n_peers; ++g) {
+        if (!peer_bufs[g]) return mn_fail(ctx, MN_ERR_INVALID, "mn_peer_gather_store: null peer buffer");
+        b.p[g] = (float*)peer_bufs[g];
+    }
+    peer_gather_store_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(rgb_d, depth_d, n, row0, b, n_peers);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}

@@ -62,3 +62,35 @@ def render_rays_sharded(render_fn: Callable[..., Tuple[Dict[str, torch.Tensor], 
         out[k] = v.squeeze(1) if res[k].dim() == 1 else v
         c += w
     return out, bool(full[:, c].max().item() > 0) if full.shape[0] else present
+
+
+class PeerGather:
+    """Fused form of the per-chunk all-gather: a symmetric [n_total, 4] result buffer per rank, peer-mapped
+    into every process (torch symmetric memory does the allocation / handle exchange / barriers - plumbing), and ONE kernel
+    of ours (`mn_peer_gather_store`) that writes this rank's (rgb, depth) rows into all of them over NVLink.  Replaces
+    `torch.cat` + `all_gather_into_tensor`; the result is valid on every rank when `gather` returns (stream-ordered)."""
+
+    def __init__(self, n_total: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.buf = symm_mem.empty(n_total, 4, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.world = self.hdl.world_size
+        self.rank = self.hdl.rank
+        import ctypes as C
+        self._ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        self.n_total = n_total
+
+    def gather(self, rgb: torch.Tensor, depth: Optional[torch.Tensor], row0: int) -> torch.Tensor:
+        from . import _cabi as K
+        dev = rgb.device
+        h = K.ctx(dev)
+        n = rgb.shape[0]
+        if row0 < 0 or row0 + n > self.n_total:
+            raise ValueError('rows outside the gather buffer')
+        rgb = K.f32c(rgb)
+        depth = K.f32c(depth) if depth is not None else None
+        self.hdl.barrier(channel=0)            # every rank has finished reading the previous contents
+        K.check(K.lib().mn_peer_gather_store(h, K.ptr(rgb), K.ptr(depth), n, row0, self._ptrs, self.world, K.stream_of(dev)), h)
+        self.hdl.barrier(channel=1)            # every rank's stores have landed
+        return self.buf

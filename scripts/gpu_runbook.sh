@@ -24,6 +24,7 @@ case "${1:-help}" in
     $G --timeout 900 -- 'ncu --set full --import-source on --clock-control none -k regex:mlp_bwd -s 4 -c 2 -o gpurun_out/mlp_bwd_kernels python bench.py --mode train --steps 1 --warmup 3 > gpurun_out/n3.log 2>&1; ls -la gpurun_out/*.ncu-rep' ;;
   scale2)       # 2-GPU lines: ray-sharded (graded form) and owner-computes sub-modules
     $G --gpus 2 --timeout 900 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -1 gpurun_out/bench_n2.json;
-                         python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --parallelism experts --no-cpu-baseline > gpurun_out/bench_n2_experts.json 2> gpurun_out/bench_n2_experts.err; tail -1 gpurun_out/bench_n2_experts.json' ;;
+                         python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --parallelism experts --no-cpu-baseline > gpurun_out/bench_n2_experts.json 2> gpurun_out/bench_n2_experts.err; tail -1 gpurun_out/bench_n2_experts.json;
+                         python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --gather peer --no-cpu-baseline > gpurun_out/bench_n2_peer.json 2> gpurun_out/bench_n2_peer.err; tail -1 gpurun_out/bench_n2_peer.json' ;;
   *) sed -n 2,6p "$0"; grep -E '^  [a-z0-9-]+\)' "$0" ;;
 esac
