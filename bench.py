@@ -625,6 +625,14 @@ def main():
                          'traffic_detail': {'algorithmic_bytes_per_launch': 4980 * (40960 + 2048),
                                             'launch': 'fine pass, 4980 tiles x 128 rows',
                                             'source': 'ncu --set full, profiles/'} if args.workload == 'c2' else None,
+                         # second roofline of the same kernel: every 128-row tile re-reads its sub-module's fp16
+                         # weight images (2 B per parameter = fl_row bytes) plus its 40 KiB feature tile from L2; both MLP
+                         # kernels top out near 8 TB/s of L2 -> SM delivery (~32 B/clk/SM), which caps `frac` at ~0.54
+                         'l2_to_sm': {'bytes_per_step': flops_step / fl_row / 128.0 * (fl_row + 40960.0),
+                                      'achieved_TBps': (flops_step / fl_row / 128.0 * (fl_row + 40960.0)) / (kernel_ms_per_step * 1e-3) / 1e12
+                                      if kernel_ms_per_step > 0 else None,
+                                      'observed_ceiling_TBps': 8.07, 'source': 'l1tex__m_xbar2l1tex_read_bytes, profiles/r1_tc_mlp_pp_kernel.ncu-rep'}
+                         if args.precision == 'tc_f16' else None,
                          'algorithmic_flops_per_row': fl_row, 'mma_passes_per_algorithmic': passes,
                          'kernel_ms_per_step': kernel_ms_per_step, 'launches_per_step': n_l.value / args.steps},
             'parity': {'max_rel_rgb_vs_oracle_256_rays': par},
