@@ -627,7 +627,7 @@ def main():
                                             'source': 'ncu --set full, profiles/'} if args.workload == 'c2' else None,
                          # second roofline of the same kernel: every 128-row tile re-reads its sub-module's fp16
                          # weight images (2 B per parameter = fl_row bytes) plus its 40 KiB feature tile from L2; both MLP
-                         # kernels top out near 8 TB/s of L2 -> SM delivery (~32 B/clk/SM), which caps `frac` at ~0.54
+                         # kernels top out near 8 TB/s of L2 -> SM delivery (~32 B/clk/SM), which caps `frac` at ~0.59 (1006 TFLOP/s at 1.68 GHz)
                          'l2_to_sm': {'bytes_per_step': flops_step / fl_row / 128.0 * (fl_row + 40960.0),
                                       'achieved_TBps': (flops_step / fl_row / 128.0 * (fl_row + 40960.0)) / (kernel_ms_per_step * 1e-3) / 1e12
                                       if kernel_ms_per_step > 0 else None,
