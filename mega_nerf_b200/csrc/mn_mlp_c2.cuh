@@ -14,6 +14,8 @@
 //                      CTAs' tensor-map TMA copies (.cta_group::2) complete_tx on it (shared::cluster address from mapa);
 //   empty[s], acc_full[slot]   tcgen05.commit ... multicast::cluster to both CTAs;
 //   epi_done[slot]     leader's barrier, 32 arrivals (16 epilogue warps per CTA, the peer's arrive remotely).
+//                      With A.c2_relay (MN_TC_C2=2) the peer's warps arrive on its own epi_local[slot] instead and the
+//                      peer's otherwise idle MMA warp forwards one remote arrive: 16 local + 1 remote arrivals.
 #pragma once
 
 
@@ -154,6 +156,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     uint64_t* f32_full = bars + 20;   //       per CTA
     uint64_t* f32_empty = bars + 21;  //       per CTA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    uint64_t* epi_local = bars + 24;  // [2]   per CTA, relay mode only
+    const bool relay = A.c2_relay != 0;
 
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -171,7 +175,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         for (int i = 0; i < kC2MaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&epi_done[i], 2 * kEpiWarps);
+            mbar_init(&epi_done[i], relay ? kEpiWarps + 1 : 2 * kEpiWarps);
+            mbar_init(&epi_local[i], kEpiWarps);
         }
         mbar_init(f32_full, 1);
         mbar_init(f32_empty, kEpiWarps);
@@ -299,6 +304,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     }
                 }
             }
+        } else if (relay && lane == 0) {
+            // peer CTA, relay mode: one remote arrive per (GEMM, slot) once all 16 local epilogue warps are done.
+            // (their release.cta arrives -> this acquire -> the release.cluster arrive below: the activation writes are
+            // ordered before the leader's acquire.cluster wait; they were already fenced to the async proxy by their writers)
+            uint32_t lph0 = 0, lph1 = 0;
+            const uint32_t epi_done_l = mapa_u32(smem_u32(epi_done), 0);
+            for (int64_t q = cl; q < n_quads; q += ncl)
+                for (int gi = 0; gi < n_gemm; ++gi)
+                    for (int sl = 0; sl < 2; ++sl) {
+                        if (sl == 0) { mbar_wait(&epi_local[0], lph0); lph0 ^= 1; }
+                        else         { mbar_wait(&epi_local[1], lph1); lph1 ^= 1; }
+                        mbar_arrive_cluster(epi_done_l + 8u * (uint32_t)sl);
+                    }
         }
     } else {
         // =========================== epilogue (16 warps per CTA, own 128 TMEM lanes) ===========================
@@ -384,7 +402,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     tc_fence_before();
                     __syncwarp();
                     if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 4, sl, gi);
-                    if (lane == 0) mbar_arrive_cluster(epi_done_l + 8u * (uint32_t)sl);
+                    if (lane == 0) {
+                        if (relay && !leader) mbar_arrive(&epi_local[sl]);
+                        else mbar_arrive_cluster(epi_done_l + 8u * (uint32_t)sl);
+                    }
                 }
             }
         }

@@ -679,6 +679,8 @@ struct TcArgs {
     int nofetch;                  // debug (MN_TC_NOFETCH=1): producers skip the TMA copies (garbage results; isolates the
                                   // MMA + epilogue pipeline from the weight stream when timing)
     int64_t n_tiles_cap;
+    int c2_relay;                 // CTA-pair kernel (MN_TC_C2=2): the peer's epilogue warps arrive on a LOCAL barrier and its idle MMA
+                                  // warp forwards ONE remote arrive per GEMM and slot to the leader (instead of 16 remote arrives)
 };
 
 struct SmemLayout {
@@ -1513,8 +1515,9 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         static int use_c2 = -1;
         if (use_c2 < 0) {
             const char* e = getenv("MN_TC_C2");
-            use_c2 = (e && e[0] == '1') ? 1 : 0;
+            use_c2 = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
         }
+        A.c2_relay = use_c2 == 2 ? 1 : 0;
         const PPLayout PL = pp_layout(P, bias_global != 0);
         const TsLayout TL = ts_layout(P);
         const C2Layout CL = c2_layout(P);
