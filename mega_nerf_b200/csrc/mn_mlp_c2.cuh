@@ -32,7 +32,7 @@ struct C2Layout {
 __host__ __device__ inline C2Layout c2_layout(const TcPlan& p) {
     C2Layout s;
     s.f32_stride = ((p.f32_floats * 4 + 15) / 16) * 16;
-    const int fixed = 2 * p.L * kTileM * 2 + s.f32_stride + 2048 + 256;
+    const int fixed = 2 * p.L * kTileM * 2 + s.f32_stride + 2048 + 512;
     int st = (kSmemMax - fixed) / kC2StageBytes;
     if (st > kC2MaxStages) st = kC2MaxStages;
     s.stages = st;
@@ -41,7 +41,7 @@ __host__ __device__ inline C2Layout c2_layout(const TcPlan& p) {
     s.f32 = s.h + 2 * p.L * kTileM * 2;
     s.sigp = s.f32 + s.f32_stride;
     s.bars = s.sigp + 2048;
-    s.total = s.bars + 256;
+    s.total = s.bars + 512;
     return s;
 }
 
@@ -124,6 +124,37 @@ __device__ __forceinline__ void tma2d_c2(uint32_t dst_smem, const CUtensorMap* t
         : "memory");
 }
 
+// First half of epi_piece16 for the trailing variant: TMEM -> +bias -> (ReLU) -> fp16 pairs kept in 8 registers (the
+// stores happen later, slab by slab); returns the partial sigma dot product if kSigma.  Same arithmetic as epi_piece16.
+template <bool kRelu, bool kSigma>
+__device__ __forceinline__ float c2_convert16(uint32_t taddr, const float* __restrict__ bias16, const float* __restrict__ sw16,
+                                              uint32_t* hpk) {
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+    const float4* b4 = reinterpret_cast<const float4*>(bias16);
+    const float4 b0 = b4[0], b1 = b4[1], b2 = b4[2], b3 = b4[3];
+    const float b[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+    tmem_ld_wait();
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + b[i];
+    if (kRelu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+    }
+    float sacc = 0.0f;
+    if (kSigma) {
+        const float4* s4 = reinterpret_cast<const float4*>(sw16);
+        const float4 s0 = s4[0], s1 = s4[1], s2 = s4[2], s3 = s4[3];
+        const float sw[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sacc = fmaf(f[i], sw[i], sacc);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hpk[e] = pack_h2(f[2 * e], f[2 * e + 1]);
+    return sacc;
+}
+
 struct C2Maps {
     CUtensorMap w64, w32, w8;   // packed weights viewed as rows of 256 B: boxes of 64 / 32 / 8 rows
     CUtensorMap x32, x16;       // feature tile images, same view: boxes of 32 / 16 rows (= K-columns)
@@ -138,6 +169,12 @@ __device__ __forceinline__ void c2_copy_rows(uint32_t dst, int row0, int rows, u
     while (mc && rows >= rc) { tma2d_c2(dst, mc, row0, bar); dst += (uint32_t)rc * 256u; row0 += rc; rows -= rc; }
 }
 
+// kTrail (MN_TC_C2=3): every epilogue warp first loads ALL its accumulator columns into registers, then converts and
+// stores them slab by slab (64 columns), announcing each slab on h_ready[slot][slab]; the leader starts the slot's next
+// GEMM as soon as slab 0 is announced by everybody (=> the whole accumulator has been read and may be overwritten) and
+// issues the K-steps of slab j right after slab j - the chain MMA -> epilogue -> MMA of a slot shrinks from the full
+// drain to one TMEM load + one slab.  Always uses the relay (one remote arrive per slab from the peer CTA).
+template <bool kTrail>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     tc_mlp_c2_kernel(const TcArgs A, const __grid_constant__ C2Maps TM) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -157,7 +194,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     uint64_t* f32_empty = bars + 21;  //       per CTA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
     uint64_t* epi_local = bars + 24;  // [2]   per CTA, relay mode only
-    const bool relay = A.c2_relay != 0;
+    uint64_t* h_ready = bars + 32;    // [2][4] leader's (kTrail): 16 local arrivals + 1 relayed from the peer
+    uint64_t* h_local = bars + 40;    // [2][4] per CTA  (kTrail): the peer's 16 epilogue warps
+    const bool relay = kTrail || A.c2_relay != 0;
 
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -178,6 +217,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             mbar_init(&epi_done[i], relay ? kEpiWarps + 1 : 2 * kEpiWarps);
             mbar_init(&epi_local[i], kEpiWarps);
         }
+        for (int i = 0; i < 8; ++i) { mbar_init(&h_ready[i], kEpiWarps + 1); mbar_init(&h_local[i], kEpiWarps); }
         mbar_init(f32_full, 1);
         mbar_init(f32_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -275,9 +315,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     const uint64_t b_step = (uint64_t)((2 * nhalf * 16) >> 4);
                     const uint64_t bd0 = make_desc(ring_base, (uint32_t)nhalf * 16, 128);
                     for (int sl = 0; sl < 2; ++sl) {
-                        // both CTAs have drained this slot's accumulator and written its activations
-                        if (sl == 0) { if (started0) { mbar_wait_cluster(epi_done_a, eph0); eph0 ^= 1; } started0 = true; }
-                        else         { if (started1) { mbar_wait_cluster(epi_done_a + 8, eph1); eph1 ^= 1; } started1 = true; }
+                        const bool prev = sl == 0 ? started0 : started1;       // this slot has an epilogue in flight
+                        const uint32_t hpar = sl == 0 ? eph0 : eph1;
+                        const uint32_t hbar = smem_u32(h_ready) + 32u * (uint32_t)sl;
+                        int waited = 0;                                         // kTrail: slab barriers of that epilogue already seen
+                        if (kTrail) {
+                            // slab 0 announced by all 32 warps => every accumulator column has been loaded: it may be overwritten
+                            if (prev) { mbar_wait_cluster(hbar, hpar); waited = 1; }
+                        } else {
+                            // both CTAs have drained this slot's accumulator and written its activations
+                            if (prev) mbar_wait_cluster(epi_done_a + 8u * (uint32_t)sl, hpar);
+                        }
+                        if (prev && !kTrail) { if (sl == 0) eph0 ^= 1; else eph1 ^= 1; }
+                        if (sl == 0) started0 = true; else started1 = true;
                         tc_fence_after();
                         if (lane == 0) trace_ev(A.desc_swap, 0, 1, sl, gi);
                         const uint32_t d_tmem = tmem_base + (uint32_t)sl * 256u;
@@ -290,6 +340,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                             for (int k0 = 0; k0 < kseg; k0 += step) {
                                 const int kc = min(step, kseg - k0);
                                 const uint64_t so = (uint64_t)stage * st_step;
+                                if (kTrail && prev && !from_x) {
+                                    // this stage reads activation columns [k0, k0 + 64) = slab k0 / 64 of the previous epilogue
+                                    const int hs = k0 >> 6;
+                                    while (waited <= hs) { mbar_wait_cluster(hbar + 8u * (uint32_t)waited, hpar); ++waited; }
+                                }
                                 mbar_wait_cluster(full_a + 8u * (uint32_t)stage, phase);
                                 tc_fence_after();
                                 c2_stage(d_tmem, from_x ? xd0 + so : ad, a_step, bd0 + so, b_step, idesc, accum, kc >> 4,
@@ -298,6 +353,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                 ad += (uint64_t)(kc >> 4) * a_step;
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
+                        }
+                        if (kTrail && prev) {
+                            // every slab barrier is consumed exactly once per GEMM (parity waits must not skip a phase)
+                            while (waited < 4) { mbar_wait_cluster(hbar + 8u * (uint32_t)waited, hpar); ++waited; }
+                            if (sl == 0) eph0 ^= 1; else eph1 ^= 1;
                         }
                         c2_commit_both(acc_full_a + 8u * (uint32_t)sl);
                         if (lane == 0) trace_ev(A.desc_swap, 0, 2, sl, gi);
@@ -310,12 +370,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             // ordered before the leader's acquire.cluster wait; they were already fenced to the async proxy by their writers)
             uint32_t lph0 = 0, lph1 = 0;
             const uint32_t epi_done_l = mapa_u32(smem_u32(epi_done), 0);
+            const uint32_t h_ready_l = mapa_u32(smem_u32(h_ready), 0);
             for (int64_t q = cl; q < n_quads; q += ncl)
                 for (int gi = 0; gi < n_gemm; ++gi)
                     for (int sl = 0; sl < 2; ++sl) {
-                        if (sl == 0) { mbar_wait(&epi_local[0], lph0); lph0 ^= 1; }
-                        else         { mbar_wait(&epi_local[1], lph1); lph1 ^= 1; }
-                        mbar_arrive_cluster(epi_done_l + 8u * (uint32_t)sl);
+                        const uint32_t lp = sl == 0 ? lph0 : lph1;
+                        if (kTrail) {
+                            for (int j = 0; j < 4; ++j) {
+                                mbar_wait(&h_local[sl * 4 + j], lp);
+                                mbar_arrive_cluster(h_ready_l + 8u * (uint32_t)(sl * 4 + j));
+                            }
+                        } else {
+                            mbar_wait(&epi_local[sl], lp);
+                            mbar_arrive_cluster(epi_done_l + 8u * (uint32_t)sl);
+                        }
+                        if (sl == 0) lph0 ^= 1; else lph1 ^= 1;
                     }
         }
     } else {
@@ -356,12 +425,73 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     const uint32_t t_acc = t_lane + (uint32_t)sl * 256u;
                     const float* bias = F32 + g.bias_off;
                     const int64_t row = row_[sl], slot = slot_[sl];
+                    // kTrail: announce slab j of this slot (leader: own barrier; peer: local barrier, forwarded by the relay)
+                    auto announce = [&](int j) {
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (leader) mbar_arrive(&h_ready[sl * 4 + j]);
+                            else mbar_arrive(&h_local[sl * 4 + j]);
+                        }
+                    };
                     if (g.epi == EPI_RGB) {
+                        uint32_t v[32];
                         if (part == 0) {
-                            uint32_t v[32];
                             tmem_ld32(t_acc, v);
                             tmem_ld_wait();
-                            if (row >= 0) tc_emit_rgb(A.m, sub, row, slot, v, bias, sigma_[sl]);
+                        }
+                        if (kTrail) {
+                            tc_fence_before();
+                            for (int j = 0; j < 4; ++j) announce(j);
+                        }
+                        if (part == 0 && row >= 0) tc_emit_rgb(A.m, sub, row, slot, v, bias, sigma_[sl]);
+                    } else if (kTrail) {
+                        const bool want_sigma = g.epi == EPI_RELU_SIGMA;
+                        const bool publish = !(want_sigma && A.m.sigma_only);
+                        const float* sw = F32 + P.sigma_w_off;
+                        unsigned char* Hsl = Hs + (size_t)sl * h_bytes;
+                        float sacc = 0.0f;
+                        const int nslab = (g.n + 63) >> 6;
+                        // the warp's four 16-column pieces as fp16 pairs (named arrays: kept in registers)
+                        uint32_t hp0[8], hp1[8], hp2[8], hp3[8];
+#define MN_C2_CONVERT(J, HP)                                                                                              \
+    {                                                                                                                    \
+        const int c0 = 64 * (J) + 16 * part;                                                                             \
+        if ((J) < nslab && c0 < g.n) {                                                                                   \
+            if (g.epi == EPI_RELU) c2_convert16<true, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, HP);              \
+            else if (g.epi == EPI_LINEAR) c2_convert16<false, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, HP);      \
+            else sacc += c2_convert16<true, true>(t_acc + (uint32_t)c0, bias + c0, sw + c0, HP);                         \
+        }                                                                                                                \
+    }
+                        MN_C2_CONVERT(0, hp0) MN_C2_CONVERT(1, hp1) MN_C2_CONVERT(2, hp2) MN_C2_CONVERT(3, hp3)
+#undef MN_C2_CONVERT
+                        tc_fence_before();      // all of this warp's TMEM reads are done: slab 0's announcement releases the accumulator
+#define MN_C2_STORE(J, HP)                                                                                               \
+    {                                                                                                                    \
+        const int c0 = 64 * (J) + 16 * part;                                                                             \
+        if ((J) < nslab && c0 < g.n && publish) {                                                                        \
+            unsigned char* dst = Hsl + (size_t)(c0 >> 3) * (kTileM * 16) + (size_t)r * 16;                               \
+            *reinterpret_cast<uint4*>(dst) = make_uint4(HP[0], HP[1], HP[2], HP[3]);                                     \
+            *reinterpret_cast<uint4*>(dst + kTileM * 16) = make_uint4(HP[4], HP[5], HP[6], HP[7]);                       \
+            fence_proxy_async();                                                                                         \
+        }                                                                                                                \
+        announce(J);                                                                                                     \
+    }
+                        MN_C2_STORE(0, hp0) MN_C2_STORE(1, hp1) MN_C2_STORE(2, hp2) MN_C2_STORE(3, hp3)
+#undef MN_C2_STORE
+                        if (want_sigma) {
+                            SIGP[part * kTileM + r] = sacc;
+                            asm volatile("bar.sync 1, 512;" ::: "memory");
+                            if (part == 0) {
+                                float s = ((SIGP[r] + SIGP[kTileM + r]) + (SIGP[2 * kTileM + r] + SIGP[3 * kTileM + r])) + sw[L];
+                                if (A.m.sigma_noise && row >= 0) s = s + A.m.sigma_noise[row];
+                                const float sg = A.m.nd.softplus ? mn_softplus_shifted(s) : fmaxf(s, 0.0f);
+                                sigma_[sl] = sg;
+                                if (A.m.sigma_only && row >= 0) {
+                                    const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
+                                    A.m.out[o] = A.m.slot_w ? sg * A.m.slot_w[slot] : sg;
+                                }
+                            }
+                            asm volatile("bar.sync 1, 512;" ::: "memory");
                         }
                     } else {
                         const bool want_sigma = g.epi == EPI_RELU_SIGMA;
@@ -402,7 +532,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     tc_fence_before();
                     __syncwarp();
                     if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 4, sl, gi);
-                    if (lane == 0) {
+                    if (lane == 0 && !kTrail) {
                         if (relay && !leader) mbar_arrive(&epi_local[sl]);
                         else mbar_arrive_cluster(epi_done_l + 8u * (uint32_t)sl);
                     }

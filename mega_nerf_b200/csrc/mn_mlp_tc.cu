@@ -1515,7 +1515,7 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         static int use_c2 = -1;
         if (use_c2 < 0) {
             const char* e = getenv("MN_TC_C2");
-            use_c2 = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
+            use_c2 = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 0;      // 1 pair, 2 + relay handshake, 3 + trailing epilogue
         }
         A.c2_relay = use_c2 == 2 ? 1 : 0;
         const PPLayout PL = pp_layout(P, bias_global != 0);
@@ -1529,12 +1529,14 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
             const uint64_t xrows = (uint64_t)n_tiles128 * (uint64_t)(P.kpe + P.kaux);
             if (!encode_rows256_map(ximg, xrows, 32, &maps.x32) || !encode_rows256_map(ximg, xrows, 16, &maps.x16))
                 return mn_fail(ctx, MN_ERR_CUDA, "cuTensorMapEncodeTiled failed for the feature tiles");
-            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL.total));
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_c2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL.total));
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_c2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL.total));
             const int64_t n_quads = n_tiles128 / 4;
             int64_t n_cl = n_quads < ctx->sm_count / 2 ? n_quads : ctx->sm_count / 2;
             if (n_cl < 1) n_cl = 1;
             mn_prof_begin(ctx, st);
-            tc_mlp_c2_kernel<<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A, maps);
+            if (use_c2 == 3) tc_mlp_c2_kernel<true><<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A, maps);
+            else tc_mlp_c2_kernel<false><<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A, maps);
         } else
         if (use_ts && !a.nd.affine && P.L % 128 == 0 && TL.stages >= 4) {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL.total));

@@ -18,8 +18,8 @@ case "${1:-help}" in
                          ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_train.csv python bench.py --mode train --steps 1 --warmup 3 > gpurun_out/l2.log 2>&1; tail -3 gpurun_out/l2.log' ;;
   ncu-mlp)      # full capture of the fine-pass launch of the forward MLP kernel
     $G --timeout 900 -- 'ncu --set full --import-source on --clock-control none -k regex:tc_mlp_pp_kernel -s 5 -c 1 -o gpurun_out/tc_mlp_pp_kernel python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-gpu-incumbent > gpurun_out/n1.log 2>&1; ls -la gpurun_out/*.ncu-rep' ;;
-  c2)           # A/B of the three 256-wide kernels on one box: ping-pong (default), CTA pair, CTA pair with the relay handshake
-    $G --timeout 900 -- 'for v in 0 1 2; do MN_TC_C2=$v python bench.py --steps 30 --no-cpu-baseline --no-gpu-incumbent > gpurun_out/bench_c2_$v.json 2>/dev/null; python -c "import json;d=json.load(open(\"gpurun_out/bench_c2_$v.json\"));print($v, d[\"ms_per_step\"], d[\"roofline\"][\"achieved\"], d[\"parity\"])"; done' ;;
+  c2)           # A/B of the 256-wide kernels on one box: ping-pong (default), CTA pair, + relay handshake, + trailing epilogue
+    $G --timeout 900 -- 'for v in 0 1 2 3; do MN_TC_C2=$v python bench.py --steps 30 --no-cpu-baseline --no-gpu-incumbent > gpurun_out/bench_c2_$v.json 2>/dev/null; python -c "import json;d=json.load(open(\"gpurun_out/bench_c2_$v.json\"));print($v, d[\"ms_per_step\"], d[\"roofline\"][\"achieved\"], d[\"parity\"])"; done' ;;
   ncu-c2)       # same for the CTA-pair kernel (the candidate for the next frac step)
     $G --timeout 900 -- 'MN_TC_C2=1 ncu --set full --import-source on --clock-control none -k regex:tc_mlp_c2_kernel -s 5 -c 1 -o gpurun_out/tc_mlp_c2_kernel python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-gpu-incumbent > gpurun_out/n2.log 2>&1; ls -la gpurun_out/*.ncu-rep' ;;
   ncu-bwd)      # full capture of the two backward kernels
