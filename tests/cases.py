@@ -158,6 +158,7 @@ def grad_cotangents(name: str, n_rays: int) -> Dict[str, torch.Tensor]:
     return {'rgb_fine': torch.randn(n_rays, 3, generator=g), 'rgb_coarse': torch.randn(n_rays, 3, generator=g)}
 
 
+TRAIN_GOLDEN_PATH = os.path.join(ROOT, 'tests', 'golden', 'train_mode_v1.pt')
 CLUSTER_GOLDEN_PATH = os.path.join(ROOT, 'tests', 'golden', 'cluster_masks_v1.pt')
 
 
