@@ -92,3 +92,54 @@ def test_random_configuration_bit_exact(MG, seed):
         for a, b in zip(MB.ref_grads(mod, n_), g_):
             for k in a:
                 assert torch.equal(a[k], b[k]), (seed, k, float((a[k] - b[k]).abs().max()))
+
+
+def test_call_surface_signatures_match_reference(MG):
+    """Drop-in boundary: every replaced symbol takes the reference's parameters, in order, with the
+    reference's defaults."""
+    import inspect
+    import mega_nerf_b200 as M
+    from mega_nerf import ray_utils as R_rays, rendering as R_rendering
+    from mega_nerf.spherical_harmonics import eval_sh as R_eval_sh
+    from mega_nerf.models import nerf as R_nerf, mega_nerf as R_mega, cascade as R_cascade
+    pairs = [(M.render_rays, R_rendering.render_rays), (M.get_rays, R_rays.get_rays), (M.get_rays_batch, R_rays.get_rays_batch),
+             (M.get_ray_directions, R_rays.get_ray_directions), (M.eval_sh, R_eval_sh),
+             (M.NeRF.__init__, R_nerf.NeRF.__init__), (M.NeRF.forward, R_nerf.NeRF.forward),
+             (M.MegaNeRF.__init__, R_mega.MegaNeRF.__init__), (M.MegaNeRF.forward, R_mega.MegaNeRF.forward),
+             (M.Cascade.__init__, R_cascade.Cascade.__init__), (M.Cascade.forward, R_cascade.Cascade.forward),
+             (M.Embedding.__init__, R_nerf.Embedding.__init__), (M.ShiftedSoftplus.__init__, R_nerf.ShiftedSoftplus.__init__)]
+    for mine, ref in pairs:
+        a, b = inspect.signature(mine), inspect.signature(ref)
+        pa = [(p.name, p.default, p.kind) for p in a.parameters.values()]
+        pb = [(p.name, p.default, p.kind) for p in b.parameters.values()]
+        assert [x[0] for x in pa] == [x[0] for x in pb], (ref.__qualname__, pa, pb)
+        assert [x[1:] for x in pa] == [x[1:] for x in pb], (ref.__qualname__, pa, pb)
+    # model_utils needs configargparse-free import: compare by source inspection of the two factory signatures
+    import importlib
+    mu = importlib.import_module('mega_nerf.models.model_utils')
+    for name in ('get_nerf', 'get_bg_nerf'):
+        assert list(inspect.signature(getattr(M, name)).parameters) == list(inspect.signature(getattr(mu, name)).parameters)
+    # state-dict layout of every model family
+    spec = O.NerfSpec(layer_dim=32, appearance_count=5)
+    for kind in ('nerf', 'cascade', 'mega'):
+        cents = O.grid_centroids(2, 2) if kind == 'mega' else None
+        net = O.make_net(kind, spec, seed=1, n_sub=4 if kind == 'mega' else 1, centroids=cents, cluster_2d=True)
+        ref = MG.ref_net(net)
+        from test_host_factories import M as _M  # noqa: F401
+        if kind == 'nerf':
+            mine = M.NeRF(spec.pos_xyz_dim, spec.pos_dir_dim, spec.layers, list(spec.skip_layers), spec.layer_dim, spec.appearance_dim,
+                          spec.affine_appearance, spec.appearance_count, spec.rgb_dim, spec.xyz_dim, M.ShiftedSoftplus())
+        elif kind == 'cascade':
+            mk = lambda: M.NeRF(spec.pos_xyz_dim, spec.pos_dir_dim, spec.layers, list(spec.skip_layers), spec.layer_dim,  # noqa: E731
+                                spec.appearance_dim, spec.affine_appearance, spec.appearance_count, spec.rgb_dim, spec.xyz_dim,
+                                M.ShiftedSoftplus())
+            mine = M.Cascade(mk(), mk())
+        else:
+            mk = lambda: M.NeRF(spec.pos_xyz_dim, spec.pos_dir_dim, spec.layers, list(spec.skip_layers), spec.layer_dim,  # noqa: E731
+                                spec.appearance_dim, spec.affine_appearance, spec.appearance_count, spec.rgb_dim, spec.xyz_dim,
+                                M.ShiftedSoftplus())
+            mine = M.MegaNeRF([mk() for _ in range(4)], cents, 1.15, False, True)
+        a, b = mine.state_dict(), ref.state_dict()
+        assert list(a) == list(b), (kind, set(a) ^ set(b))
+        assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in b)
+        mine.load_state_dict(b)                      # reference checkpoints load
