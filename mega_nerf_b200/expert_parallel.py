@@ -45,28 +45,14 @@ class _RouteOnly:
             pass
 
     def sync(self, device: torch.device):
-        from .modules import ShiftedSoftplus
+        from .modules import model_desc
         L = K.lib()
         h = K.ctx(device)
         m = self.mega
-        first = m.sub_modules[0]
         if self.handle is None or self.device != device:
             if self.handle is not None:
                 L.mn_model_destroy(self.handle)
-            d = K.ModelDesc()
-            d.kind, d.n_sub = 2, len(m.sub_modules)
-            d.pos_xyz_dim, d.pos_dir_dim = first.pos_xyz_dim, first.pos_dir_dim
-            d.layers, d.layer_dim = first.layers, first.layer_dim
-            d.appearance_dim, d.affine_appearance = first.appearance_dim, int(first.affine_appearance)
-            d.appearance_count, d.rgb_dim, d.xyz_dim = first.appearance_count, first.rgb_dim, first.xyz_dim
-            d.shifted_softplus = int(isinstance(first.sigma_activation, ShiftedSoftplus))
-            skips = list(first.skip_layers)
-            d.n_skip = len(skips)
-            for i, s in enumerate(skips):
-                d.skip_layers[i] = int(s)
-            d.boundary_margin = float(m.boundary_margin)
-            d.xyz_real = int(m.xyz_real)
-            d.cluster_dim_start = int(m.cluster_dim_start)
+            d = model_desc(m.sub_modules[0], 2, len(m.sub_modules), m.boundary_margin, m.xyz_real, m.cluster_dim_start)
             out = C.c_void_p()
             K.check(L.mn_model_create(h, C.byref(d), C.byref(out)), h)
             self.handle, self.device, self.stamp = out.value, device, None

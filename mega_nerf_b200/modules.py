@@ -72,6 +72,26 @@ class ShiftedSoftplus(nn.Module):
         return 'beta={}, threshold={}'.format(self.beta, self.threshold)
 
 
+def model_desc(first: nn.Module, kind: int, n_sub: int, margin: float, xyz_real: bool, cluster_dim_start: int) -> 'K.ModelDesc':
+    """mn_model_desc of a network whose sub-modules all look like `first` (a NeRF)."""
+    d = K.ModelDesc()
+    d.kind, d.n_sub = kind, n_sub
+    d.pos_xyz_dim, d.pos_dir_dim = first.pos_xyz_dim, first.pos_dir_dim
+    d.layers, d.layer_dim = first.layers, first.layer_dim
+    d.appearance_dim, d.affine_appearance = first.appearance_dim, int(first.affine_appearance)
+    d.appearance_count, d.rgb_dim, d.xyz_dim = first.appearance_count, first.rgb_dim, first.xyz_dim
+    d.shifted_softplus = int(isinstance(first.sigma_activation, ShiftedSoftplus)
+                             or type(first.sigma_activation).__name__ == 'ShiftedSoftplus')
+    skips = list(first.skip_layers)
+    d.n_skip = len(skips)
+    for i, s in enumerate(skips):
+        d.skip_layers[i] = int(s)
+    d.boundary_margin = float(margin)
+    d.xyz_real = int(xyz_real)
+    d.cluster_dim_start = int(cluster_dim_start)
+    return d
+
+
 class _Native:
     """Owns the mn_model handle of a top-level network and keeps its packed weights in sync."""
 
@@ -118,21 +138,7 @@ class _Native:
             if self.handle is not None:
                 L.mn_model_destroy(self.handle)
                 self.handle = None
-            d = K.ModelDesc()
-            d.kind, d.n_sub = self.kind, len(self.subs)
-            d.pos_xyz_dim, d.pos_dir_dim = first.pos_xyz_dim, first.pos_dir_dim
-            d.layers, d.layer_dim = first.layers, first.layer_dim
-            d.appearance_dim, d.affine_appearance = first.appearance_dim, int(first.affine_appearance)
-            d.appearance_count, d.rgb_dim, d.xyz_dim = first.appearance_count, first.rgb_dim, first.xyz_dim
-            d.shifted_softplus = int(isinstance(first.sigma_activation, ShiftedSoftplus)
-                                     or type(first.sigma_activation).__name__ == 'ShiftedSoftplus')
-            skips = list(first.skip_layers)
-            d.n_skip = len(skips)
-            for i, s in enumerate(skips):
-                d.skip_layers[i] = int(s)
-            d.boundary_margin = float(self.margin)
-            d.xyz_real = int(self.xyz_real)
-            d.cluster_dim_start = int(self.cluster_dim_start)
+            d = model_desc(first, self.kind, len(self.subs), self.margin, self.xyz_real, self.cluster_dim_start)
             out = C.c_void_p()
             K.check(L.mn_model_create(h, C.byref(d), C.byref(out)), h)
             self.handle = out.value
