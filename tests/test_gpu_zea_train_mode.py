@@ -62,3 +62,33 @@ def test_train_mode_gradients_match_reference(train_golden, cpu_draws):
     (res['rgb_fine'] * cot['rgb_fine'].to(DEV)).sum().backward()
     check_param_grads(pn, net, train_golden['grads_g_single'], 'train-mode g_single', E2E_TOL)
     assert global_rel_l2(pn, net, train_golden['grads_g_single']) <= E2E_L2
+
+
+def test_training_loop_under_autocast_and_gradscaler():
+    """The reference's loop (runner.py:243-274): forward under torch.cuda.amp.autocast, scaler.scale(loss).backward(),
+    scaler.step(optimizer), scaler.update() - with the default 65536 loss scale the upstream gradients reach the backward
+    kernels multiplied by 2^16 and param.grad is unscaled by the scaler before the step."""
+    from oracle import mn_oracle as O
+    m = M()
+    torch.manual_seed(0)
+    spec = O.NerfSpec(layer_dim=64, appearance_count=10)
+    pn = product_net(O.make_net('nerf', spec, seed=12)).requires_grad_(True).train()
+    rays = O.synthetic_rays(256, seed=2).to(DEV)
+    idx = O.synthetic_indices(256, 10).to(DEV).int()                  # int32 image indices, as the training loader delivers them
+    target = torch.tensor([0.9, 0.1, 0.5], device=DEV).expand(256, 3)
+    hp = Namespace(**vars(O.RenderOpts(coarse_samples=16, fine_samples=32, perturb=1.0)))
+    opt = torch.optim.Adam(pn.parameters(), lr=2e-3)
+    scaler = torch.amp.GradScaler('cuda')
+    losses = []
+    for _ in range(40):
+        with torch.autocast('cuda', dtype=torch.float16):
+            res, _ = m.render_rays(pn, None, rays, idx, hp, None, None, False, True, False)
+            loss = torch.nn.functional.mse_loss(res['rgb_fine'], target)
+        opt.zero_grad(set_to_none=True)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        losses.append(float(loss.detach()))
+    assert all(torch.isfinite(p).all() for p in pn.parameters())
+    assert scaler.get_scale() >= 65536.0                                # no inf / nan gradient ever made the scaler back off
+    assert sum(losses[-5:]) < 0.8 * sum(losses[:5]), losses
