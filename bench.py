@@ -397,6 +397,8 @@ def main():
     ap.add_argument('--no-gpu-incumbent', action='store_true', help='skip timing the restatement under torch-CUDA eager')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true', help='issue every step eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--margin', type=float, default=MARGIN, help='boundary_margin of the mixture: 1.15 = reference eval default (graded), '
+                                                                 '1.0 = hard routing, m = 1 (SURVEY.md §8d)')
     ap.add_argument('--parallelism', default='rays', choices=['rays', 'experts'],
                     help="N > 1: 'rays' = ray-sharded with replicated weights (default, graded); 'experts' = additionally "
                          "owner-computes sub-modules (sub-module k on rank k mod N, two all-to-alls per model query; eager launches)")
@@ -409,6 +411,7 @@ def main():
                          "48k-ray chunk x 1000 samples (SURVEY.md §8f-3); both diagnostics only")
     args = ap.parse_args()
     select_workload(args.workload)
+    globals()['MARGIN'] = args.margin
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
     rank = int(os.environ.get('RANK', '0'))
