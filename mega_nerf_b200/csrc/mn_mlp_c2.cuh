@@ -2,9 +2,10 @@
 //
 // A cluster of two CTAs (one SM pair) runs tcgen05.mma.cta_group::2: one instruction issued by the leader CTA drives
 // both SMs' tensor cores on a 256-row tile (128 rows per CTA).  Each CTA stages only HALF of every weight slab
-// (N/2 rows of B): measured on B200, the single-CTA kernel is bound by shared-memory traffic - per 128x256x16 MMA the
-// tensor core fetches 12 KiB of operands (A 4 KiB + B 8 KiB, ~182 cycles instead of 128) while TMA writes another
-// 8 KiB of weights into the ring; the pair halves both B terms per SM and a ring stage holds 64 K-columns (4 MMAs).
+// (N/2 rows of B): measured on B200, the single-CTA kernel sits on the L2 -> SM delivery ceiling (~32 B/clk/SM: each
+// 128-row tile re-reads 1.2 MB of weights) and its tensor core fetches 12 KiB of operands per 128x256x16
+// MMA (A 4 KiB + B 8 KiB, ~182 cycles instead of 128); the pair halves the weight bytes delivered to each SM and the B
+// operand bytes read per SM, and a ring stage holds 64 K-columns (4 MMAs).
 // Everything else follows tc_mlp_pp_kernel: two 256-row tiles (X, Y) per cluster - four consecutive 128-row tiles,
 // one sub-module thanks to the 512-row bucket alignment - GEMMs issued X_l, Y_l, X_l+1, ..., each CTA's 16 epilogue
 // warps drain its own 128 TMEM lanes under the other tile's MMAs; feature columns ride in the weight ring.

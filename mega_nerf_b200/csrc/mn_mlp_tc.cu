@@ -1455,7 +1455,8 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         if (WL.total > kSmemMax) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core MLP (512-wide): shared-memory budget exceeded");
         // MN_TC_CLUSTER=2: clusters of two CTAs share one multicast weight stream (the router's bucket alignment
         // guarantees that tiles 2p and 2p+1 belong to one sub-module).  Halves the L2 reads but measured 2-3 % SLOWER
-        // on B200 (the kernel is bound by shared-memory traffic, not by L2), so the default is one CTA per cluster.
+        // on B200: every SM still RECEIVES all weight bytes, and the ~32 B/clk/SM delivery rate is what binds these kernels
+        //  - multicast saves L2 reads, not deliveries.  The default is one CTA per cluster.
         static int cs = -1;
         if (cs < 0) {
             const char* e = getenv("MN_TC_CLUSTER");
