@@ -29,7 +29,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 N_RAYS = 4096
 COARSE, FINE = 64, 128
@@ -226,14 +225,14 @@ def run_train(args, rank, local_rank, world):
     all-reduced by DistributedDataParallel semantics are NOT part of this diagnostic (N = 1 only)."""
     import mega_nerf_b200 as M
     from mega_nerf_b200 import _cabi as K
-    from test_gpu_parity import product_net
+    from mega_nerf_b200.synthetic import build_net
     if world != 1:
         raise SystemExit('--mode train is a single-GPU diagnostic')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     spec, net, rays_h, idx_h, opts = workload()
     hp = Namespace(**vars(opts))
-    model = product_net(net).requires_grad_(True).train()
+    model = build_net(net, dev, trainable=True).train()
     opt = torch.optim.Adam(model.parameters(), lr=5e-4)
     rgbs_h = torch.rand(N_RAYS, 3, generator=torch.Generator().manual_seed(9))
     rays_pin, idx_pin, rgbs_pin = rays_h.pin_memory(), idx_h.pin_memory(), rgbs_h.pin_memory()
@@ -431,7 +430,7 @@ def main():
     import mega_nerf_b200 as M
     from mega_nerf_b200 import _cabi as K
     from oracle import mn_oracle as O            # cpu_baseline / parity sample only
-    from test_gpu_parity import product_net
+    from mega_nerf_b200.synthetic import build_net
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -441,7 +440,7 @@ def main():
 
     spec, net, rays_h, idx_h, opts = workload(seed_shift=rank)
     hp = Namespace(**vars(opts))
-    model = product_net(net).to(dev).eval()
+    model = build_net(net, dev)
     M.set_precision(args.precision)
     experts = args.parallelism == 'experts' and world > 1
     if experts:

@@ -205,7 +205,15 @@ int mn_model_create(mn_ctx* ctx, const mn_model_desc* desc, mn_model** out) {
     m->ctx = ctx;
     m->d = d;
     build_layout(m);
-    m->max_multiplicity = d.kind == 2 ? (d.boundary_margin > 1.0f ? (d.n_sub < 4 ? d.n_sub : 4) : 1) : 1;
+    // sub-modules per sample the slot capacity is sized for: 1 under hard routing; with blending a regular centroid grid
+    // puts at most 4 (2-D clustering) / 8 (3-D) cells within boundary_margin x d_min for any margin < 2.2 (the nearest cell
+    // of the next ring is 2.2 x further than the corner-sharing ones).  mn_model_set_max_multiplicity raises it for other
+    // layouts; exceeding it poisons the affected rows with NaN and sets MN_STATUS_OVERFLOW (never a silent wrong blend).
+    {
+        const int geo = d.cluster_dim_start == 1 ? 4 : 8;
+        m->max_multiplicity = (d.kind == 2 && d.boundary_margin > 1.0f) ? (d.n_sub < geo ? d.n_sub : geo) : 1;
+        if (d.kind == 2 && d.boundary_margin >= 2.2f) m->max_multiplicity = d.n_sub;
+    }
     *out = m;
     MN_CUDA(ctx, cudaMalloc(&m->packed, (size_t)d.n_sub * m->lay.total * sizeof(float)));
     MN_CUDA(ctx, cudaMemset(m->packed, 0, (size_t)d.n_sub * m->lay.total * sizeof(float)));

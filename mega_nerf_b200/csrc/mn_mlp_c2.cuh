@@ -20,25 +20,29 @@
 #pragma once
 
 
-constexpr int kC2MaxStages = 8;
-constexpr int kC2StageCols = 64;                        // activation segments: 64 K-columns x (N/2 <= 128) weight rows = <= 16 KiB
-constexpr int kC2StageBytes = kC2StageCols * 128 * 2;
-constexpr int kC2XCols = 32;                            // feature segments: 32 K-columns of weights (<= 8 KiB) + 32 feature columns (8 KiB)
-constexpr int kC2XOff = 8192;
-
+constexpr int kC2MaxStages = 16;
+// Ring geometry.  Streaming mode: a stage = 64 K-columns x (N/2 <= 128) weight rows (<= 16 KiB), or, for a feature
+// segment, 32 K-columns of weights (<= 8 KiB) + the same 32 feature columns of the CTA's tile (8 KiB at +8 KiB).
+// Shared mode (TcArgs::c2_share): half-size stages - 32 K-columns (8 KiB) / 16 + 16 (4 KiB + 4 KiB) - so that the 8 stages
+// a 256-deep layer pins while both tile slots consume them leave room for the next layer's first stages.
 struct C2Layout {
     int ring, h, f32, f32_stride, sigp, bars, total, stages;
+    int stage_cols, stage_bytes, xcols, xoff;
 };
 
-__host__ __device__ inline C2Layout c2_layout(const TcPlan& p) {
+__host__ __device__ inline C2Layout c2_layout(const TcPlan& p, bool share) {
     C2Layout s;
+    s.stage_cols = share ? 32 : 64;
+    s.stage_bytes = s.stage_cols * 128 * 2;
+    s.xcols = s.stage_cols / 2;
+    s.xoff = s.stage_bytes / 2;
     s.f32_stride = ((p.f32_floats * 4 + 15) / 16) * 16;
     const int fixed = 2 * p.L * kTileM * 2 + s.f32_stride + 2048 + 512;
-    int st = (kSmemMax - fixed) / kC2StageBytes;
+    int st = (kSmemMax - fixed) / s.stage_bytes;
     if (st > kC2MaxStages) st = kC2MaxStages;
     s.stages = st;
     s.ring = 0;
-    s.h = st * kC2StageBytes;
+    s.h = st * s.stage_bytes;
     s.f32 = s.h + 2 * p.L * kTileM * 2;
     s.sigp = s.f32 + s.f32_stride;
     s.bars = s.sigp + 2048;
@@ -84,24 +88,26 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // up to four K=16 steps of a 256-row (2-CTA) MMA against one ring stage, then release the stage in both CTAs
+// (release == 0: the stage stays resident - the other tile slot consumes it next, shared mode)
 __device__ __forceinline__ void c2_stage(uint32_t d_tmem, uint64_t ad, uint64_t a_step, uint64_t bd, uint64_t b_step, uint32_t idesc,
-                                         uint32_t accum, int nk, uint32_t empty_bar) {
+                                         uint32_t accum, int nk, uint32_t empty_bar, uint32_t release = 1u) {
     asm volatile(
-        "{\n\t.reg .pred e, p, q1, q2, q3;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t.reg .b16 msk;\n\t"
+        "{\n\t.reg .pred e, p, q1, q2, q3, r;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t.reg .b16 msk;\n\t"
         "mov.b16 msk, 3;\n\t"
         "elect.sync _|e, 0xffffffff;\n\t"
         "setp.ne.b32 p, %6, 0;\n\t"
         "setp.gt.and.s32 q1, %7, 1, e;\n\t"
         "setp.gt.and.s32 q2, %7, 2, e;\n\t"
         "setp.gt.and.s32 q3, %7, 3, e;\n\t"
+        "setp.ne.and.b32 r, %9, 0, e;\n\t"
         "add.u64 a1, %1, %2;\n\tadd.u64 a2, a1, %2;\n\tadd.u64 a3, a2, %2;\n\t"
         "add.u64 b1, %3, %4;\n\tadd.u64 b2, b1, %4;\n\tadd.u64 b3, b2, %4;\n\t"
         "@e  tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %3, %5, p;\n\t"
         "@q1 tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %5, 1;\n\t"
         "@q2 tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %5, 1;\n\t"
         "@q3 tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %5, 1;\n\t"
-        "@e  tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], msk;\n\t}"
-        ::"r"(d_tmem), "l"(ad), "l"(a_step), "l"(bd), "l"(b_step), "r"(idesc), "r"(accum), "r"(nk), "r"(empty_bar)
+        "@r  tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], msk;\n\t}"
+        ::"r"(d_tmem), "l"(ad), "l"(a_step), "l"(bd), "l"(b_step), "r"(idesc), "r"(accum), "r"(nk), "r"(empty_bar), "r"(release)
         : "memory");
 }
 __device__ __forceinline__ void c2_commit_both(uint32_t bar_addr) {
@@ -157,17 +163,19 @@ __device__ __forceinline__ float c2_convert16(uint32_t taddr, const float* __res
 }
 
 struct C2Maps {
-    CUtensorMap w64, w32, w8;   // packed weights viewed as rows of 256 B: boxes of 64 / 32 / 8 rows
+    CUtensorMap w64, w32, w8, w4;   // packed weights viewed as rows of 256 B: boxes of 64 / 32 / 8 / 4 rows
     CUtensorMap x32, x16;       // feature tile images, same view: boxes of 32 / 16 rows (= K-columns)
 };
 
 // copies `rows` x 256 B starting at row `row0` of a rows-of-256-B tensor map into this CTA's shared memory, using the
 // largest boxes first (box heights ra > rb > rc; a map pointer may be null)
 __device__ __forceinline__ void c2_copy_rows(uint32_t dst, int row0, int rows, uint32_t bar, const CUtensorMap* ma, int ra,
-                                             const CUtensorMap* mb, int rb, const CUtensorMap* mc, int rc) {
+                                             const CUtensorMap* mb, int rb, const CUtensorMap* mc, int rc,
+                                             const CUtensorMap* md = nullptr, int rd = 0) {
     while (ma && rows >= ra) { tma2d_c2(dst, ma, row0, bar); dst += (uint32_t)ra * 256u; row0 += ra; rows -= ra; }
     while (mb && rows >= rb) { tma2d_c2(dst, mb, row0, bar); dst += (uint32_t)rb * 256u; row0 += rb; rows -= rb; }
     while (mc && rows >= rc) { tma2d_c2(dst, mc, row0, bar); dst += (uint32_t)rc * 256u; row0 += rc; rows -= rc; }
+    while (md && rows >= rd) { tma2d_c2(dst, md, row0, bar); dst += (uint32_t)rd * 256u; row0 += rd; rows -= rd; }
 }
 
 // kTrail (MN_TC_C2=3): every epilogue warp first loads ALL its accumulator columns into registers, then converts and
@@ -180,23 +188,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     tc_mlp_c2_kernel(const TcArgs A, const __grid_constant__ C2Maps TM) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
-    const C2Layout SL = c2_layout(P);
+    const bool share = A.c2_share != 0;
+    const C2Layout SL = c2_layout(P, share);
     const int kStages = SL.stages;
+    const int kC2StageCols = SL.stage_cols, kC2StageBytes = SL.stage_bytes, kC2XCols = SL.xcols, kC2XOff = SL.xoff;
     unsigned char* ring = smem + SL.ring;
     unsigned char* Hs = smem + SL.h;
     float* F32 = reinterpret_cast<float*>(smem + SL.f32);
     float* SIGP = reinterpret_cast<float*>(smem + SL.sigp);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bars);
-    uint64_t* full = bars;            // [<=8] LEADER's: both CTAs' halves of the stage have landed
-    uint64_t* empty = bars + 8;       // [<=8] per CTA (released by the leader's multicast commit)
-    uint64_t* acc_full = bars + 16;   // [2]   per CTA
-    uint64_t* epi_done = bars + 18;   // [2]   leader's
-    uint64_t* f32_full = bars + 20;   //       per CTA
-    uint64_t* f32_empty = bars + 21;  //       per CTA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
-    uint64_t* epi_local = bars + 24;  // [2]   per CTA, relay mode only
-    uint64_t* h_ready = bars + 32;    // [2][4] leader's (kTrail): 16 local arrivals + 1 relayed from the peer
-    uint64_t* h_local = bars + 40;    // [2][4] per CTA  (kTrail): the peer's 16 epilogue warps
+    uint64_t* full = bars;            // [<=16] LEADER's: both CTAs' halves of the stage have landed
+    uint64_t* empty = bars + 16;      // [<=16] per CTA (released by the leader's multicast commit)
+    uint64_t* acc_full = bars + 32;   // [2]   per CTA
+    uint64_t* epi_done = bars + 34;   // [2]   leader's
+    uint64_t* f32_full = bars + 36;   //       per CTA
+    uint64_t* f32_empty = bars + 37;  //       per CTA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
+    uint64_t* epi_local = bars + 40;  // [2]   per CTA, relay mode only
+    uint64_t* h_ready = bars + 44;    // [2][4] leader's (kTrail): 16 local arrivals + 1 relayed from the peer
+    uint64_t* h_local = bars + 52;    // [2][4] per CTA  (kTrail): the peer's 16 epilogue warps
     const bool relay = kTrail || A.c2_relay != 0;
 
     uint32_t rank;
@@ -267,7 +277,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     const int nhalf = g.n >> 1;                                   // weight rows held by this CTA
                     const int K = g.k[0] + (g.nseg > 1 ? g.k[1] : 0);
                     const unsigned char* wimg = wsub + c2_off + g.w_off + (size_t)rank * K * nhalf * 2;
+                    // shared mode: a GEMM whose only operand is the activation buffer (no per-tile feature columns in its
+                    // stream) is loaded ONCE per cluster iteration; both tile slots consume the same stages
+                    const bool shared_g = share && g.nseg == 1 && g.src[0] == SRC_H;
                     for (int sl = 0; sl < 2; ++sl) {
+                        if (shared_g && sl == 1) break;
                         const int64_t my_tile = 4 * q + 2 * sl + rank;           // this CTA's 128-row tile of the slot
                         int kbase = 0;
                         for (int sgi = 0; sgi < g.nseg; ++sgi) {
@@ -286,7 +300,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                 // only complete_tx on the leader's barrier - no remote arrive on the critical path
                                 if (leader) mbar_expect_tx(&full[stage], 2u * (wbytes + xbytes));
                                 const int wrow0 = (int)((size_t)((wimg + (size_t)(kbase + k0) * nhalf * 2) - A.wpack) >> 8);
-                                c2_copy_rows(dst, wrow0, (int)(wbytes >> 8), bar, &TM.w64, 64, &TM.w32, 32, &TM.w8, 8);
+                                c2_copy_rows(dst, wrow0, (int)(wbytes >> 8), bar, &TM.w64, 64, &TM.w32, 32, &TM.w8, 8, &TM.w4, 4);
                                 if (from_x) c2_copy_rows(dst + kC2XOff, xrow0 + k0, kc, bar, &TM.x32, 32, &TM.x16, 16, nullptr, 0);
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
@@ -315,7 +329,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     const uint32_t idesc = make_idesc_m(256, g.n);
                     const uint64_t b_step = (uint64_t)((2 * nhalf * 16) >> 4);
                     const uint64_t bd0 = make_desc(ring_base, (uint32_t)nhalf * 16, 128);
+                    // shared mode: slot 0 walks the GEMM's stages WITHOUT releasing them, slot 1 walks the same stages again
+                    // (their full barriers have completed: the parity waits pass immediately) and releases each one
+                    const bool shared_g = share && g.nseg == 1 && g.src[0] == SRC_H;
+                    const int stage_g0 = stage;
+                    const uint32_t phase_g0 = phase;
                     for (int sl = 0; sl < 2; ++sl) {
+                        if (shared_g && sl == 1) { stage = stage_g0; phase = phase_g0; }
+                        const uint32_t release = (shared_g && sl == 0) ? 0u : 1u;
                         const bool prev = sl == 0 ? started0 : started1;       // this slot has an epilogue in flight
                         const uint32_t hpar = sl == 0 ? eph0 : eph1;
                         const uint32_t hbar = smem_u32(h_ready) + 32u * (uint32_t)sl;
@@ -349,7 +370,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                 mbar_wait_cluster(full_a + 8u * (uint32_t)stage, phase);
                                 tc_fence_after();
                                 c2_stage(d_tmem, from_x ? xd0 + so : ad, a_step, bd0 + so, b_step, idesc, accum, kc >> 4,
-                                         empty_a + 8u * (uint32_t)stage);
+                                         empty_a + 8u * (uint32_t)stage, release);
                                 accum = 1;
                                 ad += (uint64_t)(kc >> 4) * a_step;
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }

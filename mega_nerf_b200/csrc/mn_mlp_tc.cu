@@ -679,6 +679,8 @@ struct TcArgs {
     int nofetch;                  // debug (MN_TC_NOFETCH=1): producers skip the TMA copies (garbage results; isolates the
                                   // MMA + epilogue pipeline from the weight stream when timing)
     int64_t n_tiles_cap;
+    int c2_share;                 // CTA-pair kernel (MN_TC_C2SHARE=1): activation-only GEMMs stream their weights once for BOTH tile
+                                  // slots of a cluster iteration (stages stay resident between slot 0's and slot 1's MMAs)
     int c2_relay;                 // CTA-pair kernel (MN_TC_C2=2): the peer's epilogue warps arrive on a LOCAL barrier and its idle MMA
                                   // warp forwards ONE remote arrive per GEMM and slot to the leader (instead of 16 remote arrives)
 };
@@ -1347,9 +1349,9 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         m->tc_sub_bytes = sub_bytes;
         // tensor maps for the cta_group::2 kernel (its TMA loads must be the .tensor form to signal the peer CTA's barrier)
         const uint64_t rows = (uint64_t)(sub_bytes * m->d.n_sub / 256);
-        const uint32_t boxes[3] = {64, 32, 8};
+        const uint32_t boxes[4] = {64, 32, 8, 4};
         m->tmap_ready = 1;
-        for (int b = 0; b < 3; ++b)
+        for (int b = 0; b < 4; ++b)
             if (!encode_rows256_map(m->tc_packed, rows, boxes[b], m->tmap_w[b])) m->tmap_ready = 0;
     }
     unsigned char* base = (unsigned char*)m->tc_packed + (size_t)sub * sub_bytes;
@@ -1519,14 +1521,22 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
             use_c2 = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 0;      // 1 pair, 2 + relay handshake, 3 + trailing epilogue
         }
         A.c2_relay = use_c2 == 2 ? 1 : 0;
+        static int c2_share = -1;
+        if (c2_share < 0) {
+            const char* e = getenv("MN_TC_C2SHARE");
+            c2_share = (e && e[0] == '1') ? 1 : 0;
+        }
+        A.c2_share = c2_share;
         const PPLayout PL = pp_layout(P, bias_global != 0);
         const TsLayout TL = ts_layout(P);
-        const C2Layout CL = c2_layout(P);
-        if (use_c2 && !a.nd.affine && P.L == 256 && m->tmap_ready && CL.total <= kSmemMax && CL.stages >= 3 && (n_tiles128 % 4) == 0) {
+        const C2Layout CL = c2_layout(P, c2_share != 0);
+        if (use_c2 && !a.nd.affine && P.L == 256 && m->tmap_ready && CL.total <= kSmemMax && CL.stages >= (c2_share ? 10 : 3) &&
+            (n_tiles128 % 4) == 0) {
             C2Maps maps;
             memcpy(&maps.w64, m->tmap_w[0], 128);
             memcpy(&maps.w32, m->tmap_w[1], 128);
             memcpy(&maps.w8, m->tmap_w[2], 128);
+            memcpy(&maps.w4, m->tmap_w[3], 128);
             const uint64_t xrows = (uint64_t)n_tiles128 * (uint64_t)(P.kpe + P.kaux);
             if (!encode_rows256_map(ximg, xrows, 32, &maps.x32) || !encode_rows256_map(ximg, xrows, 16, &maps.x16))
                 return mn_fail(ctx, MN_ERR_CUDA, "cuTensorMapEncodeTiled failed for the feature tiles");

@@ -165,8 +165,11 @@ __global__ void route_scatter_kernel(int64_t B, int K, int* counters, int64_t ca
         if ((mask >> k) & 1) {
             slot = wcnt[warp][k] + __popc(bal[k] & ((1u << lane) - 1));
             if (slot >= cap) {
+                // slot capacity exceeded (more (row, sub-module) pairs than B x max_multiplicity): the contribution cannot be
+                // computed.  Loud in the data - combine_kernel turns the row into NaN, which the reference's Runner rejects
+                // (runner.py:260-261) - and in the sticky status word (MN_ERR_WORKSPACE at the next mn_check_status).
                 atomicOr(status, MN_STATUS_OVERFLOW);
-                slot = -1;
+                slot = -2;
             } else {
                 slot_row[slot] = (int)row;
                 if (slot_w) slot_w[slot] = w_in[(int64_t)k * B + row];
@@ -186,6 +189,7 @@ __global__ void combine_kernel(int64_t B, int K, const int* __restrict__ row_slo
     for (int k = 0; k < K; ++k) {  // ascending sub-module order (mega_nerf.py:34,49)
         const int slot = row_slots[row * K + k];
         if (slot >= 0) acc = acc + slot_out[(int64_t)slot * out_cols + c];
+        else if (slot == -2) acc = __int_as_float(0x7fc00000);   // dropped contribution (capacity overflow): poison, never a silent wrong blend
     }
     out[i] = acc;
 }

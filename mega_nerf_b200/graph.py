@@ -33,6 +33,21 @@ class GraphedRenderRays:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.results: Optional[Dict[str, torch.Tensor]] = None
         self.warmup = warmup
+        net = nerf.module if hasattr(nerf, 'module') and not hasattr(nerf, '_native') else nerf
+        self._native = net._native()
+        self._params = [p for sub in self._native.subs for p in sub.parameters()]
+        self._versions = -1
+
+    def _weights_version(self) -> int:
+        return sum(p._version for p in self._params)
+
+    def refresh_weights(self) -> None:
+        """Re-pack the native weight images (in place: the captured graph reads the same device buffers) if a parameter
+        changed since the last pack - e.g. an optimiser step between two validation renders.  Called by every replay."""
+        v = self._weights_version()
+        if v != self._versions:
+            self._native.sync(self.rays.device)
+            self._versions = v
 
     def _run(self) -> Dict[str, torch.Tensor]:
         with torch.no_grad():      # inference path only (a recording call would switch to the fp32 training kernels)
@@ -61,10 +76,12 @@ class GraphedRenderRays:
         # thread_local: other threads of the process (e.g. the NCCL watchdog polling its events) must not invalidate the capture
         with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
             self.results = self._run()
+        self._versions = self._weights_version()
 
     def __call__(self, rays: torch.Tensor, image_indices: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
         if self.graph is None:
             self.capture(rays, image_indices)
+        self.refresh_weights()
         self._load(rays, image_indices)
         self.graph.replay()
         return self.results

@@ -108,6 +108,24 @@ class _Native:
         self.device = None
         self.stamp = None
         self.keep = []
+        self.max_multiplicity = None      # None: the library's geometric default (mn_model_create)
+
+    def invalidate(self):
+        """Force a re-pack of the native weights at the next call.  Needed only after updates that bypass autograd's
+        version counters (`p.data.copy_(...)`, writes through raw pointers); everything else - optimiser steps,
+        `load_state_dict`, in-place ops on the parameters - is detected through `p._version`."""
+        self.stamp = None
+
+    def _validate(self):
+        """All sub-modules of one native model share ONE layout (mn_model_desc is taken from sub-module 0)."""
+        ref = {k: tuple(v.shape) for k, v in self.subs[0].state_dict().items()}
+        for i, sub in enumerate(self.subs[1:], 1):
+            got = {k: tuple(v.shape) for k, v in sub.state_dict().items()}
+            if got != ref:
+                bad = sorted(k for k in set(ref) | set(got) if ref.get(k) != got.get(k))
+                raise RuntimeError(f'mega_nerf_b200: sub-module {i} differs from sub-module 0 in {bad[:4]} '
+                                   f'(e.g. {bad[0]}: {got.get(bad[0])} vs {ref.get(bad[0])}); all sub-modules of a '
+                                   'MegaNeRF / Cascade must have identical shapes')
 
     def __del__(self):
         try:
@@ -140,10 +158,13 @@ class _Native:
                 self.handle = None
             d = model_desc(first, self.kind, len(self.subs), self.margin, self.xyz_real, self.cluster_dim_start)
             out = C.c_void_p()
+            self._validate()
             K.check(L.mn_model_create(h, C.byref(d), C.byref(out)), h)
             self.handle = out.value
             self.device = device
             self.stamp = None
+            if self.max_multiplicity is not None:
+                K.check(L.mn_model_set_max_multiplicity(self.handle, int(self.max_multiplicity)), h)
         stamp = self._stamp()
         if stamp != self.stamp:
             keep = []
@@ -316,7 +337,23 @@ def _module_forward(native: _Native, x, use_coarse: bool, sigma_only: bool, sigm
     return native.forward(rows, B, device, use_coarse, sigma_only, sigma_noise, out_cols, keep)
 
 
-class NeRF(nn.Module):
+class _NativeOwner:
+    """Mixin of the three network classes: the native handle is process-local state, never copied or pickled
+    (copy.deepcopy / pickle / torch.save of a module that has already run would otherwise duplicate the raw handle
+    and free it twice)."""
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_native_obj'] = None
+        return state
+
+    def invalidate_native_weights(self) -> None:
+        """Re-pack the native weights at the next call (see _Native.invalidate)."""
+        if self.__dict__.get('_native_obj') is not None:
+            self._native_obj.invalidate()
+
+
+class NeRF(_NativeOwner, nn.Module):
     """models/nerf.py:45-113 (constructor) / :115-160 (forward)."""
 
     def __init__(self, pos_xyz_dim: int, pos_dir_dim: int, layers: int, skip_layers: List[int], layer_dim: int,
@@ -378,7 +415,7 @@ class NeRF(nn.Module):
         return _module_forward(self._native(), x, True, sigma_only, sigma_noise, self.rgb_dim)
 
 
-class MegaNeRF(nn.Module):
+class MegaNeRF(_NativeOwner, nn.Module):
     """models/mega_nerf.py:7-61."""
 
     def __init__(self, sub_modules: List[nn.Module], centroids: torch.Tensor, boundary_margin: float, xyz_real: bool,
@@ -401,11 +438,21 @@ class MegaNeRF(nn.Module):
         self._native_obj.centroids = self.centroids
         return self._native_obj
 
+    def set_max_multiplicity(self, n: int) -> None:
+        """Sub-modules per sample the routing slot capacity is sized for (blending only).  The default covers regular
+        centroid grids (4 for 2-D clustering, 8 for 3-D, all sub-modules for boundary_margin >= 2.2); raise it for
+        irregular layouts.  Exceeding it never blends silently wrong: the affected rows become NaN and the next
+        status check raises."""
+        nat = self._native()
+        nat.max_multiplicity = int(n)
+        if nat.handle is not None:
+            K.check(K.lib().mn_model_set_max_multiplicity(nat.handle, int(n)), K.ctx(nat.device))
+
     def forward(self, x, sigma_only: bool = False, sigma_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         return _module_forward(self._native(), x, True, sigma_only, sigma_noise, self.sub_modules[0].rgb_dim)
 
 
-class Cascade(nn.Module):
+class Cascade(_NativeOwner, nn.Module):
     """models/cascade.py:7-18."""
 
     def __init__(self, coarse: nn.Module, fine: nn.Module):

@@ -25,11 +25,22 @@ def _rays(directions: torch.Tensor, c2w: torch.Tensor, near: float, far: float, 
     d = K.f32c(directions)
     m = K.f32c(c2w.to(dev))
     n_poses = m.shape[0] if batched else 1
-    P = d.numel() // 3 // (n_poses if batched else 1)
-    out = torch.empty(*d.shape[:-1], 8, device=dev, dtype=torch.float32)
+    # batched poses with ONE shared direction table [P,3] (the only shape the reference's loader passes,
+    # filesystem_dataset.py:118): `directions @ c2w[:, :, :3].transpose(1, 2)` broadcasts to [n,P,3]
+    shared_dirs = batched and d.dim() == 2
+    if batched and not shared_dirs and d.shape[0] != n_poses:
+        if d.shape[0] != 1:
+            raise RuntimeError(f'get_rays_batch: directions {tuple(d.shape)} do not broadcast against {n_poses} poses')
+        d, shared_dirs = d[0], True
+    if shared_dirs:
+        P = d.shape[0]
+        out = torch.empty(n_poses, P, 8, device=dev, dtype=torch.float32)
+    else:
+        P = d.numel() // 3 // n_poses
+        out = torch.empty(*d.shape[:-1], 8, device=dev, dtype=torch.float32)
     has_alt = ray_altitude_range is not None
-    K.check(K.lib().mn_rays(h, K.ptr(d), int(batched), K.ptr(m), n_poses, P, float(near), float(far), int(has_alt),
-                            float(ray_altitude_range[0]) if has_alt else 0.0,
+    K.check(K.lib().mn_rays(h, K.ptr(d), int(batched and not shared_dirs), K.ptr(m), n_poses, P, float(near), float(far),
+                            int(has_alt), float(ray_altitude_range[0]) if has_alt else 0.0,
                             float(ray_altitude_range[1]) if has_alt else 0.0, K.ptr(out), K.stream_of(dev)), h)
     return out
 
@@ -42,5 +53,5 @@ def get_rays(directions: torch.Tensor, c2w: torch.Tensor, near: float, far: floa
 
 def get_rays_batch(directions: torch.Tensor, c2w: torch.Tensor, near: float, far: float,
                    ray_altitude_range: List[float]) -> torch.Tensor:
-    """[n,P,3] x [n,3,4] -> [n,P,8]  (ray_utils.py:33-41)."""
+    """[n,P,3] or [P,3] x [n,3,4] -> [n,P,8]  (ray_utils.py:33-41; the loader passes [P,3], filesystem_dataset.py:118)."""
     return _rays(directions, c2w, near, far, ray_altitude_range, True)

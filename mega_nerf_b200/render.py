@@ -339,13 +339,28 @@ def _render(net, bg, rays, image_indices, hparams, sphere_center, sphere_radius,
                     res[f'fg_{name}'] = val
                     res[f'bg_{name}'] = torch.zeros_like(val)
     present = bool(bg is not None and with_bg.shape[0] > 0)
-    if bg is not None and not present and 'RANK' in os.environ and net.training and bg._native().needs_grad():
-        # Distributed training with no background ray in this batch: the reference renders one dummy background
-        # ray and adds 0 x its colour (rendering.py:143-171) so that every bg parameter still takes part in the
-        # backward pass (all-zero gradients) and the optimiser steps on every rank.  Same effect, without the render:
+    if bg is not None and not present and 'RANK' in os.environ and net.training:
+        # Distributed training with no background ray in this batch (rendering.py:143-171): the reference renders ONE
+        # dummy background ray through bg_nerf - i.e. through its DistributedDataParallel wrapper, whose forward is
+        # what arms the gradient reducer for this iteration - and adds 0 x its colour, so that this rank joins the
+        # bg all-reduce with all-zero gradients and the optimiser steps on every rank.  Same here, through `call_bg`;
+        # the random draws (jitter, density noise, resampling) are consumed in the reference's order.
+        half = S // 2
+        bz1 = torch.linspace(0, 1, half, device=dev)
+        rnd = torch.rand(1, half, device=dev) if perturb > 0 else None
+        bz = sg.stratify(bz1, rnd, perturb, 1, half)
+        real = hparams.train_mega_nerf is not None                       # rendering.py:147 (no container_path here)
+        c2d = real and net.cluster_dim_start == 1
+        first = torch.zeros(1, device=dev, dtype=with_bg.dtype)
+        mk = lambda zz: sg.points_outside(rays, first, zz, center, radius, real, c2d)
+        bpts, breal = mk(bz)
+        dummy = _two_pass(sg, bg, hparams, rays[:1, 3:6], idx[:1].contiguous() if idx is not None else None, bpts, bz,
+                          torch.ones(1, device=dev, dtype=torch.float32), get_depth, get_depth_variance, False, True,
+                          breal, mk, call_bg)
         key = f'rgb_{"fine" if hparams.fine_samples > 0 else "coarse"}'
-        touch = sum(p.sum() for p in bg.parameters() if p.requires_grad)
-        res[key] = res[key] + 0 * touch
+        # `results[key][:0] += 0 * grad_results[key]`: an EMPTY slice - the values never mix (a non-finite dummy colour
+        # cannot poison the batch), only the graph edge to the bg parameters is added
+        res[key] = torch.cat([res[key], (0 * dummy[key])[:0]], 0)
         present = True
     return res, present
 

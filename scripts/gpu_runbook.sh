@@ -8,8 +8,8 @@ G=/usr/local/graft/bin/gpurun
 case "${1:-help}" in
   tests)        # the whole GPU suite, most-verified files first (the driver runs the same with -x)
     $G --timeout 900 -- 'python -m pytest tests -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1; tail -40 gpurun_out/gpu_tests.log' ;;
-  staging)      # the GPU tests written without hardware access (train-mode parity, fused render, expert parallel, kernel variants)
-    $G --timeout 900 -- 'MN_GPU_STAGING=1 python -m pytest tests/test_gpu_zea_train_mode.py tests/test_gpu_zf_fused_render.py tests/test_gpu_zg_expert_parallel.py tests/test_gpu_zh_kernel_variants.py -q --tb=short -p no:cacheprovider > gpurun_out/staging_tests.log 2>&1; tail -60 gpurun_out/staging_tests.log' ;;
+  staging)      # (historic name) the four GPU test files first run on hardware in round 2 - now part of the default suite
+    $G --timeout 900 -- 'python -m pytest tests/test_gpu_zea_train_mode.py tests/test_gpu_zf_fused_render.py tests/test_gpu_zg_expert_parallel.py tests/test_gpu_zh_kernel_variants.py -q --tb=short -p no:cacheprovider > gpurun_out/staging_tests.log 2>&1; tail -60 gpurun_out/staging_tests.log' ;;
   bench)        # graded line (+ gpu_incumbent), reference arm, training and cluster diagnostics
     $G --timeout 900 -- 'python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -1 gpurun_out/bench_n1.json;
                          python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null;

@@ -13,7 +13,7 @@ import mega_nerf_b200 as M
 from mega_nerf_b200 import _cabi as K
 from oracle import mn_oracle as O
 import cases as Cs
-from test_gpu_parity import product_net
+from mega_nerf_b200.synthetic import build_net
 from bench import flops_per_row
 
 width = int(sys.argv[1]) if len(sys.argv) > 1 else 256
@@ -23,7 +23,7 @@ spec = O.NerfSpec(layer_dim=width)
 net = O.make_net('nerf', spec, seed=3)
 n = 148 * 128 * tps
 x = Cs.nerf_rows(spec, 4096, 9).repeat(n // 4096 + 1, 1)[:n].contiguous().to(dev)
-p = product_net(net)
+p = build_net(net, dev)
 M.set_precision(os.environ.get('MN_B200_PRECISION', 'tc_f16'))
 L, h = K.lib(), K.ctx(dev)
 for _ in range(3):

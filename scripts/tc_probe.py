@@ -21,13 +21,13 @@ def child():
     import mega_nerf_b200 as M
     from oracle import mn_oracle as O
     import cases as C
-    from test_gpu_parity import product_net
+    from mega_nerf_b200.synthetic import build_net
     dev = torch.device('cuda:0')
     for cfg in CONFIGS:
         spec = O.NerfSpec(layer_dim=cfg['layer_dim'], layers=cfg['layers'], skip_layers=cfg['skip_layers'])
         net = O.make_net('nerf', spec, seed=3)
         x = C.nerf_rows(spec, cfg['n'], 9)
-        p = product_net(net)
+        p = build_net(net, dev)
         for so in (True, False):
             xin = (C.nerf_rows(spec, cfg['n'], 9, sigma_only=True) if so else x).to(dev)
             M.set_precision('fp32')

@@ -12,7 +12,7 @@ import mega_nerf_b200 as M
 from mega_nerf_b200 import _cabi as K
 from oracle import mn_oracle as O
 import cases as Cs
-from test_gpu_parity import product_net
+from mega_nerf_b200.synthetic import build_net
 
 dev = torch.device('cuda:0')
 WIDTH = int(os.environ.get('TRACE_WIDTH', '256'))
@@ -20,7 +20,7 @@ spec = O.NerfSpec(layer_dim=WIDTH)
 net = O.make_net('nerf', spec, seed=3)
 n = 148 * 128 * (8 if WIDTH == 256 else 4)
 x = Cs.nerf_rows(spec, n, 9).to(dev)
-p = product_net(net)
+p = build_net(net, dev)
 M.set_precision('tc_f16')
 lib = K.lib()
 lib.mn_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]

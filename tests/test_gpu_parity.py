@@ -38,26 +38,14 @@ def relerr(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 def product_nerf(spec: O.NerfSpec, w):
-    m = M()
-    net = m.NeRF(spec.pos_xyz_dim, spec.pos_dir_dim, spec.layers, list(spec.skip_layers), spec.layer_dim,
-                 spec.appearance_dim, spec.affine_appearance, spec.appearance_count, spec.rgb_dim, spec.xyz_dim,
-                 m.ShiftedSoftplus() if spec.shifted_softplus else torch.nn.ReLU())
-    net.load_state_dict(w)
-    return net
+    from mega_nerf_b200.synthetic import nerf_from_spec
+    return nerf_from_spec(spec, w)
 
 
 def product_net(net: O.Net):
-    m = M()
-    subs = [product_nerf(net.spec, w) for w in net.weights]
-    if net.kind == 'nerf':
-        out = subs[0]
-    elif net.kind == 'cascade':
-        out = m.Cascade(subs[0], subs[1])
-    else:
-        out = m.MegaNeRF(subs, net.centroids.clone(), net.boundary_margin, net.xyz_real, net.cluster_2d)
-    # inference parity: frozen parameters, so that calls outside no_grad are not recorded for backward (the
-    # recording path always runs the fp32 kernels, tests/test_gpu_zc_backward.py)
-    return out.to(DEV).eval().requires_grad_(False)
+    """The product network with the oracle net's weights (mega_nerf_b200/synthetic.py), frozen, in eval mode."""
+    from mega_nerf_b200.synthetic import build_net
+    return build_net(net, DEV)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -74,6 +62,9 @@ def test_raygen(golden):
         assert r.shape == g.shape and relerr(r, g) <= 5e-7, tag
         rb = m.get_rays_batch(dirs.view(1, -1, 3).expand(4, -1, -1).contiguous().to(DEV), c2w.to(DEV), 0.1, 3.0, alt)
         assert relerr(rb, golden[f'rays_batch_{tag}']) <= 5e-7, tag
+        # the shape the reference's loader passes (filesystem_dataset.py:118): ONE [P,3] direction table, n poses
+        rs = m.get_rays_batch(dirs.view(-1, 3).to(DEV), c2w.to(DEV), 0.1, 3.0, alt)
+        assert rs.shape == golden[f'rays_batch_{tag}'].shape and relerr(rs, golden[f'rays_batch_{tag}']) <= 5e-7, tag
 
 
 def test_embed(golden):

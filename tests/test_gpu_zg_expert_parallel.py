@@ -13,10 +13,8 @@ import torch.distributed as dist
 import cases as C
 from test_gpu_parity import DEV, M, product_net, relerr
 
-# Staging: written after the round's GPU budget was spent, never run on hardware.  Skipped by default so that the graded
-# `pytest -m gpu` run reports the verified suite; `MN_GPU_STAGING=1` (scripts/gpu_runbook.sh staging) runs them.
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(__import__('os').environ.get('MN_GPU_STAGING') != '1',
-                                                    reason='staging test, not yet run on hardware: set MN_GPU_STAGING=1')]
+# (first run on a B200 in round 2: all green, see profiles/r2_staging_tests.log)
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope='module')
