@@ -1,7 +1,7 @@
 """Builds mega_nerf_b200 networks from a plain description (spec attributes + per-sub-module state dicts).
 
-Used by bench.py, __graft_entry__.smoke() and the GPU tests to instantiate the SAME seeded random-init weights the
-oracle / the reference were given (there are no datasets or checkpoints on the GPU box).  Nothing here computes:
+Used by bench.py, __graft_entry__.smoke() and the GPU tests to instantiate the SAME seeded random-init weights the CPU checker /
+the reference were given (there are no datasets or checkpoints on the GPU box).  Nothing here computes:
 it is `NeRF(...)` / `MegaNeRF(...)` / `Cascade(...)` + `load_state_dict`.  `net` is duck-typed: any object with
 `kind` ('nerf' | 'cascade' | 'mega'), `spec` (the NeRF constructor arguments of models/nerf.py:46-49 as attributes),
 `weights` (list of state dicts with the reference's parameter names) and, for 'mega', `centroids`, `boundary_margin`,
