@@ -9,9 +9,12 @@ A "step" is one render_rays() pass over one batch of synthetic rays: BASELINE.js
 With N > 1 (torchrun, one rank per GPU) rays are sharded: every rank renders its own 4096 rays with
 replicated weights and the per-ray results (rgb + depth) are all-gathered over NCCL each step (weak scaling).
 
+With N > 1 the per-GPU batch is BASELINE configs[2]'s shard (65 536 rays / 8 = 8192 rays per GPU) instead of configs[1]'s 4096.
+
 Prints ONE JSON line on rank 0 (see the task contract): value = ray-samples/s with inputs resident in HBM
 (device-timed with CUDA events), e2e = the same through the public API from pinned host buffers including
-H2D/D2H, roofline for the dominant (MLP) kernel, cpu_baseline = the oracle port timed on the host cores.
+H2D/D2H, roofline for the dominant (MLP) kernel, cpu_baseline = the UNMODIFIED reference (baseline/_ref, see
+baseline/README.md; `kind: "reference"`) timed on the host cores - the oracle port (`kind: "port"`) when _ref is absent.
 """
 from __future__ import annotations
 
@@ -38,6 +41,9 @@ MARGIN = 1.15
 WORKLOADS = {
     'c2': dict(desc='BASELINE configs[1]: mega-nerf 8-submodule 256-ch', rays=4096, spec={}, grid=(2, 4), sh_deg=None,
                kernel='tc_mlp_pp_kernel'),
+    # configs[2]: 65 536 rays per iteration over 8 GPUs = 8192 rays per GPU; the default when N > 1
+    'c3': dict(desc='BASELINE configs[2] shard: mega-nerf 8-submodule 256-ch, 65536 rays / 8 GPUs', rays=8192, spec={}, grid=(2, 4),
+               sh_deg=None, kernel='tc_mlp_pp_kernel'),
     'c4': dict(desc='BASELINE configs[3] shape: mega-nerf 25-submodule 512-ch', rays=4096, spec=dict(layer_dim=512), grid=(5, 5),
                sh_deg=None, kernel='tc_mlp_wide_kernel'),
     'c5': dict(desc='BASELINE configs[4]: mega-nerf-sh-3 (SH degree 2 head) 8-submodule 256-ch', rays=8192,
@@ -61,6 +67,81 @@ def peaks():
     return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, src='fallback')
 
 
+# ------------------------------------------------------------------------------------------------
+# The unmodified reference (baseline/_ref/mega_nerf, a copy of /root/reference/mega_nerf made by baseline/make_ref.py)
+# ------------------------------------------------------------------------------------------------
+_REF = None
+
+
+def load_reference():
+    """-> namespace with the reference's own render_rays / NeRF / MegaNeRF / Cascade / ShiftedSoftplus, or None."""
+    global _REF
+    if _REF is not None:
+        return _REF or None
+    ref_root = os.path.join(ROOT, 'baseline', '_ref')
+    if os.environ.get('MN_BENCH_NO_REF') == '1' or not os.path.isdir(os.path.join(ref_root, 'mega_nerf')):
+        _REF = False
+        return None
+    try:
+        sys.path.insert(0, ref_root)
+        from mega_nerf.rendering import render_rays
+        from mega_nerf.models.nerf import NeRF, ShiftedSoftplus
+        from mega_nerf.models.mega_nerf import MegaNeRF
+        from mega_nerf.models.cascade import Cascade
+        import mega_nerf
+        _REF = Namespace(render_rays=render_rays, NeRF=NeRF, ShiftedSoftplus=ShiftedSoftplus, MegaNeRF=MegaNeRF,
+                         Cascade=Cascade, path=os.path.dirname(mega_nerf.__file__))
+    except Exception as e:  # noqa: BLE001
+        log(f'baseline/_ref present but not importable ({e!r}); falling back to the oracle port')
+        _REF = False
+    finally:
+        if ref_root in sys.path:
+            sys.path.remove(ref_root)
+    return _REF or None
+
+
+def reference_net(R, net, device='cpu'):
+    """The reference's own modules (models/nerf.py:45, mega_nerf.py:7, cascade.py:7) holding the workload's weights."""
+    spec = net.spec
+    subs = []
+    for w in net.weights:
+        m = R.NeRF(spec.pos_xyz_dim, spec.pos_dir_dim, spec.layers, list(spec.skip_layers), spec.layer_dim, spec.appearance_dim,
+                   spec.affine_appearance, spec.appearance_count, spec.rgb_dim, spec.xyz_dim,
+                   R.ShiftedSoftplus() if spec.shifted_softplus else torch.nn.ReLU())
+        m.load_state_dict(w)
+        subs.append(m)
+    if net.kind == 'nerf':
+        out = subs[0]
+    elif net.kind == 'cascade':
+        out = R.Cascade(subs[0], subs[1])
+    else:
+        out = R.MegaNeRF(subs, net.centroids.clone(), net.boundary_margin, net.xyz_real, net.cluster_2d)
+    return out.to(device).eval()
+
+
+def cpu_renderer(O, net, opts):
+    """-> (fn(rays, idx) -> results, kind): the reference itself when baseline/_ref is there, else the oracle port."""
+    R = load_reference()
+    if R is not None:
+        rnet, hp = reference_net(R, net), Namespace(**vars(opts))
+        return (lambda r, i: R.render_rays(rnet, None, r, i, hp, None, None, True, False, False)[0]), 'reference'
+    return (lambda r, i: O.render_rays(net, None, r, i, opts, None, None, True, False, False)[0]), 'port'
+
+
+def kernel_traffic(kernel: str, workload_name: str, precision: str):
+    """DRAM traffic per launch of `kernel` from the committed ncu capture of this workload (profiles/kernel_traffic.json)."""
+    p = os.path.join(ROOT, 'profiles', 'kernel_traffic.json')
+    if not os.path.exists(p):
+        return None
+    try:
+        for e in json.load(open(p)):
+            if e['kernel'] == kernel and e['workload'] == workload_name and e['precision'] == precision:
+                return e
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def workload(seed_shift: int = 0):
     from oracle import mn_oracle as O
     spec = O.NerfSpec(**WL['spec'])
@@ -71,6 +152,12 @@ def workload(seed_shift: int = 0):
     opts = O.RenderOpts(coarse_samples=COARSE, fine_samples=FINE, use_cascade=False, perturb=1.0, pos_dir_dim=spec.pos_dir_dim,
                         sh_deg=WL['sh_deg'], model_chunk_size=32 * 1024)
     return spec, net, rays, idx, opts
+
+
+def workload_string() -> str:
+    """Identical in both arms (the driver compares the strings)."""
+    return (f'{WL["desc"]}, {N_RAYS} rays x ({COARSE} coarse + {FINE} fine) samples per GPU, boundary_margin {MARGIN}, '
+            'random-init weights, synthetic rays')
 
 
 def flops_per_row(spec) -> int:
@@ -136,23 +223,26 @@ def usable_cpus() -> int:
     return max(1, n)
 
 
-def cpu_rays_per_sec(O, net, rays, idx, opts, n_probe: int = 64) -> float:
-    """Quick probe of the oracle's speed on this host, used to bound the timed CPU samples."""
+def cpu_rays_per_sec(render, rays, idx, n_probe: int = 64) -> float:
+    """Quick probe of the CPU renderer's speed on this host, used to bound the timed CPU samples."""
     with torch.inference_mode():
-        O.render_rays(net, None, rays[:n_probe], idx[:n_probe], opts, None, None, True, False, False)
+        render(rays[:n_probe], idx[:n_probe])
         t0 = time.perf_counter()
-        O.render_rays(net, None, rays[:n_probe], idx[:n_probe], opts, None, None, True, False, False)
+        render(rays[:n_probe], idx[:n_probe])
         return n_probe / (time.perf_counter() - t0)
 
 
 def run_reference(args, rank: int):
-    """The reference algorithm (oracle port of /root/reference, see oracle/mn_oracle.py) on the host CPU."""
+    """The reference's own CPU implementation of the path on the host cores: the unmodified mega_nerf.rendering.render_rays
+    + mega_nerf.models from baseline/_ref (kind "reference"); the oracle port of it (oracle/mn_oracle.py, kind "port") only
+    when _ref is absent."""
     if rank != 0:
         return
     from oracle import mn_oracle as O
     torch.set_num_threads(usable_cpus())
     spec, net, rays, idx, opts = workload()
-    rate = cpu_rays_per_sec(O, net, rays, idx, opts)
+    render, kind = cpu_renderer(O, net, opts)
+    rate = cpu_rays_per_sec(render, rays, idx)
     # bounded sample: the whole --steps/--warmup run should take about two minutes of CPU time
     sample = int(min(N_RAYS, max(64, rate * 120.0 / (args.steps + args.warmup)))) // 64 * 64
     r, i = rays[:sample], idx[:sample]
@@ -160,7 +250,7 @@ def run_reference(args, rank: int):
     with torch.inference_mode():
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            O.render_rays(net, None, r, i, opts, None, None, True, False, False)
+            render(r, i)
             if s >= args.warmup:
                 times.append(time.perf_counter() - t0)
     tot = sum(times)
@@ -169,10 +259,11 @@ def run_reference(args, rank: int):
         'impl': 'reference', 'metric': 'ray-samples/sec (MLP+composite)', 'value': value, 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{WL["desc"]}, {N_RAYS} rays x ({COARSE}+{FINE}) samples, margin {MARGIN}; '
-                               f'each CPU step renders a {sample}-ray sample of it'},
-        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                         'sample': f'{sample} of {N_RAYS} rays per step, {args.steps} steps'},
+        'config': {'workload': workload_string(), 'cpu_sample': f'each CPU step renders a {sample}-ray sample of it'},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': kind,
+                         'sample': f'{sample} of {N_RAYS} rays per step, {args.steps} steps',
+                         'what': ('unmodified mega_nerf.rendering.render_rays + mega_nerf.models (baseline/_ref), torch CPU fp32, '
+                                  'inference_mode' if kind == 'reference' else 'oracle port (baseline/_ref absent)')},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -180,15 +271,23 @@ def run_reference(args, rank: int):
 
 
 def gpu_incumbent(O, net, rays_d, idx_d, opts, dev, steps: int = 5):
-    """SURVEY.md §8d "GPU incumbent": the reference algorithm as PyTorch eager ops on the SAME B200 (the oracle
-    restatement moved to CUDA: cuBLAS GEMMs + ~10^3 elementwise launches per step) in the three precisions the
-    reference can run in - fp32, TF32, and autocast fp16 (its default, runner.py:243).  A baseline leg like
-    cpu_baseline: reported next to the product's number, never on the product path.  Any failure is reported, not raised."""
-    out = {'kind': 'port (oracle restatement under torch-CUDA eager, same GPU)', 'unit': 'samples/s', 'steps': steps}
+    """SURVEY.md §8d "GPU incumbent": the UNMODIFIED reference (baseline/_ref: mega_nerf.rendering.render_rays over
+    mega_nerf.models, i.e. cuBLAS GEMMs + ~10^3 ATen elementwise launches per step) through torch-CUDA on the SAME B200
+    in the three precisions it can run in - fp32, TF32, and autocast fp16 (its default, runner.py:243); the oracle
+    restatement moved to CUDA when _ref is absent.  A baseline leg like cpu_baseline: reported next to the product's
+    number, never on the product path.  Any failure is reported, not raised."""
+    R = load_reference()
+    out = {'kind': 'reference (baseline/_ref under torch-CUDA eager, same GPU)' if R is not None else
+                   'port (oracle restatement under torch-CUDA eager, same GPU)', 'unit': 'samples/s', 'steps': steps}
     try:
-        netd = O.net_to(net, dev)
         n = rays_d.shape[0]
         samples = n * (opts.coarse_samples + opts.fine_samples)
+        if R is not None:
+            rnet, hp = reference_net(R, net, dev), Namespace(**vars(opts))
+            render = lambda: R.render_rays(rnet, None, rays_d, idx_d, hp, None, None, True, False, False)   # noqa: E731
+        else:
+            netd = O.net_to(net, dev)
+            render = lambda: O.render_rays(netd, None, rays_d, idx_d, opts, None, None, True, False, False)  # noqa: E731
         saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
         for name, tf32, amp in (('fp32', False, False), ('tf32', True, False), ('amp_fp16', True, True)):
             torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -196,7 +295,7 @@ def gpu_incumbent(O, net, rays_d, idx_d, opts, dev, steps: int = 5):
 
             def step():
                 with torch.inference_mode(), torch.autocast('cuda', dtype=torch.float16, enabled=amp):
-                    O.render_rays(netd, None, rays_d, idx_d, opts, None, None, True, False, False)
+                    render()
             for _ in range(2):
                 step()
             torch.cuda.synchronize()
@@ -394,7 +493,8 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('MN_B200_PRECISION', 'tc_f16'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-incumbent', action='store_true', help='skip timing the restatement under torch-CUDA eager')
-    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS),
+                    help="default: 'c2' (BASELINE configs[1], 4096 rays) on one GPU, 'c3' (configs[2]: 8192 rays per GPU) when N > 1")
     ap.add_argument('--no-graph', action='store_true', help='issue every step eagerly instead of replaying a CUDA graph')
     ap.add_argument('--margin', type=float, default=MARGIN, help='boundary_margin of the mixture: 1.15 = reference eval default (graded), '
                                                                  '1.0 = hard routing, m = 1 (SURVEY.md §8d)')
@@ -409,13 +509,14 @@ def main():
                          "workload through the recording path (SURVEY.md §8f-1); 'cluster' = the cluster-mask kernel on one "
                          "48k-ray chunk x 1000 samples (SURVEY.md §8f-3); both diagnostics only")
     args = ap.parse_args()
-    select_workload(args.workload)
-    globals()['MARGIN'] = args.margin
-    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
-
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.workload is None:
+        args.workload = 'c2' if max(world, args.gpus) == 1 else 'c3'
+    select_workload(args.workload)
+    globals()['MARGIN'] = args.margin
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
         run_reference(args, rank)
         return
@@ -479,7 +580,8 @@ def main():
         if graphed is None:
             return step_eager()
         res = graphed(rays_d, idx_d)                 # device-resident inputs -> static buffers (D2D) -> graph replay
-        exchange(res)
+        if graphed.post is None:
+            exchange(res)
         return res
 
     def step_e2e():
@@ -490,7 +592,7 @@ def main():
         else:
             res = graphed(rays_pin, idx_pin)         # pinned host inputs -> static device buffers (H2D) -> graph replay
         packed = torch.cat([res['rgb_fine'], res['depth_fine'].unsqueeze(-1)], -1)
-        if world > 1:
+        if world > 1 and not (graphed is not None and graphed.post is not None):
             if pg is not None:
                 pg.gather(res['rgb_fine'], res['depth_fine'], rank * N_RAYS)
             else:
@@ -526,7 +628,9 @@ def main():
     launches_per_step = L.mn_launch_count(h) - launches0      # kernels of ours per step (the graph replays the same list)
     if not args.no_graph:
         try:
-            graphed = M.GraphedRenderRays(model, hp, N_RAYS, dev, with_indices=True, get_depth=True)
+            # the per-step exchange (pack + all-gather) is captured with the render: one graph launch per step at any N
+            graphed = M.GraphedRenderRays(model, hp, N_RAYS, dev, with_indices=True, get_depth=True,
+                                          post=exchange if (world > 1 and pg is None) else None)
             graphed.capture(rays_d, idx_d)
             for _ in range(args.warmup):
                 step_resident()
@@ -560,41 +664,81 @@ def main():
     K.check(L.mn_profile_read(h, C.byref(tot_ms), C.byref(n_l)), h)
     K.check(L.mn_profile_enable(h, 0), h)
     clocks = sampler.stop() if rank == 0 else None      # sampled over the resident, e2e and kernel-timing sections
-    slots, tiles = (model._ep.last_pairs, 0) if experts else nat.stats(dev)                # of the last (fine) pass
-    rows_fine = N_RAYS * FINE
-    mult = slots / rows_fine
+
+    def pairs_of_last_query():
+        # routed (sample, sub-module) pairs of the most recent model query, read back from the device counters
+        return model._ep.last_pairs if experts else nat.stats(dev)[0]
+    pairs_fine = pairs_of_last_query()                    # the last query of a step is the fine pass
+    # the coarse pass of the two-pass render issues exactly the query of a coarse-only render of the same rays
+    hp_coarse = Namespace(**{**vars(hp), 'fine_samples': 0})
+    with torch.no_grad():
+        M.render_rays(model, None, rays_d, idx_d, hp_coarse, None, None, True, False, False)
+    pairs_coarse = pairs_of_last_query()
+    m_coarse, m_fine = pairs_coarse / (N_RAYS * COARSE), pairs_fine / (N_RAYS * FINE)
+    mult = (pairs_coarse + pairs_fine) / (N_RAYS * (COARSE + FINE))
     pk = peaks()
     fl_row = flops_per_row(spec)
-    # per step: coarse + fine launches; algorithmic flops = rows * m * flops_row (m measured on the fine pass)
-    flops_step = N_RAYS * (COARSE + FINE) * mult * fl_row
+    # per step: coarse + fine launches; algorithmic flops = routed pairs of BOTH passes (each measured) * flops_row
+    flops_step = (pairs_coarse + pairs_fine) * fl_row
     kernel_ms_per_step = tot_ms.value / args.steps
     achieved = flops_step / (kernel_ms_per_step * 1e-3) / 1e12 if kernel_ms_per_step > 0 else 0.0
     passes = {'fp32': 1, 'tc_f16': 1, 'tc_f16x3': 3}[args.precision]
+    kernel_name = {'fp32': 'mlp_simt_kernel', 'tc_f16': WL['kernel'], 'tc_f16x3': 'tc_mlp_kernel<split>'}[args.precision]
+    traffic = kernel_traffic(kernel_name, args.workload if world == 1 else 'c3', args.precision)
 
     log(f'mlp kernel: {kernel_ms_per_step:.3f} ms/step, m={mult:.3f}')
-    if experts:
-        EP.disable(model)          # the parity sample below runs on rank 0 alone: no collectives allowed there
-    if rank == 0:
-        # parity sample against the oracle (not timed): 256 rays
-        torch.set_num_threads(usable_cpus())
-        with torch.inference_mode():
-            ref, _ = O.render_rays(net, None, rays_h[:256], idx_h[:256], opts, None, None, True, False, False)
-        got, _ = M.render_rays(model, None, rays_d[:256], idx_d[:256], hp, None, None, True, False, False)
-        par = float((got['rgb_fine'].cpu() - ref['rgb_fine']).abs().max() / ref['rgb_fine'].abs().max())
+    # ---- parity against the CPU checker (not timed).  Every rank checks (a) the first N_PAR of its own rays through the
+    # single-GPU call and, when N > 1, (b) its OWN copy of the gathered buffer: the rows of its own segment and of its right
+    # neighbour's segment (that rank's seeded rays are regenerated here); the maxima are all-reduced.
+    N_PAR = 128
+    torch.set_num_threads(max(1, usable_cpus() // max(1, min(world, 8))))
 
-        log(f'parity sample done: {par:.2e}')
+    def check_rows(rays_c, idx_c):
+        with torch.inference_mode():
+            ref, _ = O.render_rays(net, None, rays_c, idx_c, opts, None, None, True, False, False)
+        return ref['rgb_fine'], ref['depth_fine']
+
+    def rel(a, b):
+        return float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max())
+    ref_rgb, ref_depth = check_rows(rays_h[:N_PAR], idx_h[:N_PAR])
+    with torch.no_grad():
+        got, _ = M.render_rays(model, None, rays_d[:N_PAR], idx_d[:N_PAR], hp, None, None, True, False, False)
+    par_rgb, par_depth = rel(got['rgb_fine'], ref_rgb), rel(got['depth_fine'], ref_depth)
+    par_g_rgb = par_g_depth = None
+    if world > 1:
+        step_resident()                                     # one more exchange: every rank holds the buffer of THESE inputs
+        torch.cuda.synchronize()
+        gbuf = (pg.buf if pg is not None else gather_buf).cpu()
+        nb = (rank + 1) % world
+        _, _, rays_nb, idx_nb, _ = workload(seed_shift=nb)
+        nb_rgb, nb_depth = check_rows(rays_nb[:N_PAR], idx_nb[:N_PAR])
+        own, oth = gbuf[rank * N_RAYS: rank * N_RAYS + N_PAR], gbuf[nb * N_RAYS: nb * N_RAYS + N_PAR]
+        t = torch.tensor([max(rel(own[:, :3], ref_rgb), rel(oth[:, :3], nb_rgb)),
+                          max(rel(own[:, 3], ref_depth), rel(oth[:, 3], nb_depth)), par_rgb, par_depth],
+                         device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        par_g_rgb, par_g_depth, par_rgb, par_depth = [float(v) for v in t.tolist()]
+    if experts:
+        EP.disable(model)
+    if rank == 0:
+        log(f'parity: rgb {par_rgb:.2e} depth {par_depth:.2e}' + (f' gathered rgb {par_g_rgb:.2e} depth {par_g_depth:.2e}' if world > 1 else ''))
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            # the reference's own CPU path (baseline/_ref; oracle port when absent) on a bounded sample of the same batch
             torch.set_num_threads(usable_cpus())
-            rate = cpu_rays_per_sec(O, net, rays_h, idx_h, opts)
+            render_cpu, cpu_kind = cpu_renderer(O, net, opts)
+            rate = cpu_rays_per_sec(render_cpu, rays_h, idx_h)
             n_cpu = int(min(N_RAYS, max(64, rate * 15.0))) // 64 * 64         # ~15 s of CPU work
             with torch.inference_mode():
                 t0 = time.perf_counter()
-                O.render_rays(net, None, rays_h[:n_cpu], idx_h[:n_cpu], opts, None, None, True, False, False)
+                ref_out = render_cpu(rays_h[:n_cpu], idx_h[:n_cpu])
                 dt = time.perf_counter() - t0
             cpu = {'value': n_cpu * (COARSE + FINE) / dt, 'unit': 'samples/s', 'cores': torch.get_num_threads(),
-                   'kind': 'port', 'sample': f'first {n_cpu} of the {N_RAYS} rays of the same batch ({dt:.1f} s), after a 64-ray probe'}
-            log(f'cpu baseline: {cpu["value"]:.3e} samples/s on {cpu["cores"]} threads')
+                   'kind': cpu_kind, 'sample': f'first {n_cpu} of the {N_RAYS} rays of the same batch ({dt:.1f} s), after a 64-ray probe'}
+            if cpu_kind == 'reference':
+                # the checker itself against the unmodified reference on this box (bit-exact in the build container)
+                cpu['oracle_vs_reference_max_abs_rgb'] = float((ref_out['rgb_fine'][:N_PAR] - ref_rgb).abs().max())
+            log(f'cpu baseline ({cpu_kind}): {cpu["value"]:.3e} samples/s on {cpu["cores"]} threads')
 
         line = {
             'metric': 'ray-samples/sec (MLP+composite)', 'value': value, 'unit': 'samples/s',
@@ -602,8 +746,10 @@ def main():
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', 'tc_f16': 'f16 operands / f32 accumulate', 'tc_f16x3': 'f16x3 split / f32 accumulate'}[args.precision],
             'data': 'synthetic',
-            'config': {'workload': f'{WL["desc"]}, {N_RAYS} rays x ({COARSE} coarse + {FINE} fine) '
-                                   f'per GPU, boundary_margin {MARGIN} (m = {mult:.3f} sub-modules/sample), random-init weights',
+            'config': {'workload': workload_string(),
+                       'per_gpu_rays': N_RAYS,
+                       'sub_modules_per_sample': {'coarse_pass': m_coarse, 'fine_pass': m_fine, 'step': mult,
+                                                  'how': 'routed (sample, sub-module) pairs of each pass read back from the device counters'},
                        'parallelism': (f'ray-sharded x{world} + owner-computes sub-modules (k mod {world}), 2 all-to-alls per query, '
                                        f'1 all-gather of [rays,4] per step' if experts else
                                        f'ray-sharded x{world}, weights replicated, 1 all-gather of [rays,4] per step'
@@ -617,27 +763,27 @@ def main():
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'tensor',
-                         'kernel': {'fp32': 'mlp_simt_kernel', 'tc_f16': WL['kernel'], 'tc_f16x3': 'tc_mlp_kernel<split>'}[args.precision],
+                         'kernel': kernel_name,
                          'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
                          'frac_of_sustained_peak': achieved / pk['tflops_sustained'] if pk['tflops_sustained'] else None,
                          'peak_source': pk['src'],
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the fine-pass launch (4980 tiles) from
-                         # profiles/r1_tc_mlp_pp_kernel.ncu-rep; algorithmic: 40 KiB feature tile + 2 KiB outputs per tile = 209 MB
-                         'traffic': 229.5e6 if (args.precision == 'tc_f16' and args.workload == 'c2') else None,
-                         'traffic_detail': {'algorithmic_bytes_per_launch': 4980 * (40960 + 2048),
-                                            'launch': 'fine pass, 4980 tiles x 128 rows',
-                                            'source': 'ncu --set full, profiles/'} if args.workload == 'c2' else None,
-                         # second roofline of the same kernel: every 128-row tile re-reads its sub-module's fp16
-                         # weight images (2 B per parameter = fl_row bytes) plus its 40 KiB feature tile from L2; both MLP
-                         # kernels top out near 8 TB/s of L2 -> SM delivery (~32 B/clk/SM), which caps `frac` at ~0.59 (1006 TFLOP/s at 1.68 GHz)
-                         'l2_to_sm': {'bytes_per_step': flops_step / fl_row / 128.0 * (fl_row + 40960.0),
-                                      'achieved_TBps': (flops_step / fl_row / 128.0 * (fl_row + 40960.0)) / (kernel_ms_per_step * 1e-3) / 1e12
-                                      if kernel_ms_per_step > 0 else None,
-                                      'observed_ceiling_TBps': 8.07, 'source': 'l1tex__m_xbar2l1tex_read_bytes, profiles/r1_tc_mlp_pp_kernel.ncu-rep'}
-                         if args.precision == 'tc_f16' else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload, from the committed
+                         # `ncu --set full` capture (profiles/kernel_traffic.json, written by scripts/ncu_extract.py from the
+                         # .ncu-rep next to it); null when no capture of this (kernel, workload, precision) is committed
+                         'traffic': traffic['dram_bytes'] if traffic else None,
+                         'traffic_detail': traffic,
                          'algorithmic_flops_per_row': fl_row, 'mma_passes_per_algorithmic': passes,
                          'kernel_ms_per_step': kernel_ms_per_step, 'launches_per_step': n_l.value / args.steps},
-            'parity': {'max_rel_rgb_vs_oracle_256_rays': par},
+            'parity': {'max_rel_rgb_vs_oracle': par_rgb, 'max_rel_depth_vs_oracle': par_depth, 'rays_checked_per_rank': N_PAR,
+                       'max_rel_rgb_gathered': par_g_rgb, 'max_rel_depth_gathered': par_g_depth,
+                       'gathered_check': (f'every rank compares its own copy of the all-gathered [rays,4] buffer (own segment + right '
+                                          f"neighbour's segment, {N_PAR} rays each) with the CPU oracle; max over the {world} ranks")
+                       if world > 1 else None,
+                       'tolerance': 1e-4, 'pass': bool(max(par_rgb, par_g_rgb or 0.0) <= 1e-4),
+                       'note': ('tc_f16 rounds both MMA operands to fp16 (what the reference itself does on a GPU under autocast): rendered '
+                                'rgb passes the 1e-4 north-star tolerance on this random-init workload with ~2x headroom; tc_f16x3 '
+                                '(3 MMA passes, <= 1e-5 per MLP row) is the parity-grade tensor mode, fp32 the CUDA-core one')
+                       if args.precision == 'tc_f16' else None},
         }
         if cpu is not None:
             line['cpu_baseline'] = cpu

@@ -23,11 +23,16 @@ from .render import render_rays
 
 class GraphedRenderRays:
     def __init__(self, nerf: nn.Module, hparams: Namespace, n_rays: int, device: torch.device, with_indices: bool = True,
-                 get_depth: bool = True, get_depth_variance: bool = False, warmup: int = 2):
+                 get_depth: bool = True, get_depth_variance: bool = False, warmup: int = 2, post=None):
+        """`post(results)`, if given, runs right after render_rays INSIDE the captured region - e.g. the per-chunk
+        exchange of a multi-GPU render (`torch.distributed.all_gather_into_tensor` on NCCL is capturable), so that a
+        step stays one graph launch; whatever it returns is kept in `self.post_result`."""
         if nerf.training:
             raise ValueError('GraphedRenderRays replays the inference path; call nerf.eval() first')
         self.nerf, self.hparams = nerf, hparams
         self.flags = (get_depth, get_depth_variance, False)
+        self.post = post
+        self.post_result = None
         self.rays = torch.zeros(n_rays, 8, device=device, dtype=torch.float32)
         self.indices = torch.zeros(n_rays, device=device, dtype=torch.float32) if with_indices else None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -52,6 +57,8 @@ class GraphedRenderRays:
     def _run(self) -> Dict[str, torch.Tensor]:
         with torch.no_grad():      # inference path only (a recording call would switch to the fp32 training kernels)
             res, _ = render_rays(self.nerf, None, self.rays, self.indices, self.hparams, None, None, *self.flags)
+            if self.post is not None:
+                self.post_result = self.post(res)
         return res
 
     def _load(self, rays: torch.Tensor, image_indices: Optional[torch.Tensor]) -> None:
