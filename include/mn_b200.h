@@ -76,6 +76,16 @@ int mn_ray_directions(mn_ctx* ctx, int W, int H, float fx, float fy, float cx, f
 int mn_rays(mn_ctx* ctx, const float* dirs_d, int dirs_batched, const float* c2w_d, int n_poses, int64_t P,
             float near, float far, int has_altitude, float alt_max, float alt_min, float* out_d, void* stream);
 
+/* The loader's use of get_rays_batch (mega_nerf/datasets/filesystem_dataset.py:109-124): one ray per
+ * (image, pixel) pair of a training chunk.  The reference computes the full [#unique images, #unique pixels, 8] product on
+ * the device, copies it to the host (`.cpu()`, :121) and gathers the pairs there (:125); this entry computes the M pairs only.
+ *   dirs_d [P,3] (the shared direction table, :40-47); c2w_d [n_poses,3,4]; img_idx_d / pix_idx_d int32 [M] (row of c2w_d /
+ *   row of dirs_d); out_d [M,8].  An index outside its table raises MN_ERR_INVALID at the next mn_check_status (the
+ *   reference's fancy indexing raises IndexError) and the ray is NaN. */
+int mn_rays_pairs(mn_ctx* ctx, const float* dirs_d, int64_t P, const float* c2w_d, int n_poses, const int32_t* img_idx_d,
+                  const int32_t* pix_idx_d, int64_t M, float near, float far, int has_altitude, float alt_max, float alt_min,
+                  float* out_d, void* stream);
+
 /* ---- sampling --------------------------------------------------------- mega_nerf/rendering.py */
 /* Coarse depths + optional stratified jitter + points (rendering.py:82-87, 472-483).
  *   rays_d [N,8]; z_steps_d [S] (torch.linspace(0,1,S) — passed in, never restated);

@@ -160,6 +160,8 @@ int mn_check_status(mn_ctx* ctx, void* stream) {
         return mn_fail(ctx, MN_ERR_SPHERE,
                        "Not all your cameras are bounded by the unit sphere; please make sure the cameras are "
                        "normalized properly!");
+    if (h & MN_STATUS_INDEX)
+        return mn_fail(ctx, MN_ERR_INVALID, "index out of range (image / pixel index of a ray pair)");
     if (h & MN_STATUS_OVERFLOW)
         return mn_fail(ctx, MN_ERR_WORKSPACE, "routing slot capacity exceeded (raise max multiplicity)");
     return MN_OK;

@@ -14,6 +14,7 @@
 // device status bits (mn_ctx::status_d)
 #define MN_STATUS_SPHERE 1u
 #define MN_STATUS_OVERFLOW 2u
+#define MN_STATUS_INDEX 4u
 
 #include <vector>
 

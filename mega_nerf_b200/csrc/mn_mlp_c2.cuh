@@ -55,11 +55,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_r
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
     return r;
 }
+// Remote arrive with the DEFAULT semantics (release at CTA scope), the form CUTLASS's ClusterBarrier::arrive(cta_id) uses.
+// `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive - a GPU-scope barrier on the critical
+// path of every epilogue (~1 us under load) - and `.acquire.cluster` waits to a CCTL.IVALL (L1 invalidate) after every
+// successful try_wait of the MMA warp.  Neither is needed here: what crosses the CTA boundary is shared memory written
+// through the generic proxy and already fenced to the async proxy by its writers (fence.proxy.async), read by
+// tcgen05.mma; nothing in global memory is published through these barriers.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA bulk copy into THIS CTA's shared memory, completion signalled on a (possibly remote) cluster barrier address
 __device__ __forceinline__ void bulk_g2s_cbar(void* dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar_cluster_addr) {
@@ -74,7 +77,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar_addr, uint32_t pa
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
         if (ok) return;
@@ -241,6 +244,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    clk_stamp(A.desc_swap, 0);
 
     auto sub_of = [&](int64_t tile) -> int {
         int sub = A.m.fixed_sub;
@@ -564,6 +568,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
     tc_fence_before();
     cluster_sync_all();
+    clk_stamp(A.desc_swap, 1);
     if (warp == kWarpProd) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }

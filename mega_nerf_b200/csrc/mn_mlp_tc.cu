@@ -39,6 +39,15 @@ __device__ __forceinline__ void trace_ev(int on, int who, int ev, int sl, int gi
         g_trace[(who * 2048 + i) * 2 + 1] = t;
     }
 }
+// SM clock during the kernel (MN_TC_TRACE=1): thread 0 of CTA 0 stamps (clock64, globaltimer) at kernel start and end.
+__device__ unsigned long long g_clk[4];
+__device__ __forceinline__ void clk_stamp(int on, int which) {
+    if (!on || blockIdx.x != 0 || threadIdx.x != 0) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_clk[2 * which] = (unsigned long long)clock64();
+    g_clk[2 * which + 1] = t;
+}
 constexpr int kMaxStages = 4;
 // weight ring geometry: single pass = 3 stages x 64 K-columns (32 KiB); split mode (H holds hi+lo planes) = 4 x 32 columns
 __host__ __device__ constexpr int ring_slab_cols(bool split) { return split ? 32 : 64; }
@@ -62,6 +71,11 @@ struct TcGemm {
     int w_off;       // byte offset of the weight image inside one precision plane of a sub-module
     int bias_off;    // float offset inside the sub-module's fp32 block
     int epi;
+    // Bias folded into the GEMM (TcArgs::bias_mma): two rows of the weight image hold fp16(b) and fp16(b - fp16(b)); the A
+    // operand has the constant 1.0 in the two matching K columns, so the accumulator starts from the fp32-accurate bias and
+    // the epilogue neither loads nor adds it (those loads cost as many shared-memory wavefronts as the activation stores).
+    int kext;        // 16 extra K columns appended to an activation-only GEMM (constant columns L, L+1 of the H buffer), else 0
+    int bias_row;    // K index of the fp16(b) row inside the (padded, extended) image; -1: bias stays in the epilogue (rgb head)
 };
 
 struct TcPlan {
@@ -75,6 +89,7 @@ struct TcPlan {
     int x_tile_bytes;      // bytes of one feature tile image (one plane)
     int L;
     int bstride;           // floats reserved per GEMM bias in the fp32 block (256; 512 for the 512-wide network)
+    int bias_mma_ok;       // every trunk / head GEMM has a place for its bias rows (spare feature columns or the H extension)
 };
 
 int pad16(int x) { return (x + 15) / 16 * 16; }
@@ -86,9 +101,11 @@ bool build_plan(const NetDims& nd, TcPlan* p) {
     P = TcPlan{};
     P.L = nd.L;
     P.bstride = nd.L > 256 ? 512 : 256;
-    P.kpe = pad16(nd.in_xyz);
-    P.kaux = nd.aux > 0 ? pad16(nd.aux) : 0;
+    // two spare (zero-padded) columns per feature segment are reserved for the constant 1.0 that multiplies the bias rows
+    P.kpe = pad16(nd.in_xyz + 2);
+    P.kaux = nd.aux > 0 ? pad16(nd.aux + 2) : 0;
     int woff = 0, ng = 0;
+    P.bias_mma_ok = nd.L <= 256 ? 1 : 0;
     auto add = [&](int n, int s0, int k0, int s1, int k1, int epi) {
         TcGemm& g = P.g[ng];
         g.n = n;
@@ -97,7 +114,23 @@ bool build_plan(const NetDims& nd, TcPlan* p) {
         g.w_off = woff;
         g.bias_off = ng * P.bstride;
         g.epi = epi;
-        woff += (k0 + k1) * n * 2;
+        g.kext = 0;
+        g.bias_row = -1;
+        if (epi != EPI_RGB && nd.L <= 256) {
+            // spare (zero-padded) columns of a feature segment carry the constant 1.0 for free; an activation-only GEMM gets
+            // 16 extra K columns instead
+            int off = 0;
+            for (int sgi = 0; sgi < g.nseg; ++sgi) {
+                const int real = g.src[sgi] == SRC_XPE ? nd.in_xyz : (g.src[sgi] == SRC_XAUX ? nd.aux : -1);
+                if (real >= 0 && g.k[sgi] - real >= 2 && g.bias_row < 0) g.bias_row = off + real;
+                off += g.k[sgi];
+            }
+            if (g.bias_row < 0) {
+                if (g.nseg == 1 && s0 == SRC_H) { g.kext = 16; g.bias_row = k0; }
+                else P.bias_mma_ok = 0;
+            }
+        }
+        woff += (k0 + k1 + g.kext) * n * 2;
         ++ng;
     };
     for (int i = 0; i < nd.layers; ++i) {
@@ -226,18 +259,23 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 // One 16-column piece of the epilogue for one accumulator row: TMEM -> +bias -> (ReLU) -> fp16 (hi [, lo]) ->
 // two 16-byte stores into the next layer's A operand.  Returns the partial sigma dot product if kSigma.
-template <bool kSplit, bool kRelu, bool kSigma>
+// kBias = false: the accumulator already contains the bias (TcArgs::bias_mma), nothing is loaded or added here.
+template <bool kSplit, bool kRelu, bool kSigma, bool kBias = true>
 __device__ __forceinline__ float epi_piece16(uint32_t taddr, const float* __restrict__ bias16, const float* __restrict__ sw16,
                                              unsigned char* dst, size_t lo_off, bool store) {
     uint32_t v[16];
     tmem_ld16(taddr, v);
-    const float4* b4 = reinterpret_cast<const float4*>(bias16);
-    const float4 b0 = b4[0], b1 = b4[1], b2 = b4[2], b3 = b4[3];
-    const float b[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+    float b[16];
+    if (kBias) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias16);
+        const float4 b0 = b4[0], b1 = b4[1], b2 = b4[2], b3 = b4[3];
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+        b[8] = b2.x; b[9] = b2.y; b[10] = b2.z; b[11] = b2.w; b[12] = b3.x; b[13] = b3.y; b[14] = b3.z; b[15] = b3.w;
+    }
     tmem_ld_wait();
     float f[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + b[i];
+    for (int i = 0; i < 16; ++i) f[i] = kBias ? __uint_as_float(v[i]) + b[i] : __uint_as_float(v[i]);
     float sacc = 0.0f;
     if (kSigma || kSplit) {
         if (kRelu) {
@@ -326,7 +364,8 @@ __device__ __forceinline__ void tc_emit_rgb(const MlpArgs& m, int sub, int64_t r
 // weight packing: nn.Linear weight [N_src][K_src] fp32 -> image [K/8][N][8] fp16 (hi) and the residual (lo)
 // ------------------------------------------------------------------------------------------------
 __global__ void tc_pack_kernel(const float* __restrict__ wt /* packed fp32, K-major Wt[k][n_src] */, int n_src, int k_src,
-                               int N, int K, int k_real0, int k_pad0, __half* __restrict__ hi, __half* __restrict__ lo) {
+                               int N, int K, int k_real0, int k_pad0, __half* __restrict__ hi, __half* __restrict__ lo,
+                               const float* __restrict__ bias, int n_bias, int bias_row) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)N * K) return;
     // i enumerates the image linearly: ((k/8)*N + n)*8 + k%8
@@ -334,6 +373,15 @@ __global__ void tc_pack_kernel(const float* __restrict__ wt /* packed fp32, K-ma
     const int n = (int)((i / 8) % N);
     const int kc = (int)(i / (8 * (int64_t)N));
     const int k = kc * 8 + k8;
+    if (bias_row >= 0 && (k == bias_row || k == bias_row + 1)) {
+        // bias rows (TcGemm::bias_row): fp16(b), then the fp16 residual - their sum against the A operand's constant 1.0
+        // columns reproduces b to ~2^-22 relative inside the fp32 accumulator
+        const float b = n < n_bias ? bias[n] : 0.0f;
+        const __half bh = __float2half_rn(b);
+        hi[i] = k == bias_row ? bh : __float2half_rn(b - __half2float(bh));
+        if (lo) lo[i] = __float2half_rn(0.0f);
+        return;
+    }
     int ks;
     if (k < k_pad0) ks = k < k_real0 ? k : -1;
     else ks = k_real0 + (k - k_pad0);
@@ -373,7 +421,7 @@ __global__ void tc_pack_f32_kernel(const float* __restrict__ src, int n, float* 
 // feature tiles
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTileM) tc_encode_kernel(const MlpArgs a, int kpe, int kaux, int split,
-                                                           __half* __restrict__ ximg, int64_t plane_stride_halves) {
+                                                           __half* __restrict__ ximg, int64_t plane_stride_halves, int ones) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __half* img = reinterpret_cast<__half*>(sm_raw);                  // hi image, then lo image
     const int ktot = kpe + kaux;
@@ -440,6 +488,12 @@ __global__ void __launch_bounds__(kTileM) tc_encode_kernel(const MlpArgs a, int 
             for (int c = col; c < ktot; ++c) put(c, 0.0f);
         }
     }
+    if (ones) {
+        // constant columns that multiply the bias rows of the weight images (TcGemm::bias_row)
+        put(nd.in_xyz, 1.0f);
+        put(nd.in_xyz + 1, 1.0f);
+        if (kaux > 0) { put(kpe + nd.aux, 1.0f); put(kpe + nd.aux + 1, 1.0f); }
+    }
     __syncthreads();
     const int nvec = ktot * kTileM * 2 / 16;
     const uint4* s4 = reinterpret_cast<const uint4*>(img);
@@ -471,11 +525,11 @@ __device__ __forceinline__ void pe_band(float x, int k, float* s, float* c) {
 // channels in registers and writes the tile image straight to global memory with 16-byte stores (thread t of a
 // chunk writes bytes [t*16, t*16+16) -> fully coalesced); no shared-memory staging, no 2-byte bank-conflicted stores.
 template <int XD, int NFX, int NFD, int APP>
-__global__ void __launch_bounds__(kTileM) tc_encode_fast_kernel(const MlpArgs a, __half* __restrict__ ximg) {
+__global__ void __launch_bounds__(kTileM) tc_encode_fast_kernel(const MlpArgs a, __half* __restrict__ ximg, int ones) {
     constexpr int IN_XYZ = XD * (1 + 2 * NFX);
-    constexpr int KPE = (IN_XYZ + 15) / 16 * 16;
+    constexpr int KPE = (IN_XYZ + 2 + 15) / 16 * 16;
     constexpr int IN_DIR = NFD > 0 ? 3 + 6 * NFD : 0;
-    constexpr int KAUX = (IN_DIR + APP + 15) / 16 * 16;
+    constexpr int KAUX = (IN_DIR + APP + 2 + 15) / 16 * 16;
     const int t = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t slot0 = tile * kTileM;
@@ -503,6 +557,7 @@ __global__ void __launch_bounds__(kTileM) tc_encode_fast_kernel(const MlpArgs a,
                 }
             }
         }
+        if (ones) { v[IN_XYZ] = 1.0f; v[IN_XYZ + 1] = 1.0f; }     // constant columns for the bias rows (TcGemm::bias_row)
 #pragma unroll
         for (int c = 0; c < KPE / 8; ++c)
             out[c * kTileM] = make_uint4(pack_h2(v[8 * c], v[8 * c + 1]), pack_h2(v[8 * c + 2], v[8 * c + 3]),
@@ -546,6 +601,7 @@ __global__ void __launch_bounds__(kTileM) tc_encode_fast_kernel(const MlpArgs a,
                 }
             }
         }
+        if (ones) { v[IN_DIR + APP] = 1.0f; v[IN_DIR + APP + 1] = 1.0f; }
 #pragma unroll
         for (int c = 0; c < KAUX / 8; ++c)
             out[(KPE / 8 + c) * kTileM] = make_uint4(pack_h2(v[8 * c], v[8 * c + 1]), pack_h2(v[8 * c + 2], v[8 * c + 3]),
@@ -981,29 +1037,33 @@ struct PPLayout {
     int ring, h, f32, f32_stride, sigp, bars, total, stages;
 };
 
-__host__ __device__ inline PPLayout pp_layout(const TcPlan& p, bool bias_global) {
+// bias_mma: the H buffers have 16 extra K columns (constant 1.0 in columns L and L+1) and the staged fp32 block shrinks
+// to [sigma_w (L) | sigma_b (4) | rgb bias (32)] - the biases of all other GEMMs ride in the weight images.
+__host__ __device__ inline int pp_h_bytes(const TcPlan& p, bool bias_mma) { return (p.L + (bias_mma ? 16 : 0)) * kTileM * 2; }
+__host__ __device__ inline PPLayout pp_layout(const TcPlan& p, bool bias_mma) {
     PPLayout s;
-    const int fixed = 2 * p.L * kTileM * 2 + (bias_global ? 0 : ((p.f32_floats * 4 + 15) / 16) * 16) + 2048 + 256;
+    s.f32_stride = bias_mma ? (p.L + 4 + 32) * 4 : ((p.f32_floats * 4 + 15) / 16) * 16;
+    const int fixed = 2 * pp_h_bytes(p, bias_mma) + s.f32_stride + 2048 + 256;
     int kPPStages = (kSmemMax - fixed) / kPPStageBytes;
     if (kPPStages > kPPMaxStages) kPPStages = kPPMaxStages;
     s.stages = kPPStages;
     s.ring = 0;
     s.h = kPPStages * kPPStageBytes;
-    s.f32 = s.h + 2 * p.L * kTileM * 2;
-    s.f32_stride = ((p.f32_floats * 4 + 15) / 16) * 16;
-    s.sigp = s.f32 + (bias_global ? 0 : s.f32_stride);    // ONE block: both tiles of a pair belong to the same sub-module
+    s.f32 = s.h + 2 * pp_h_bytes(p, bias_mma);
+    s.sigp = s.f32 + s.f32_stride;    // ONE fp32 block: both tiles of a pair belong to the same sub-module
     s.bars = s.sigp + 2048;
     s.total = s.bars + 256;
     return s;
 }
 
-// kBiasGlobal: biases / sigma weights are read straight from global memory (L2) by the epilogue instead of being
-// staged in shared memory; the 24 KiB saved buy a fourth weight-ring stage.
-template <bool kBiasGlobal>
+// kBiasMma: every bias except the rgb head's is part of its GEMM (TcGemm::bias_row / kext): the epilogue neither loads nor
+// adds biases - in the ncu capture of the previous version those broadcast loads were as many shared-memory wavefronts as
+// the activation stores, on a kernel whose shared-memory pipe (tensor-core operand reads + TMA fills + LSU) was 100 % busy.
+template <bool kBiasMma>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
-    const PPLayout SL = pp_layout(P, kBiasGlobal);
+    const PPLayout SL = pp_layout(P, kBiasMma);
     const int kPPStages = SL.stages;
     unsigned char* ring = smem + SL.ring;
     unsigned char* Hs = smem + SL.h;
@@ -1022,8 +1082,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     const int64_t n_slots = A.m.counters ? A.m.counters[CNT_NSLOTS] : A.m.B;
     const int64_t n_tiles = (n_slots + kTileM - 1) / kTileM;
     const int n_gemm = A.m.sigma_only ? P.n_trunk : P.n_gemm;
-    const int h_bytes = P.L * kTileM * 2;
+    const int h_bytes = pp_h_bytes(P, kBiasMma);
+    // fp32 block in shared memory: the packed block as is, or (kBiasMma) [sigma_w | sigma_b | rgb bias]
+    const float* SW = kBiasMma ? F32 : F32 + P.sigma_w_off;
+    const float* RGBB = kBiasMma ? F32 + P.L + 4 : F32 + P.g[P.n_gemm - 1].bias_off;
 
+    if (kBiasMma && threadIdx.x < 2 * kTileM) {
+        // constant K columns L .. L+15 of both activation buffers: (1, 1, 0, ..., 0) in every row
+        unsigned char* hx = Hs + (size_t)(threadIdx.x / kTileM) * h_bytes + (size_t)(P.L / 8) * (kTileM * 16) + (size_t)(threadIdx.x % kTileM) * 16;
+        *reinterpret_cast<uint4*>(hx) = make_uint4(0x3C003C00u, 0u, 0u, 0u);          // two fp16 1.0
+        *reinterpret_cast<uint4*>(hx + kTileM * 16) = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < kPPMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
@@ -1042,6 +1112,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    clk_stamp(A.desc_swap, 0);
 
     auto sub_of = [&](int64_t tile) -> int {
         int sub = A.m.fixed_sub;
@@ -1069,12 +1140,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                 const int sub0 = sub_of(t0);
                 for (int sl = 0; sl < 2; ++sl)
                     if (tiles[sl] < n_tiles) wsub[sl] = A.wpack + (size_t)sub0 * P.sub_bytes;
-                if (!kBiasGlobal && sub0 != last_sub) {
+                if (sub0 != last_sub) {
                     // the bias / sigma block is re-staged only when the sub-module changes (a handful of times per launch):
                     // the weight stream of consecutive pairs is not interrupted by waiting for the epilogue
                     if (last_sub >= 0) { mbar_wait(&f32_empty[0], fph_e); fph_e ^= 1; }
-                    mbar_expect_tx(&f32_full[0], f32_bytes);
-                    bulk_g2s(reinterpret_cast<unsigned char*>(F32), wsub[0] + (size_t)P.plane_bytes * 2, f32_bytes, &f32_full[0]);
+                    const unsigned char* fsrc = wsub[0] + (size_t)P.plane_bytes * 2;
+                    if (kBiasMma) {
+                        const uint32_t sb = (uint32_t)(P.L + 4) * 4u;
+                        mbar_expect_tx(&f32_full[0], sb + 128u);
+                        bulk_g2s(reinterpret_cast<unsigned char*>(F32), fsrc + (size_t)P.sigma_w_off * 4, sb, &f32_full[0]);
+                        bulk_g2s(reinterpret_cast<unsigned char*>(F32) + sb, fsrc + (size_t)P.g[P.n_gemm - 1].bias_off * 4, 128u, &f32_full[0]);
+                    } else {
+                        mbar_expect_tx(&f32_full[0], f32_bytes);
+                        bulk_g2s(reinterpret_cast<unsigned char*>(F32), fsrc, f32_bytes, &f32_full[0]);
+                    }
                     last_sub = sub0;
                 }
                 for (int gi = 0; gi < n_gemm; ++gi) {
@@ -1084,7 +1163,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                         const unsigned char* wimg = wsub[sl] + g.w_off;
                         int kbase = 0;
                         for (int sgi = 0; sgi < g.nseg; ++sgi) {
-                            const int kseg = g.k[sgi];
+                            const int kseg = g.k[sgi] + ((kBiasMma && g.src[sgi] == SRC_H) ? g.kext : 0);
                             if (g.src[sgi] != SRC_H) {
                                 // feature segment: 16 K-columns of weights + the same 16 K-columns of the tile's feature image
                                 const __half* xt = A.ximg + tiles[sl] * (int64_t)(P.kpe + P.kaux) * kTileM +
@@ -1148,8 +1227,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                     const uint32_t d_tmem = tmem_base + (uint32_t)sl * 256u;
                     uint32_t accum = 0;
                     for (int sgi = 0; sgi < g.nseg; ++sgi) {
-                        int rem = g.k[sgi];
                         const bool from_x = g.src[sgi] != SRC_H;
+                        int rem = g.k[sgi] + ((kBiasMma && !from_x) ? g.kext : 0);
                         if (from_x) {
                             // one K=16 MMA per stage; the A operand (feature columns) sits in the stage itself
                             for (; rem > 0; rem -= kPPXCols) {
@@ -1196,7 +1275,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
         for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
             const int64_t t0 = 2 * pr;
             const bool valid1 = t0 + 1 < n_tiles;
-            if (!kBiasGlobal) {
+            {
                 const int sub0 = sub_of(t0);
                 if (sub0 != last_sub) {
                     if (last_sub >= 0) {            // done with the previous sub-module's block
@@ -1210,17 +1289,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
             }
             int64_t slot_[2], row_[2] = {-1, -1};
             float sigma_[2] = {0.0f, 0.0f};
-            const float* fb_[2] = {nullptr, nullptr};
             for (int sl = 0; sl < 2; ++sl) {
                 if (sl == 1 && !valid1) continue;
                 slot_[sl] = (t0 + sl) * kTileM + r;
                 if (slot_[sl] < n_slots) row_[sl] = A.m.slot_row ? (int64_t)A.m.slot_row[slot_[sl]] : slot_[sl];
-                if (kBiasGlobal) {
-                    fb_[sl] = reinterpret_cast<const float*>(A.wpack + (size_t)sub_of(t0 + sl) * P.sub_bytes +
-                                                             (size_t)P.plane_bytes * 2);
-                } else {
-                    fb_[sl] = F32;
-                }
             }
             for (int gi = 0; gi < n_gemm; ++gi) {
                 const TcGemm& g = P.g[gi];
@@ -1232,8 +1304,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                     tc_fence_after();
                     if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 3, sl, gi);   // epilogue: accumulator ready
                     const uint32_t t_acc = t_lane + (uint32_t)sl * 256u;
-                    const float* Fb = fb_[sl];
-                    const float* bias = Fb + g.bias_off;
+                    const float* bias = kBiasMma ? F32 : F32 + g.bias_off;      // kBiasMma: never dereferenced for trunk GEMMs
                     const int64_t row = row_[sl], slot = slot_[sl];
                     if (A.nofetch >= 3) {
                     } else if (g.epi == EPI_RGB) {
@@ -1241,12 +1312,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                             uint32_t v[32];
                             tmem_ld32(t_acc, v);
                             tmem_ld_wait();
-                            if (row >= 0) tc_emit_rgb(A.m, A.m.nd.affine ? sub_of(t0 + sl) : 0, row, slot, v, bias, sigma_[sl]);
+                            if (row >= 0) tc_emit_rgb(A.m, A.m.nd.affine ? sub_of(t0 + sl) : 0, row, slot, v, RGBB, sigma_[sl]);
                         }
                     } else {
                         const bool want_sigma = g.epi == EPI_RELU_SIGMA;
                         const bool publish = !(want_sigma && A.m.sigma_only);
-                        const float* sw = Fb + P.sigma_w_off;
+                        const float* sw = SW;
                         unsigned char* Hsl = Hs + (size_t)sl * h_bytes;
                         float sacc = 0.0f;
                         const int nslab = (g.n + 63) >> 6;
@@ -1255,11 +1326,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                             if (c0 < g.n) {
                                 unsigned char* dst = Hsl + (size_t)(c0 >> 3) * (kTileM * 16) + (size_t)r * 16;
                                 if (g.epi == EPI_RELU)
-                                    epi_piece16<false, true, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
+                                    epi_piece16<false, true, false, !kBiasMma>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
                                 else if (g.epi == EPI_LINEAR)
-                                    epi_piece16<false, false, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
+                                    epi_piece16<false, false, false, !kBiasMma>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
                                 else
-                                    sacc += epi_piece16<false, true, true>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, publish);
+                                    sacc += epi_piece16<false, true, true, !kBiasMma>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, publish);
                             }
                         }
                         if (publish) fence_proxy_async();
@@ -1289,6 +1360,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     }
     tc_fence_before();
     __syncthreads();
+    clk_stamp(A.desc_swap, 1);
     if (warp == kWarpProd) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }
@@ -1370,7 +1442,13 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
             MN_LAUNCH_CHECK(ctx);
             return MN_OK;
         }
-        tc_pack_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, k_real0, k_pad0, hi, lo);
+        {
+            // hi / lo planes carry the bias rows and (activation-only GEMMs) the 16-column K extension; the other images do not
+            const int Kx = K + g.kext;
+            const int64_t nx = (int64_t)g.n * Kx;
+            tc_pack_kernel<<<(unsigned)mn_cdiv(nx, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, Kx, k_real0, k_pad0, hi, lo, bias, n_bias,
+                                                                     g.bias_row);
+        }
         MN_LAUNCH_CHECK(ctx);
         tc_pack_half_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, g.n < 128 ? g.n : 128, k_real0, k_pad0,
                                                                     reinterpret_cast<__half*>(base + ts_off + g.w_off));
@@ -1441,15 +1519,43 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     A.ximg = ximg;
     A.x_plane_halves = (int64_t)n_tiles128 * (P.kpe + P.kaux) * kTileM;
 
+    // ---- kernel selection (environment switches are read once per process; defaults: ping-pong kernel with the biases
+    // folded into the GEMMs for layer_dim <= 256, the wide kernel for 512, the split kernel for tc_f16x3)
+    static int use_pp = -1, bias_mma_env = -1, use_ts = -1, use_c2 = -1, c2_share = -1;
+    if (use_pp < 0) {
+        const char* e = getenv("MN_TC_PINGPONG");
+        use_pp = (e && e[0] == '0') ? 0 : 1;
+        e = getenv("MN_TC_BIASMMA");
+        bias_mma_env = (e && e[0] == '1') ? 1 : 0;       // opt-in: measured 4 % SLOWER on B200 (907 vs 943 TFLOP/s) - see DESIGN.md §7
+        e = getenv("MN_TC_TS");
+        use_ts = (e && e[0] == '1') ? 1 : 0;
+        e = getenv("MN_TC_C2");
+        use_c2 = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 0;      // 1 pair, 2 + relay handshake, 3 + trailing epilogue
+        e = getenv("MN_TC_C2SHARE");
+        c2_share = (e && e[0] == '1') ? 1 : 0;
+    }
+    A.c2_relay = use_c2 == 2 ? 1 : 0;
+    A.c2_share = c2_share;
+    const C2Layout CL = c2_layout(P, c2_share != 0);
+    const TsLayout TL = ts_layout(P);
+    const bool run_c2 = !split && P.L == 256 && use_c2 && !a.nd.affine && m->tmap_ready && CL.total <= kSmemMax &&
+                        CL.stages >= (c2_share ? 10 : 3) && (n_tiles128 % 4) == 0;
+    const bool run_ts = !split && P.L <= 256 && !run_c2 && use_ts && !a.nd.affine && P.L % 128 == 0 && TL.stages >= 4;
+    const bool bias_mma = !split && P.L <= 256 && !run_c2 && !run_ts && use_pp && bias_mma_env && P.bias_mma_ok &&
+                          pp_layout(P, true).total <= kSmemMax && pp_layout(P, true).stages >= 3;
+    const PPLayout PL = pp_layout(P, bias_mma);
+    const bool run_pp = !split && P.L <= 256 && !run_c2 && !run_ts && use_pp && PL.total <= kSmemMax;
+    const int ones = (bias_mma && run_pp) ? 1 : 0;     // the feature tiles carry the constant-1 columns only for that kernel
+
     const size_t enc_sm = (size_t)P.x_tile_bytes * (split ? 2 : 1);
     MN_CUDA(ctx, cudaFuncSetAttribute(tc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_sm));
     const NetDims& ndE = a.nd;
     const bool fast_shape = !split && ndE.xyz_dim == 3 && ndE.nf_xyz == 12 && ndE.nf_dir == 4 && ndE.app == 48 && ndE.app_in_dira &&
                             (m->lay.emb % 4) == 0;
     if (fast_shape)
-        tc_encode_fast_kernel<3, 12, 4, 48><<<(unsigned)n_tiles128, kTileM, 0, st>>>(a, ximg);
+        tc_encode_fast_kernel<3, 12, 4, 48><<<(unsigned)n_tiles128, kTileM, 0, st>>>(a, ximg, ones);
     else
-        tc_encode_kernel<<<(unsigned)n_tiles128, kTileM, enc_sm, st>>>(a, P.kpe, P.kaux, split, ximg, A.x_plane_halves);
+        tc_encode_kernel<<<(unsigned)n_tiles128, kTileM, enc_sm, st>>>(a, P.kpe, P.kaux, split, ximg, A.x_plane_halves, ones);
     MN_LAUNCH_CHECK(ctx);
 
     if (P.L > 256) {
@@ -1500,38 +1606,7 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         mn_prof_begin(ctx, st);
         tc_mlp_kernel<true><<<grid, kThreads, total, st>>>(A);
     } else {
-        static int use_pp = -1;
-        if (use_pp < 0) {
-            const char* e = getenv("MN_TC_PINGPONG");
-            use_pp = (e && e[0] == '0') ? 0 : 1;
-        }
-        static int bias_global = -1;
-        if (bias_global < 0) {
-            const char* e = getenv("MN_TC_BIAS_GLOBAL");
-            bias_global = (e && e[0] == '1') ? 1 : 0;
-        }
-        static int use_ts = -1;
-        if (use_ts < 0) {
-            const char* e = getenv("MN_TC_TS");
-            use_ts = (e && e[0] == '1') ? 1 : 0;
-        }
-        static int use_c2 = -1;
-        if (use_c2 < 0) {
-            const char* e = getenv("MN_TC_C2");
-            use_c2 = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 0;      // 1 pair, 2 + relay handshake, 3 + trailing epilogue
-        }
-        A.c2_relay = use_c2 == 2 ? 1 : 0;
-        static int c2_share = -1;
-        if (c2_share < 0) {
-            const char* e = getenv("MN_TC_C2SHARE");
-            c2_share = (e && e[0] == '1') ? 1 : 0;
-        }
-        A.c2_share = c2_share;
-        const PPLayout PL = pp_layout(P, bias_global != 0);
-        const TsLayout TL = ts_layout(P);
-        const C2Layout CL = c2_layout(P, c2_share != 0);
-        if (use_c2 && !a.nd.affine && P.L == 256 && m->tmap_ready && CL.total <= kSmemMax && CL.stages >= (c2_share ? 10 : 3) &&
-            (n_tiles128 % 4) == 0) {
+        if (run_c2) {
             C2Maps maps;
             memcpy(&maps.w64, m->tmap_w[0], 128);
             memcpy(&maps.w32, m->tmap_w[1], 128);
@@ -1548,14 +1623,13 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
             mn_prof_begin(ctx, st);
             if (use_c2 == 3) tc_mlp_c2_kernel<true><<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A, maps);
             else tc_mlp_c2_kernel<false><<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A, maps);
-        } else
-        if (use_ts && !a.nd.affine && P.L % 128 == 0 && TL.stages >= 4) {
+        } else if (run_ts) {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL.total));
             mn_prof_begin(ctx, st);
             tc_mlp_ts_kernel<<<grid, kTsThreads, TL.total, st>>>(A);
-        } else if (use_pp && PL.total <= kSmemMax) {
+        } else if (run_pp) {
             const unsigned grid_pp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
-            if (bias_global) {
+            if (bias_mma) {
                 MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
                 mn_prof_begin(ctx, st);
                 tc_mlp_pp_kernel<true><<<grid_pp, kThreads, PL.total, st>>>(A);
@@ -1573,6 +1647,12 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     mn_prof_end(ctx, st);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
+}
+
+extern "C" int mn_debug_read_clock(unsigned long long* out4) {
+    cudaDeviceSynchronize();
+    if (out4) cudaMemcpyFromSymbol(out4, g_clk, sizeof(unsigned long long) * 4);
+    return 0;
 }
 
 extern "C" int mn_debug_read_trace(unsigned long long* out, unsigned int* counts, int reset) {

@@ -35,13 +35,9 @@ __device__ __forceinline__ bool plane_bound(const float* o, const float* d, floa
     return true;
 }
 
-__global__ void rays_kernel(const float* __restrict__ dirs, int dirs_batched, const float* __restrict__ c2w, int n_poses,
-                            int64_t P, float near, float far, int has_alt, float alt0, float alt1, float* out) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)n_poses * P) return;
-    const int64_t pose = t / P, p = t % P;
-    const float* dv = dirs + (dirs_batched ? t : p) * 3;
-    const float* M = c2w + pose * 12;
+// one ray from a camera-space direction and a 3x4 pose: rotate, normalise, plane-truncated bounds (ray_utils.py:21-84)
+__device__ __forceinline__ void make_ray(const float* __restrict__ dv, const float* __restrict__ M, float near, float far, int has_alt,
+                                         float alt0, float alt1, float* __restrict__ r) {
     float d[3], o[3];
     for (int i = 0; i < 3; ++i) {
         float acc = dv[0] * M[i * 4 + 0];
@@ -61,10 +57,34 @@ __global__ void rays_kernel(const float* __restrict__ dirs, int dirs_batched, co
         fb = fminf(fb, far);
         fb = fmaxf(nb, fb);
     }
-    float* r = out + t * 8;
     r[0] = o[0]; r[1] = o[1]; r[2] = o[2];
     r[3] = d[0]; r[4] = d[1]; r[5] = d[2];
     r[6] = nb; r[7] = fb;
+}
+
+__global__ void rays_kernel(const float* __restrict__ dirs, int dirs_batched, const float* __restrict__ c2w, int n_poses,
+                            int64_t P, float near, float far, int has_alt, float alt0, float alt1, float* out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_poses * P) return;
+    const int64_t pose = t / P, p = t % P;
+    make_ray(dirs + (dirs_batched ? t : p) * 3, c2w + pose * 12, near, far, has_alt, alt0, alt1, out + t * 8);
+}
+
+// The loader's use of get_rays_batch (filesystem_dataset.py:109-124) wants ONE ray per (image, pixel) pair of a chunk; the
+// reference builds the full [#unique images, #unique pixels, 8] product on the device, copies it to the host and gathers the
+// pairs there.  This kernel computes exactly the M pairs: ray m = (pose img_idx[m], direction pix_idx[m]).
+__global__ void rays_pairs_kernel(const float* __restrict__ dirs, int64_t P, const float* __restrict__ c2w, int n_poses,
+                                  const int* __restrict__ img_idx, const int* __restrict__ pix_idx, int64_t M, float near,
+                                  float far, int has_alt, float alt0, float alt1, float* out, unsigned int* status) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M) return;
+    const int pose = img_idx[t], pix = pix_idx[t];
+    if (pose < 0 || pose >= n_poses || pix < 0 || pix >= P) {      // the reference's fancy indexing raises IndexError here
+        atomicOr(status, MN_STATUS_INDEX);
+        for (int i = 0; i < 8; ++i) out[t * 8 + i] = __int_as_float(0x7fc00000);
+        return;
+    }
+    make_ray(dirs + (int64_t)pix * 3, c2w + (int64_t)pose * 12, near, far, has_alt, alt0, alt1, out + t * 8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -773,6 +793,17 @@ int mn_ray_directions(mn_ctx* ctx, int W, int H, float fx, float fy, float cx, f
     if (!ctx || !out_d || W <= 0 || H <= 0) return MN_ERR_INVALID;
     const int64_t n = (int64_t)W * H;
     ray_directions_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(W, H, fx, fy, cx, cy, center_pixels, out_d);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}
+
+int mn_rays_pairs(mn_ctx* ctx, const float* dirs_d, int64_t P, const float* c2w_d, int n_poses, const int32_t* img_idx_d,
+                  const int32_t* pix_idx_d, int64_t M, float near, float far, int has_altitude, float alt_max, float alt_min,
+                  float* out_d, void* stream) {
+    if (!ctx || !dirs_d || !c2w_d || !img_idx_d || !pix_idx_d || !out_d || M < 0 || P < 0 || n_poses < 0) return MN_ERR_INVALID;
+    if (M == 0) return MN_OK;
+    rays_pairs_kernel<<<(unsigned)mn_cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(dirs_d, P, c2w_d, n_poses, img_idx_d, pix_idx_d, M, near,
+                                                                                   far, has_altitude, alt_max, alt_min, out_d, ctx->status_d);
     MN_LAUNCH_CHECK(ctx);
     return MN_OK;
 }

@@ -6,7 +6,8 @@ train.py / eval.py / Runner import the B200 path unchanged:
 
 Replaced names (runner.py:33-35, filesystem_dataset.py:18):
     mega_nerf.rendering.render_rays, mega_nerf.models.model_utils.get_nerf / get_bg_nerf,
-    mega_nerf.ray_utils.get_rays / get_ray_directions / get_rays_batch, and the model classes.
+    mega_nerf.ray_utils.get_rays / get_ray_directions / get_rays_batch, the model classes, and
+    FilesystemDataset._load_chunk_inner (the chunk loader's ray generation, filesystem_dataset.py:95-131).
 """
 from __future__ import annotations
 
@@ -68,3 +69,23 @@ def install(patch_loaded: bool = True) -> None:
                 for k, v in target.items():
                     if hasattr(m, k):
                         setattr(m, k, v)
+    patch_loader()
+
+
+def patch_loader() -> bool:
+    """Bind the fused chunk loader (mega_nerf_b200/loader.py) over
+    `FilesystemDataset._load_chunk_inner` (filesystem_dataset.py:95-131) if that module is - or can be - imported."""
+    from . import loader
+    m = sys.modules.get('mega_nerf.datasets.filesystem_dataset')
+    if m is None:
+        try:
+            m = importlib.import_module('mega_nerf.datasets.filesystem_dataset')
+        except Exception:       # e.g. no reference on the path, or its imports (np.int, pyarrow) unavailable
+            return False
+    cls = getattr(m, 'FilesystemDataset', None)
+    if cls is None:
+        return False
+    if getattr(cls._load_chunk_inner, '__module__', '') != loader.__name__:
+        cls._reference_load_chunk_inner = cls._load_chunk_inner
+        cls._load_chunk_inner = loader._load_chunk_inner
+    return True

@@ -55,3 +55,25 @@ def get_rays_batch(directions: torch.Tensor, c2w: torch.Tensor, near: float, far
                    ray_altitude_range: List[float]) -> torch.Tensor:
     """[n,P,3] or [P,3] x [n,3,4] -> [n,P,8]  (ray_utils.py:33-41; the loader passes [P,3], filesystem_dataset.py:118)."""
     return _rays(directions, c2w, near, far, ray_altitude_range, True)
+
+
+def get_rays_pairs(directions: torch.Tensor, c2ws: torch.Tensor, image_index: torch.Tensor, pixel_index: torch.Tensor,
+                   near: float, far: float, ray_altitude_range: Optional[List[float]]) -> torch.Tensor:
+    """[P,3] directions x [n,3,4] poses, evaluated for M (image, pixel) pairs only -> [M,8].
+    Equals `get_rays_batch(directions, c2ws, ...)[image_index, pixel_index]` (what filesystem_dataset.py:109-125 computes
+    through the full [n,P,8] product and a host-side gather) without the product."""
+    dev = directions.device
+    h = K.ctx(dev)
+    d = K.f32c(directions).view(-1, 3)
+    m = K.f32c(c2ws.to(dev)).view(-1, 3, 4)
+    ii = image_index.to(dev, torch.int32).contiguous().view(-1)
+    pi = pixel_index.to(dev, torch.int32).contiguous().view(-1)
+    if ii.shape != pi.shape:
+        raise ValueError('image_index and pixel_index must have the same length')
+    M = ii.shape[0]
+    out = torch.empty(M, 8, device=dev, dtype=torch.float32)
+    has_alt = ray_altitude_range is not None
+    K.check(K.lib().mn_rays_pairs(h, K.ptr(d), d.shape[0], K.ptr(m), m.shape[0], K.ptr(ii), K.ptr(pi), M, float(near), float(far),
+                                  int(has_alt), float(ray_altitude_range[0]) if has_alt else 0.0,
+                                  float(ray_altitude_range[1]) if has_alt else 0.0, K.ptr(out), K.stream_of(dev)), h)
+    return out

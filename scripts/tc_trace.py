@@ -30,6 +30,11 @@ for it in range(3):
 buf = (C.c_ulonglong * (4 * 4096))()
 cnt = (C.c_uint * 2)()
 lib.mn_debug_read_trace(buf, cnt, 0)
+clk = (C.c_ulonglong * 4)()
+lib.mn_debug_read_clock.argtypes = [C.c_void_p]
+lib.mn_debug_read_clock(clk)
+if clk[3] > clk[1]:
+    print(f'SM clock during the kernel (CTA 0): {(clk[2] - clk[0]) / (clk[3] - clk[1]):.3f} GHz over {(clk[3] - clk[1]) / 1e3:.1f} us')
 ev = []
 for who in range(2):
     for i in range(min(cnt[who], 2048)):

@@ -41,7 +41,7 @@ print('VARIANT_OK')
 def run_variant(tmp_path, name, env):
     out = tmp_path / f'{name}.pt'
     e = dict(os.environ)
-    for k in ('MN_TC_C2', 'MN_TC_C2SHARE', 'MN_TC_TS', 'MN_TC_PINGPONG'):
+    for k in ('MN_TC_C2', 'MN_TC_C2SHARE', 'MN_TC_TS', 'MN_TC_PINGPONG', 'MN_TC_BIASMMA'):
         e.pop(k, None)
     e.update(env)
     r = subprocess.run([sys.executable, '-c', CHILD.format(root=ROOT), str(out)], env=e, capture_output=True, text=True, timeout=240)
@@ -56,6 +56,7 @@ def default_out(tmp_path_factory):
 
 @pytest.mark.parametrize('name,env', [('c2', {'MN_TC_C2': '1'}), ('ts', {'MN_TC_TS': '1'}), ('single_tile', {'MN_TC_PINGPONG': '0'}),
                                       ('c2_relay', {'MN_TC_C2': '2'}), ('c2_trailing', {'MN_TC_C2': '3'}),
+                                      ('pp_bias_in_gemm', {'MN_TC_BIASMMA': '1'}),
                                       ('c2_share', {'MN_TC_C2': '1', 'MN_TC_C2SHARE': '1'}),
                                       ('c2_relay_share', {'MN_TC_C2': '2', 'MN_TC_C2SHARE': '1'})])
 def test_variant_matches_default_kernel(tmp_path, default_out, name, env):
