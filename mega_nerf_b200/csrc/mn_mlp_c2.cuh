@@ -262,9 +262,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         // =========================== TMA producer (each CTA streams its N-half of every weight slab) ===========================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0, fph_e = 0;
+            uint32_t phase = 0, fph_e = 0, p_ahead = 0;
             int last_sub = -1;
             const uint32_t f32_bytes = (uint32_t)SL.f32_stride;
+            const uint32_t empty_pa = smem_u32(empty);
             const uint32_t full_l = mapa_u32(smem_u32(full), 0);          // the LEADER's full[] barriers count both halves
             const uint32_t ring_a = smem_u32(ring);
             for (int64_t q = cl; q < n_quads; q += ncl) {
@@ -297,16 +298,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                 const int kc = min(step, kseg - k0);
                                 const uint32_t wbytes = (uint32_t)(kc * nhalf * 2);
                                 const uint32_t xbytes = from_x ? (uint32_t)(kc * kTileM * 2) : 0u;
-                                const uint32_t bar = full_l + 8u * (uint32_t)stage;
-                                const uint32_t dst = ring_a + (uint32_t)stage * kC2StageBytes;
-                                mbar_wait(&empty[stage], phase ^ 1);
+                                if (!p_ahead) mbar_wait(&empty[stage], phase ^ 1);
+                                const int cur = stage;
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                                p_ahead = mbar_test_a(empty_pa + 8u * (uint32_t)stage, phase ^ 1);    // look-ahead, overlaps the copies below
+                                const uint32_t bar = full_l + 8u * (uint32_t)cur;
+                                const uint32_t dst = ring_a + (uint32_t)cur * kC2StageBytes;
                                 // the leader announces the bytes of BOTH CTAs (the streams are symmetric); the peer's copies
                                 // only complete_tx on the leader's barrier - no remote arrive on the critical path
-                                if (leader) mbar_expect_tx(&full[stage], 2u * (wbytes + xbytes));
+                                if (leader) mbar_expect_tx(&full[cur], 2u * (wbytes + xbytes));
                                 const int wrow0 = (int)((size_t)((wimg + (size_t)(kbase + k0) * nhalf * 2) - A.wpack) >> 8);
                                 c2_copy_rows(dst, wrow0, (int)(wbytes >> 8), bar, &TM.w64, 64, &TM.w32, 32, &TM.w8, 8, &TM.w4, 4);
                                 if (from_x) c2_copy_rows(dst + kC2XOff, xrow0 + k0, kc, bar, &TM.x32, 32, &TM.x16, 16, nullptr, 0);
-                                if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
                             kbase += kseg;
                         }
@@ -318,7 +321,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         // =========================== MMA issuer: leader CTA only, whole warp, one elected lane issues ===========================
         if (leader) {
             int stage = 0;
-            uint32_t phase = 0, eph0 = 0, eph1 = 0;
+            uint32_t phase = 0, eph0 = 0, eph1 = 0, ahead = 0;
             bool started0 = false, started1 = false;
             const uint32_t h_base = smem_u32(Hs), ring_base = smem_u32(ring);
             const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
@@ -339,7 +342,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     const int stage_g0 = stage;
                     const uint32_t phase_g0 = phase;
                     for (int sl = 0; sl < 2; ++sl) {
-                        if (shared_g && sl == 1) { stage = stage_g0; phase = phase_g0; }
+                        if (shared_g && sl == 1) { stage = stage_g0; phase = phase_g0; ahead = 0; }
                         const uint32_t release = (shared_g && sl == 0) ? 0u : 1u;
                         const bool prev = sl == 0 ? started0 : started1;       // this slot has an epilogue in flight
                         const uint32_t hpar = sl == 0 ? eph0 : eph1;
@@ -371,13 +374,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                     const int hs = k0 >> 6;
                                     while (waited <= hs) { mbar_wait_cluster(hbar + 8u * (uint32_t)waited, hpar); ++waited; }
                                 }
-                                mbar_wait_cluster(full_a + 8u * (uint32_t)stage, phase);
+                                const uint32_t cur = (uint32_t)stage;
+                                if (!ahead) mbar_wait_cluster(full_a + 8u * cur, phase);
                                 tc_fence_after();
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                                // look-ahead probe of the next stage (streaming mode only: in shared mode slot 1 rewinds), issued
+                                // before this stage's MMAs so that its latency overlaps them
+                                ahead = share ? 0u : mbar_test_a(full_a + 8u * (uint32_t)stage, phase);
                                 c2_stage(d_tmem, from_x ? xd0 + so : ad, a_step, bd0 + so, b_step, idesc, accum, kc >> 4,
-                                         empty_a + 8u * (uint32_t)stage, release);
+                                         empty_a + 8u * cur, release);
                                 accum = 1;
                                 ad += (uint64_t)(kc >> 4) * a_step;
-                                if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
                         }
                         if (kTrail && prev) {

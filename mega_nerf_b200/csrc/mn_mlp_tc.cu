@@ -59,6 +59,7 @@ constexpr int kEpiWarps = 16;
 // highest warp id on an SM sub-partition, so the latency-critical single-thread roles get the top ids.
 constexpr int kWarpProd = 16;
 constexpr int kWarpMma = 17;
+constexpr int kPPThreads = kThreads;
 
 enum { SRC_H = 0, SRC_XPE = 1, SRC_XAUX = 2 };
 enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
@@ -632,6 +633,19 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) 
         }
     }
 }
+// Non-blocking look-ahead probe (mbarrier.test_wait): issued BEFORE the current stage's work so that its ~100-cycle latency
+// overlaps that work instead of heading the next stage's dependent chain.  A single thread pays ~260 cycles per ring stage
+// for wait -> issue -> signal when these are strictly sequential (scripts/probes/l2_stream_probe.cu: throughput of a
+// one-thread TMA ring is proportional to the stage size and independent of its depth) - as long as two 128-cycle MMAs.
+__device__ __forceinline__ uint32_t mbar_test_a(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+    return ok;
+}
 // one ring stage worth of MMAs (one or two K=16 steps) + the commit that releases the stage, issued by one
 // elected lane; everything is predicated, no branches.
 __device__ __forceinline__ void mma_stage(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint64_t ad2, uint64_t bd2, uint32_t idesc,
@@ -645,6 +659,26 @@ __device__ __forceinline__ void mma_stage(uint32_t d_tmem, uint64_t ad, uint64_t
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %4, %5, 1;\n\t"
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}"
         ::"r"(d_tmem), "l"(ad), "l"(bd), "l"(ad2), "l"(bd2), "r"(idesc), "r"(accum), "r"(two), "r"(empty_bar_addr)
+        : "memory");
+}
+// Two consecutive ring stages of one GEMM in one issue block: up to four K=16 MMAs (A contiguous in the activation buffer,
+// B in stage a then stage b), each stage released by its own commit.  n_b = MMAs of the second stage (1 or 2).
+__device__ __forceinline__ void mma_stage2(uint32_t d_tmem, uint64_t ad, uint64_t a_step, uint64_t bda, uint64_t bdb, uint64_t b_step,
+                                           uint32_t idesc, uint32_t accum, uint32_t n_b, uint32_t empty_a, uint32_t empty_b) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, q;\n\t.reg .b64 a1, a2, a3, b1, b3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.gt.and.u32 q, %8, 1, e;\n\t"
+        "add.u64 a1, %1, %2;\n\tadd.u64 a2, a1, %2;\n\tadd.u64 a3, a2, %2;\n\t"
+        "add.u64 b1, %3, %5;\n\tadd.u64 b3, %4, %5;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %6, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %6, 1;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, %4, %6, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %6, 1;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t}"
+        ::"r"(d_tmem), "l"(ad), "l"(a_step), "l"(bda), "l"(bdb), "l"(b_step), "r"(idesc), "r"(accum), "r"(n_b), "r"(empty_a), "r"(empty_b)
         : "memory");
 }
 __device__ __forceinline__ void commit_elect(uint32_t bar_addr) {
@@ -1034,8 +1068,15 @@ constexpr int kPPXCols = 16;
 constexpr int kPPXOff = 8192;
 
 struct PPLayout {
-    int ring, h, f32, f32_stride, sigp, bars, total, stages;
+    int ring, h, f32, f32_stride, sigp, bars, prog, total, stages;
 };
+// Stage program of the ping-pong kernel: ONE 16-byte entry per ring stage of a tile pair, shared by the TMA producer and the
+// MMA issuer, so that both single-thread roles run a flat loop (no nested GEMM / segment / K loops, no address arithmetic
+// beyond one add): their per-stage dependent chain is what paces the kernel (see the probe notes at mbar_test_a).
+//   x = weight byte offset inside the sub-module image   y = weight bytes | (feature offset / 16, 0xFFFF = none) << 16
+//   z = flags | MMA N << 8                               w = activation-operand offset >> 4 (descriptor units)
+constexpr int kPPMaxProg = 208;
+enum { PF_SLOT1 = 1, PF_FIRST = 2, PF_LAST = 4, PF_FROM_X = 8, PF_TWO = 16, PF_PAIR = 32 };   // PF_PAIR: this and the next entry are consecutive activation stages of one GEMM - the MMA warp issues them together
 
 // bias_mma: the H buffers have 16 extra K columns (constant 1.0 in columns L and L+1) and the staged fp32 block shrinks
 // to [sigma_w (L) | sigma_b (4) | rgb bias (32)] - the biases of all other GEMMs ride in the weight images.
@@ -1043,7 +1084,7 @@ __host__ __device__ inline int pp_h_bytes(const TcPlan& p, bool bias_mma) { retu
 __host__ __device__ inline PPLayout pp_layout(const TcPlan& p, bool bias_mma) {
     PPLayout s;
     s.f32_stride = bias_mma ? (p.L + 4 + 32) * 4 : ((p.f32_floats * 4 + 15) / 16) * 16;
-    const int fixed = 2 * pp_h_bytes(p, bias_mma) + s.f32_stride + 2048 + 256;
+    const int fixed = 2 * pp_h_bytes(p, bias_mma) + s.f32_stride + 2048 + 256 + kPPMaxProg * 16;
     int kPPStages = (kSmemMax - fixed) / kPPStageBytes;
     if (kPPStages > kPPMaxStages) kPPStages = kPPMaxStages;
     s.stages = kPPStages;
@@ -1052,15 +1093,31 @@ __host__ __device__ inline PPLayout pp_layout(const TcPlan& p, bool bias_mma) {
     s.f32 = s.h + 2 * pp_h_bytes(p, bias_mma);
     s.sigp = s.f32 + s.f32_stride;    // ONE fp32 block: both tiles of a pair belong to the same sub-module
     s.bars = s.sigp + 2048;
-    s.total = s.bars + 256;
+    s.prog = s.bars + 256;
+    s.total = s.prog + kPPMaxProg * 16;
     return s;
+}
+
+__host__ __device__ inline int pp_gemm_stages(const TcGemm& g, bool bias_mma) {
+    int n = 0;
+    for (int sgi = 0; sgi < g.nseg; ++sgi) {
+        const bool fx = g.src[sgi] != SRC_H;
+        const int kk = g.k[sgi] + ((bias_mma && !fx) ? g.kext : 0);
+        n += fx ? (kk + kPPXCols - 1) / kPPXCols : (kk + kPPSlabCols - 1) / kPPSlabCols;
+    }
+    return n;
+}
+__host__ __device__ inline int pp_prog_entries(const TcPlan& p, int n_gemm, bool bias_mma) {
+    int n = 0;
+    for (int gi = 0; gi < n_gemm; ++gi) n += 2 * pp_gemm_stages(p.g[gi], bias_mma);
+    return n;
 }
 
 // kBiasMma: every bias except the rgb head's is part of its GEMM (TcGemm::bias_row / kext): the epilogue neither loads nor
 // adds biases - in the ncu capture of the previous version those broadcast loads were as many shared-memory wavefronts as
 // the activation stores, on a kernel whose shared-memory pipe (tensor-core operand reads + TMA fills + LSU) was 100 % busy.
 template <bool kBiasMma>
-__global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) {
+__global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
     const PPLayout SL = pp_layout(P, kBiasMma);
@@ -1087,6 +1144,35 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     const float* SW = kBiasMma ? F32 : F32 + P.sigma_w_off;
     const float* RGBB = kBiasMma ? F32 + P.L + 4 : F32 + P.g[P.n_gemm - 1].bias_off;
 
+    // ---- stage program (see kPPMaxProg): entries in the order both roles walk a tile pair: GEMM, slot, segment, K
+    uint4* PROG = reinterpret_cast<uint4*>(smem + SL.prog);
+    auto stages_of = [&](const TcGemm& g) -> int { return pp_gemm_stages(g, kBiasMma); };
+    const int n_prog = pp_prog_entries(P, n_gemm, kBiasMma);       // <= kPPMaxProg: checked by the launcher
+    if (threadIdx.x >= 64 && threadIdx.x < 66) PROG[n_prog + (threadIdx.x - 64)] = make_uint4(0u, 0u, 0u, 0u);   // read-ahead padding
+    if ((int)threadIdx.x < 2 * n_gemm) {
+        const int gi = threadIdx.x >> 1, sl = threadIdx.x & 1;
+        const TcGemm& g = P.g[gi];
+        int e = 0;
+        for (int j = 0; j < gi; ++j) e += 2 * stages_of(P.g[j]);
+        const int total = stages_of(g);
+        e += sl * total;
+        int kbase = 0, cnt = 0;
+        for (int sgi = 0; sgi < g.nseg; ++sgi) {
+            const bool fx = g.src[sgi] != SRC_H;
+            const int kk = g.k[sgi] + ((kBiasMma && !fx) ? g.kext : 0);
+            const int step = fx ? kPPXCols : kPPSlabCols;
+            for (int k0 = 0; k0 < kk; k0 += step, ++cnt, ++e) {
+                const int kc = min(step, kk - k0);
+                const uint32_t xo = fx ? (uint32_t)(((g.src[sgi] == SRC_XAUX ? P.kpe * kTileM * 2 : 0) + k0 * kTileM * 2) >> 4) : 0xFFFFu;
+                const bool pair = !fx && ((k0 / kPPSlabCols) & 1) == 0 && k0 + kPPSlabCols < kk;      // even activation stage with a successor
+                const uint32_t fl = (sl ? PF_SLOT1 : 0) | (cnt == 0 ? PF_FIRST : 0) | (cnt == total - 1 ? PF_LAST : 0) | (fx ? PF_FROM_X : 0) |
+                                    ((!fx && kc == kPPSlabCols) ? PF_TWO : 0) | (pair ? PF_PAIR : 0);
+                PROG[e] = make_uint4((uint32_t)(g.w_off + (kbase + k0) * g.n * 2), (uint32_t)(kc * g.n * 2) | (xo << 16),
+                                     fl | ((uint32_t)g.n << 8), fx ? 0u : (uint32_t)(((k0 >> 3) * (kTileM * 16)) >> 4));
+            }
+            kbase += kk;
+        }
+    }
     if (kBiasMma && threadIdx.x < 2 * kTileM) {
         // constant K columns L .. L+15 of both activation buffers: (1, 1, 0, ..., 0) in every row
         unsigned char* hx = Hs + (size_t)(threadIdx.x / kTileM) * h_bytes + (size_t)(P.L / 8) * (kTileM * 16) + (size_t)(threadIdx.x % kTileM) * 16;
@@ -1127,24 +1213,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
     const int64_t n_pairs = (n_tiles + 1) / 2;
 
     if (warp == kWarpProd) {
-        // =========================== TMA producer ===========================
-        if (lane == 0 && A.nofetch < 4) {
-            int stage = 0;
-            uint32_t phase = 0, fph_e = 0;
+        // =========================== TMA producer: table-driven (PROG) ===========================
+        // One thread.  Its per-stage dependent chain (wait -> expect_tx -> copy) is as long as the stage's two MMAs, so the
+        // loop is kept flat: one 16-byte table entry per ring stage, look-ahead probe of the next stage's empty barrier.
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, fph_e = 0, ahead = 0;
             int last_sub = -1;
             const uint32_t f32_bytes = (uint32_t)SL.f32_stride;
+            const uint32_t empty_pa = smem_u32(empty), full_pa = smem_u32(full), ring_pa = smem_u32(ring);
+            const uint32_t nst = (uint32_t)kPPStages;
+            const int64_t xtile_bytes = (int64_t)(P.kpe + P.kaux) * kTileM * 2;
             for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
                 const int64_t t0 = 2 * pr;
-                const int64_t tiles[2] = {t0, t0 + 1};
-                const unsigned char* wsub[2] = {nullptr, nullptr};
                 const int sub0 = sub_of(t0);
-                for (int sl = 0; sl < 2; ++sl)
-                    if (tiles[sl] < n_tiles) wsub[sl] = A.wpack + (size_t)sub0 * P.sub_bytes;
+                const unsigned char* wsub = A.wpack + (size_t)sub0 * P.sub_bytes;
+                const unsigned char* xt0 = reinterpret_cast<const unsigned char*>(A.ximg) + t0 * xtile_bytes;
+                const bool valid1 = t0 + 1 < n_tiles;
                 if (sub0 != last_sub) {
                     // the bias / sigma block is re-staged only when the sub-module changes (a handful of times per launch):
                     // the weight stream of consecutive pairs is not interrupted by waiting for the epilogue
                     if (last_sub >= 0) { mbar_wait(&f32_empty[0], fph_e); fph_e ^= 1; }
-                    const unsigned char* fsrc = wsub[0] + (size_t)P.plane_bytes * 2;
+                    const unsigned char* fsrc = wsub + (size_t)P.plane_bytes * 2;
                     if (kBiasMma) {
                         const uint32_t sb = (uint32_t)(P.L + 4) * 4u;
                         mbar_expect_tx(&f32_full[0], sb + 128u);
@@ -1156,112 +1245,89 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_pp_kernel(const TcArgs A) 
                     }
                     last_sub = sub0;
                 }
-                for (int gi = 0; gi < n_gemm; ++gi) {
-                    const TcGemm& g = P.g[gi];
-                    for (int sl = 0; sl < 2; ++sl) {
-                        if (!wsub[sl]) continue;
-                        const unsigned char* wimg = wsub[sl] + g.w_off;
-                        int kbase = 0;
-                        for (int sgi = 0; sgi < g.nseg; ++sgi) {
-                            const int kseg = g.k[sgi] + ((kBiasMma && g.src[sgi] == SRC_H) ? g.kext : 0);
-                            if (g.src[sgi] != SRC_H) {
-                                // feature segment: 16 K-columns of weights + the same 16 K-columns of the tile's feature image
-                                const __half* xt = A.ximg + tiles[sl] * (int64_t)(P.kpe + P.kaux) * kTileM +
-                                                   (g.src[sgi] == SRC_XAUX ? (int64_t)P.kpe * kTileM : 0);
-                                const uint32_t wbytes = (uint32_t)(kPPXCols * g.n * 2), xbytes = (uint32_t)(kPPXCols * kTileM * 2);
-                                for (int k0 = 0; k0 < kseg; k0 += kPPXCols) {
-                                    unsigned char* st_base = ring + (size_t)stage * kPPStageBytes;
-                                    mbar_wait(&empty[stage], phase ^ 1);
-                                    if (A.nofetch) { mbar_arrive(&full[stage]); if (++stage == kPPStages) { stage = 0; phase ^= 1; } continue; }
-                                    mbar_expect_tx(&full[stage], wbytes + xbytes);
-                                    bulk_g2s(st_base, wimg + (size_t)(kbase + k0) * g.n * 2, wbytes, &full[stage]);
-                                    bulk_g2s(st_base + kPPXOff, xt + (size_t)k0 * kTileM, xbytes, &full[stage]);
-                                    if (++stage == kPPStages) { stage = 0; phase ^= 1; }
-                                }
-                            } else {
-                                for (int k0 = 0; k0 < kseg; k0 += kPPSlabCols) {
-                                    const int kc = min(kPPSlabCols, kseg - k0);
-                                    const uint32_t bytes = (uint32_t)(kc * g.n * 2);
-                                    mbar_wait(&empty[stage], phase ^ 1);
-                                    if (A.nofetch) { mbar_arrive(&full[stage]); if (++stage == kPPStages) { stage = 0; phase ^= 1; } continue; }
-                                    mbar_expect_tx(&full[stage], bytes);
-                                    bulk_g2s(ring + (size_t)stage * kPPStageBytes, wimg + (size_t)(kbase + k0) * g.n * 2, bytes,
-                                             &full[stage]);
-                                    if (++stage == kPPStages) { stage = 0; phase ^= 1; }
-                                }
-                            }
-                            kbase += kseg;
-                        }
-                    }
+                for (int e = 0; e < n_prog; ++e) {
+                    const uint4 E = PROG[e];
+                    const bool slot1 = (E.z & PF_SLOT1) != 0;
+                    if (slot1 && !valid1) continue;
+                    const uint32_t cur = stage;
+                    if (!ahead) mbar_wait_a(empty_pa + 8u * cur, phase ^ 1);
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
+                    ahead = mbar_test_a(empty_pa + 8u * stage, phase ^ 1);       // next stage: latency overlaps the copies below
+                    const uint32_t bar = full_pa + 8u * cur, dst = ring_pa + cur * (uint32_t)kPPStageBytes;
+                    const uint32_t wbytes = E.y & 0xFFFFu, xo = E.y >> 16;
+                    const bool has_x = xo != 0xFFFFu;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(wbytes + (has_x ? (uint32_t)(kPPXCols * kTileM * 2) : 0u)) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "l"(wsub + E.x), "r"(wbytes), "r"(bar) : "memory");
+                    if (has_x)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(dst + (uint32_t)kPPXOff), "l"(xt0 + (slot1 ? xtile_bytes : 0) + (int64_t)(xo << 4)),
+                                       "r"((uint32_t)(kPPXCols * kTileM * 2)), "r"(bar) : "memory");
                 }
             }
         }
     } else if (warp == kWarpMma) {
-        // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
-        int stage = 0;
-        uint32_t phase = 0, eph0 = 0, eph1 = 0;
+        // =========================== MMA issuer (whole warp, one elected lane issues): table-driven (PROG) ===========================
+        uint32_t stage = 0, phase = 0, eph0 = 0, eph1 = 0;
+        uint32_t ahead = 0;              // the look-ahead probe of the CURRENT stage's full barrier already succeeded
         bool started0 = false, started1 = false;
         const uint32_t h_base = smem_u32(Hs), ring_base = smem_u32(ring);
         const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
         const uint32_t acc_full_a = smem_u32(acc_full), epi_done_a = smem_u32(epi_done);
+        const uint32_t nst = (uint32_t)kPPStages;
         const uint64_t xd0 = make_desc(ring_base + (uint32_t)kPPXOff, kTileM * 16, 128);
+        const uint64_t bd_base = make_desc(ring_base, 0, 128);                 // LBO (= N * 16 bytes) is added per entry
+        const uint64_t hd0 = make_desc(h_base, kTileM * 16, 128), hd1 = make_desc(h_base + (uint32_t)h_bytes, kTileM * 16, 128);
         const uint64_t a_step = (uint64_t)((2 * kTileM * 16) >> 4);
         const uint64_t st_step = (uint64_t)(kPPStageBytes >> 4);
+        uint32_t accum = 0;
         for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
-            const int64_t t0 = 2 * pr;
-            const bool valid1 = t0 + 1 < n_tiles;
-            for (int gi = 0; gi < n_gemm; ++gi) {
-                const TcGemm& g = P.g[gi];
-                const uint32_t idesc = make_idesc(g.n);
-                const uint64_t b_step = (uint64_t)((2 * g.n * 16) >> 4);
-                const uint64_t bd0 = make_desc(ring_base, (uint32_t)g.n * 16, 128);
-                for (int sl = 0; sl < 2; ++sl) {
-                    if (sl == 1 && !valid1) continue;
+            const bool valid1 = 2 * pr + 1 < n_tiles;
+            uint4 E = PROG[0];
+            for (int e = 0; e < n_prog;) {
+                const uint32_t fl = E.z & 0xFFu, N = E.z >> 8;
+                const uint4 E1 = PROG[e + 1], E2 = PROG[e + 2];      // prefetched: the table has two spare entries at its end
+                if ((fl & PF_SLOT1) && !valid1) { ++e; E = E1; continue; }
+                const uint32_t sl = (fl & PF_SLOT1) ? 1u : 0u;
+                if (fl & PF_FIRST) {
                     // the previous GEMM of this tile slot has been drained from TMEM and its activations are in H[sl]
-                    if (A.nofetch < 2) {
                     if (sl == 0) { if (started0) { mbar_wait_a(epi_done_a, eph0); eph0 ^= 1; } started0 = true; }
                     else         { if (started1) { mbar_wait_a(epi_done_a + 8, eph1); eph1 ^= 1; } started1 = true; }
-                    }
-                    tc_fence_after();
-                    if (lane == 0) trace_ev(A.desc_swap, 0, 1, sl, gi);          // MMA: dependencies satisfied, start issuing
-                    const uint32_t d_tmem = tmem_base + (uint32_t)sl * 256u;
-                    uint32_t accum = 0;
-                    for (int sgi = 0; sgi < g.nseg; ++sgi) {
-                        const bool from_x = g.src[sgi] != SRC_H;
-                        int rem = g.k[sgi] + ((kBiasMma && !from_x) ? g.kext : 0);
-                        if (from_x) {
-                            // one K=16 MMA per stage; the A operand (feature columns) sits in the stage itself
-                            for (; rem > 0; rem -= kPPXCols) {
-                                const uint64_t so = (uint64_t)stage * st_step;
-                                if (A.nofetch < 4) mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
-                                tc_fence_after();
-                                mma_stage(d_tmem, xd0 + so, bd0 + so, 0, 0, idesc, accum, 0u, empty_a + 8u * (uint32_t)stage);
-                                accum = 1;
-                                if (++stage == kPPStages) { stage = 0; phase ^= 1; }
-                            }
-                            continue;
-                        }
-                        uint64_t ad = make_desc(h_base + (uint32_t)(sl * h_bytes), kTileM * 16, 128);
-                        while (rem > 0) {
-                            const uint32_t two = rem >= 32 ? 1u : 0u;
-                            const uint64_t bd = bd0 + (uint64_t)stage * st_step;
-                            if (A.nofetch < 4) mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
-                            tc_fence_after();
-                            mma_stage(d_tmem, ad, bd, ad + a_step, bd + b_step, idesc, accum, two, empty_a + 8u * (uint32_t)stage);
-                            accum = 1;
-                            ad += two ? 2 * a_step : a_step;
-                            rem -= 32;
-                            if (++stage == kPPStages) { stage = 0; phase ^= 1; }
-                        }
-                    }
-                    commit_elect(acc_full_a + 8u * (uint32_t)sl);
-                    if (lane == 0) trace_ev(A.desc_swap, 0, 2, sl, gi);          // MMA: all MMAs of this GEMM issued
+                    accum = 0;
                 }
+                const uint32_t cur = stage;
+                if (!ahead) mbar_wait_a(full_a + 8u * cur, phase);
+                if (++stage == nst) { stage = 0; phase ^= 1; }
+                if (fl & PF_PAIR) {
+                    // two activation stages (up to 4 MMAs) per iteration: the loop overhead of this single warp - not the data -
+                    // is what paces the kernel (ncu: it never waits on `full`, it is busy with ~90 instructions per stage)
+                    const uint32_t cur1 = stage;
+                    if (!mbar_test_a(full_a + 8u * cur1, phase)) mbar_wait_a(full_a + 8u * cur1, phase);
+                    tc_fence_after();
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
+                    ahead = mbar_test_a(full_a + 8u * stage, phase);
+                    const uint64_t ad = (sl ? hd1 : hd0) + (uint64_t)E.w;
+                    const uint64_t bb = bd_base + ((uint64_t)N << 16);
+                    mma_stage2(tmem_base + sl * 256u, ad, a_step, bb + (uint64_t)cur * st_step, bb + (uint64_t)cur1 * st_step, (uint64_t)(2u * N),
+                               make_idesc((int)N), accum, ((E1.z & PF_TWO) ? 2u : 1u), empty_a + 8u * cur, empty_a + 8u * cur1);
+                    accum = 1;
+                    if (E1.z & PF_LAST) commit_elect(acc_full_a + 8u * sl);
+                    e += 2;
+                    E = E2;
+                    continue;
+                }
+                tc_fence_after();
+                ahead = mbar_test_a(full_a + 8u * stage, phase);              // next stage, overlapped with the issue below
+                const uint64_t so = (uint64_t)cur * st_step;
+                const uint64_t ad = (fl & PF_FROM_X) ? xd0 + so : (sl ? hd1 : hd0) + (uint64_t)E.w;
+                const uint64_t bd = bd_base + so + ((uint64_t)N << 16);        // LBO field = N * 16 bytes >> 4 = N
+                mma_stage(tmem_base + sl * 256u, ad, bd, ad + a_step, bd + (uint64_t)(2u * N), make_idesc((int)N), accum,
+                          (fl & PF_TWO) ? 1u : 0u, empty_a + 8u * cur);
+                accum = 1;
+                if (fl & PF_LAST) commit_elect(acc_full_a + 8u * sl);
+                ++e;
+                E = E1;
             }
-        }
-        if (A.nofetch >= 4) {   // debug: nobody consumed the accumulators; drain the tensor pipe before TMEM is freed
-            commit_elect(smem_u32(&f32_full[1]));
-            mbar_wait_a(smem_u32(&f32_full[1]), 0);
         }
     } else if (A.nofetch < 4) {
         // =========================== epilogue (16 warps) ===========================
@@ -1544,7 +1610,8 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     const bool bias_mma = !split && P.L <= 256 && !run_c2 && !run_ts && use_pp && bias_mma_env && P.bias_mma_ok &&
                           pp_layout(P, true).total <= kSmemMax && pp_layout(P, true).stages >= 3;
     const PPLayout PL = pp_layout(P, bias_mma);
-    const bool run_pp = !split && P.L <= 256 && !run_c2 && !run_ts && use_pp && PL.total <= kSmemMax;
+    const bool run_pp = !split && P.L <= 256 && !run_c2 && !run_ts && use_pp && PL.total <= kSmemMax && PL.stages >= 3 &&
+                        pp_prog_entries(P, P.n_gemm, bias_mma) + 2 <= kPPMaxProg;
     const int ones = (bias_mma && run_pp) ? 1 : 0;     // the feature tiles carry the constant-1 columns only for that kernel
 
     const size_t enc_sm = (size_t)P.x_tile_bytes * (split ? 2 : 1);
@@ -1632,11 +1699,11 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
             if (bias_mma) {
                 MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
                 mn_prof_begin(ctx, st);
-                tc_mlp_pp_kernel<true><<<grid_pp, kThreads, PL.total, st>>>(A);
+                tc_mlp_pp_kernel<true><<<grid_pp, kPPThreads, PL.total, st>>>(A);
             } else {
                 MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
                 mn_prof_begin(ctx, st);
-                tc_mlp_pp_kernel<false><<<grid_pp, kThreads, PL.total, st>>>(A);
+                tc_mlp_pp_kernel<false><<<grid_pp, kPPThreads, PL.total, st>>>(A);
             }
         } else {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
