@@ -14,7 +14,6 @@
 // i.e. [K/8][R][8] fp16.  UMMA descriptor: LBO = R*16 (next 8-column chunk), SBO = 128 (next 8-row group).
 // The epilogue's per-row 16-byte stores and the packer's images are contiguous in this layout, any K that
 // is a multiple of 16 works, and no TMA tensor map is needed (plain 1-D bulk copies).
-#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -72,11 +71,6 @@ struct TcGemm {
     int w_off;       // byte offset of the weight image inside one precision plane of a sub-module
     int bias_off;    // float offset inside the sub-module's fp32 block
     int epi;
-    // Bias folded into the GEMM (TcArgs::bias_mma): two rows of the weight image hold fp16(b) and fp16(b - fp16(b)); the A
-    // operand has the constant 1.0 in the two matching K columns, so the accumulator starts from the fp32-accurate bias and
-    // the epilogue neither loads nor adds it (those loads cost as many shared-memory wavefronts as the activation stores).
-    int kext;        // 16 extra K columns appended to an activation-only GEMM (constant columns L, L+1 of the H buffer), else 0
-    int bias_row;    // K index of the fp16(b) row inside the (padded, extended) image; -1: bias stays in the epilogue (rgb head)
 };
 
 struct TcPlan {
@@ -90,7 +84,6 @@ struct TcPlan {
     int x_tile_bytes;      // bytes of one feature tile image (one plane)
     int L;
     int bstride;           // floats reserved per GEMM bias in the fp32 block (256; 512 for the 512-wide network)
-    int bias_mma_ok;       // every trunk / head GEMM has a place for its bias rows (spare feature columns or the H extension)
 };
 
 int pad16(int x) { return (x + 15) / 16 * 16; }
@@ -102,11 +95,9 @@ bool build_plan(const NetDims& nd, TcPlan* p) {
     P = TcPlan{};
     P.L = nd.L;
     P.bstride = nd.L > 256 ? 512 : 256;
-    // two spare (zero-padded) columns per feature segment are reserved for the constant 1.0 that multiplies the bias rows
-    P.kpe = pad16(nd.in_xyz + 2);
-    P.kaux = nd.aux > 0 ? pad16(nd.aux + 2) : 0;
+    P.kpe = pad16(nd.in_xyz);
+    P.kaux = nd.aux > 0 ? pad16(nd.aux) : 0;
     int woff = 0, ng = 0;
-    P.bias_mma_ok = nd.L <= 256 ? 1 : 0;
     auto add = [&](int n, int s0, int k0, int s1, int k1, int epi) {
         TcGemm& g = P.g[ng];
         g.n = n;
@@ -115,23 +106,7 @@ bool build_plan(const NetDims& nd, TcPlan* p) {
         g.w_off = woff;
         g.bias_off = ng * P.bstride;
         g.epi = epi;
-        g.kext = 0;
-        g.bias_row = -1;
-        if (epi != EPI_RGB && nd.L <= 256) {
-            // spare (zero-padded) columns of a feature segment carry the constant 1.0 for free; an activation-only GEMM gets
-            // 16 extra K columns instead
-            int off = 0;
-            for (int sgi = 0; sgi < g.nseg; ++sgi) {
-                const int real = g.src[sgi] == SRC_XPE ? nd.in_xyz : (g.src[sgi] == SRC_XAUX ? nd.aux : -1);
-                if (real >= 0 && g.k[sgi] - real >= 2 && g.bias_row < 0) g.bias_row = off + real;
-                off += g.k[sgi];
-            }
-            if (g.bias_row < 0) {
-                if (g.nseg == 1 && s0 == SRC_H) { g.kext = 16; g.bias_row = k0; }
-                else P.bias_mma_ok = 0;
-            }
-        }
-        woff += (k0 + k1 + g.kext) * n * 2;
+        woff += (k0 + k1) * n * 2;
         ++ng;
     };
     for (int i = 0; i < nd.layers; ++i) {
@@ -260,23 +235,18 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 // One 16-column piece of the epilogue for one accumulator row: TMEM -> +bias -> (ReLU) -> fp16 (hi [, lo]) ->
 // two 16-byte stores into the next layer's A operand.  Returns the partial sigma dot product if kSigma.
-// kBias = false: the accumulator already contains the bias (TcArgs::bias_mma), nothing is loaded or added here.
-template <bool kSplit, bool kRelu, bool kSigma, bool kBias = true>
+template <bool kSplit, bool kRelu, bool kSigma>
 __device__ __forceinline__ float epi_piece16(uint32_t taddr, const float* __restrict__ bias16, const float* __restrict__ sw16,
                                              unsigned char* dst, size_t lo_off, bool store) {
     uint32_t v[16];
     tmem_ld16(taddr, v);
-    float b[16];
-    if (kBias) {
-        const float4* b4 = reinterpret_cast<const float4*>(bias16);
-        const float4 b0 = b4[0], b1 = b4[1], b2 = b4[2], b3 = b4[3];
-        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
-        b[8] = b2.x; b[9] = b2.y; b[10] = b2.z; b[11] = b2.w; b[12] = b3.x; b[13] = b3.y; b[14] = b3.z; b[15] = b3.w;
-    }
+    const float4* b4 = reinterpret_cast<const float4*>(bias16);
+    const float4 b0 = b4[0], b1 = b4[1], b2 = b4[2], b3 = b4[3];
+    const float b[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
     tmem_ld_wait();
     float f[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = kBias ? __uint_as_float(v[i]) + b[i] : __uint_as_float(v[i]);
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + b[i];
     float sacc = 0.0f;
     if (kSigma || kSplit) {
         if (kRelu) {
@@ -365,8 +335,7 @@ __device__ __forceinline__ void tc_emit_rgb(const MlpArgs& m, int sub, int64_t r
 // weight packing: nn.Linear weight [N_src][K_src] fp32 -> image [K/8][N][8] fp16 (hi) and the residual (lo)
 // ------------------------------------------------------------------------------------------------
 __global__ void tc_pack_kernel(const float* __restrict__ wt /* packed fp32, K-major Wt[k][n_src] */, int n_src, int k_src,
-                               int N, int K, int k_real0, int k_pad0, __half* __restrict__ hi, __half* __restrict__ lo,
-                               const float* __restrict__ bias, int n_bias, int bias_row) {
+                               int N, int K, int k_real0, int k_pad0, __half* __restrict__ hi, __half* __restrict__ lo) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)N * K) return;
     // i enumerates the image linearly: ((k/8)*N + n)*8 + k%8
@@ -374,15 +343,6 @@ __global__ void tc_pack_kernel(const float* __restrict__ wt /* packed fp32, K-ma
     const int n = (int)((i / 8) % N);
     const int kc = (int)(i / (8 * (int64_t)N));
     const int k = kc * 8 + k8;
-    if (bias_row >= 0 && (k == bias_row || k == bias_row + 1)) {
-        // bias rows (TcGemm::bias_row): fp16(b), then the fp16 residual - their sum against the A operand's constant 1.0
-        // columns reproduces b to ~2^-22 relative inside the fp32 accumulator
-        const float b = n < n_bias ? bias[n] : 0.0f;
-        const __half bh = __float2half_rn(b);
-        hi[i] = k == bias_row ? bh : __float2half_rn(b - __half2float(bh));
-        if (lo) lo[i] = __float2half_rn(0.0f);
-        return;
-    }
     int ks;
     if (k < k_pad0) ks = k < k_real0 ? k : -1;
     else ks = k_real0 + (k - k_pad0);
@@ -422,7 +382,7 @@ __global__ void tc_pack_f32_kernel(const float* __restrict__ src, int n, float* 
 // feature tiles
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTileM) tc_encode_kernel(const MlpArgs a, int kpe, int kaux, int split,
-                                                           __half* __restrict__ ximg, int64_t plane_stride_halves, int ones) {
+                                                           __half* __restrict__ ximg, int64_t plane_stride_halves) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __half* img = reinterpret_cast<__half*>(sm_raw);                  // hi image, then lo image
     const int ktot = kpe + kaux;
@@ -489,12 +449,6 @@ __global__ void __launch_bounds__(kTileM) tc_encode_kernel(const MlpArgs a, int 
             for (int c = col; c < ktot; ++c) put(c, 0.0f);
         }
     }
-    if (ones) {
-        // constant columns that multiply the bias rows of the weight images (TcGemm::bias_row)
-        put(nd.in_xyz, 1.0f);
-        put(nd.in_xyz + 1, 1.0f);
-        if (kaux > 0) { put(kpe + nd.aux, 1.0f); put(kpe + nd.aux + 1, 1.0f); }
-    }
     __syncthreads();
     const int nvec = ktot * kTileM * 2 / 16;
     const uint4* s4 = reinterpret_cast<const uint4*>(img);
@@ -526,11 +480,11 @@ __device__ __forceinline__ void pe_band(float x, int k, float* s, float* c) {
 // channels in registers and writes the tile image straight to global memory with 16-byte stores (thread t of a
 // chunk writes bytes [t*16, t*16+16) -> fully coalesced); no shared-memory staging, no 2-byte bank-conflicted stores.
 template <int XD, int NFX, int NFD, int APP>
-__global__ void __launch_bounds__(kTileM) tc_encode_fast_kernel(const MlpArgs a, __half* __restrict__ ximg, int ones) {
+__global__ void __launch_bounds__(kTileM) tc_encode_fast_kernel(const MlpArgs a, __half* __restrict__ ximg) {
     constexpr int IN_XYZ = XD * (1 + 2 * NFX);
-    constexpr int KPE = (IN_XYZ + 2 + 15) / 16 * 16;
+    constexpr int KPE = (IN_XYZ + 15) / 16 * 16;
     constexpr int IN_DIR = NFD > 0 ? 3 + 6 * NFD : 0;
-    constexpr int KAUX = (IN_DIR + APP + 2 + 15) / 16 * 16;
+    constexpr int KAUX = (IN_DIR + APP + 15) / 16 * 16;
     const int t = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t slot0 = tile * kTileM;
@@ -558,7 +512,6 @@ __global__ void __launch_bounds__(kTileM) tc_encode_fast_kernel(const MlpArgs a,
                 }
             }
         }
-        if (ones) { v[IN_XYZ] = 1.0f; v[IN_XYZ + 1] = 1.0f; }     // constant columns for the bias rows (TcGemm::bias_row)
 #pragma unroll
         for (int c = 0; c < KPE / 8; ++c)
             out[c * kTileM] = make_uint4(pack_h2(v[8 * c], v[8 * c + 1]), pack_h2(v[8 * c + 2], v[8 * c + 3]),
@@ -602,7 +555,6 @@ __global__ void __launch_bounds__(kTileM) tc_encode_fast_kernel(const MlpArgs a,
                 }
             }
         }
-        if (ones) { v[IN_DIR + APP] = 1.0f; v[IN_DIR + APP + 1] = 1.0f; }
 #pragma unroll
         for (int c = 0; c < KAUX / 8; ++c)
             out[(KPE / 8 + c) * kTileM] = make_uint4(pack_h2(v[8 * c], v[8 * c + 1]), pack_h2(v[8 * c + 2], v[8 * c + 3]),
@@ -690,27 +642,8 @@ __device__ __forceinline__ void commit_elect(uint32_t bar_addr) {
 }
 
 
-// up to four K=16 steps against one ring stage; A either from TMEM (address + 8 columns per step) or from
-// shared memory (descriptor + a_step per step); one elected lane issues, then releases the stage.
-__device__ __forceinline__ void ts_stage_tmem(uint32_t d_tmem, uint32_t a_tmem, uint64_t bd, uint64_t b_step, uint32_t idesc,
-                                              uint32_t accum, int nk, uint32_t empty_bar) {
-    asm volatile(
-        "{\n\t.reg .pred e, p, q1, q2, q3;\n\t.reg .b64 b1, b2, b3;\n\t.reg .b32 a1, a2, a3;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "setp.gt.and.s32 q1, %6, 1, e;\n\t"
-        "setp.gt.and.s32 q2, %6, 2, e;\n\t"
-        "setp.gt.and.s32 q3, %6, 3, e;\n\t"
-        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
-        "add.u64 b1, %2, %3;\n\tadd.u64 b2, b1, %3;\n\tadd.u64 b3, b2, %3;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %4, p;\n\t"
-        "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %4, 1;\n\t"
-        "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %4, 1;\n\t"
-        "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %4, 1;\n\t"
-        "@e  tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(bd), "l"(b_step), "r"(idesc), "r"(accum), "r"(nk), "r"(empty_bar)
-        : "memory");
-}
+// up to four K=16 steps against one ring stage (A from shared memory: descriptor + a_step per step); one elected lane issues,
+// then releases the stage.
 __device__ __forceinline__ void ts_stage_smem(uint32_t d_tmem, uint64_t ad, uint64_t a_step, uint64_t bd, uint64_t b_step,
                                               uint32_t idesc, uint32_t accum, int nk, uint32_t empty_bar) {
     asm volatile(
@@ -731,29 +664,6 @@ __device__ __forceinline__ void ts_stage_smem(uint32_t d_tmem, uint64_t ad, uint
         : "memory");
 }
 
-// Probe up to four mbarriers back to back (their ~100-cycle try_wait latencies overlap), then block on whatever
-// was not ready yet.  Unused slots repeat a valid (address, parity) pair.
-__device__ __forceinline__ void mbar_wait4(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1, uint32_t a2, uint32_t p2, uint32_t a3,
-                                           uint32_t p3) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred q0, q1, q2, q3;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
-        "and.pred q0, q0, q1;\n\tand.pred q2, q2, q3;\n\tand.pred q0, q0, q2;\n\t"
-        "selp.u32 %0, 1, 0, q0;\n\t}"
-        : "=r"(ok)
-        : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2), "r"(a3), "r"(p3)
-        : "memory");
-    if (ok) return;
-    mbar_wait_a(a0, p0);
-    mbar_wait_a(a1, p1);
-    mbar_wait_a(a2, p2);
-    mbar_wait_a(a3, p3);
-}
-
 
 // ------------------------------------------------------------------------------------------------
 // the MLP kernel
@@ -766,13 +676,7 @@ struct TcArgs {
     int64_t x_plane_halves;
     int split;                    // 1: three MMA passes (hi*hi + hi*lo + lo*hi)
     int desc_swap;                // debug: 1 = record the in-kernel timeline (MN_TC_TRACE)
-    int nofetch;                  // debug (MN_TC_NOFETCH=1): producers skip the TMA copies (garbage results; isolates the
-                                  // MMA + epilogue pipeline from the weight stream when timing)
     int64_t n_tiles_cap;
-    int c2_share;                 // CTA-pair kernel (MN_TC_C2SHARE=1): activation-only GEMMs stream their weights once for BOTH tile
-                                  // slots of a cluster iteration (stages stay resident between slot 0's and slot 1's MMAs)
-    int c2_relay;                 // CTA-pair kernel (MN_TC_C2=2): the peer's epilogue warps arrive on a LOCAL barrier and its idle MMA
-                                  // warp forwards ONE remote arrive per GEMM and slot to the leader (instead of 16 remote arrives)
 };
 
 struct SmemLayout {
@@ -1078,19 +982,16 @@ struct PPLayout {
 constexpr int kPPMaxProg = 208;
 enum { PF_SLOT1 = 1, PF_FIRST = 2, PF_LAST = 4, PF_FROM_X = 8, PF_TWO = 16, PF_PAIR = 32 };   // PF_PAIR: this and the next entry are consecutive activation stages of one GEMM - the MMA warp issues them together
 
-// bias_mma: the H buffers have 16 extra K columns (constant 1.0 in columns L and L+1) and the staged fp32 block shrinks
-// to [sigma_w (L) | sigma_b (4) | rgb bias (32)] - the biases of all other GEMMs ride in the weight images.
-__host__ __device__ inline int pp_h_bytes(const TcPlan& p, bool bias_mma) { return (p.L + (bias_mma ? 16 : 0)) * kTileM * 2; }
-__host__ __device__ inline PPLayout pp_layout(const TcPlan& p, bool bias_mma) {
+__host__ __device__ inline PPLayout pp_layout(const TcPlan& p) {
     PPLayout s;
-    s.f32_stride = bias_mma ? (p.L + 4 + 32) * 4 : ((p.f32_floats * 4 + 15) / 16) * 16;
-    const int fixed = 2 * pp_h_bytes(p, bias_mma) + s.f32_stride + 2048 + 256 + kPPMaxProg * 16;
+    s.f32_stride = ((p.f32_floats * 4 + 15) / 16) * 16;
+    const int fixed = 2 * p.L * kTileM * 2 + s.f32_stride + 2048 + 256 + kPPMaxProg * 16;
     int kPPStages = (kSmemMax - fixed) / kPPStageBytes;
     if (kPPStages > kPPMaxStages) kPPStages = kPPMaxStages;
     s.stages = kPPStages;
     s.ring = 0;
     s.h = kPPStages * kPPStageBytes;
-    s.f32 = s.h + 2 * pp_h_bytes(p, bias_mma);
+    s.f32 = s.h + 2 * p.L * kTileM * 2;
     s.sigp = s.f32 + s.f32_stride;    // ONE fp32 block: both tiles of a pair belong to the same sub-module
     s.bars = s.sigp + 2048;
     s.prog = s.bars + 256;
@@ -1098,29 +999,23 @@ __host__ __device__ inline PPLayout pp_layout(const TcPlan& p, bool bias_mma) {
     return s;
 }
 
-__host__ __device__ inline int pp_gemm_stages(const TcGemm& g, bool bias_mma) {
+__host__ __device__ inline int pp_gemm_stages(const TcGemm& g) {
     int n = 0;
-    for (int sgi = 0; sgi < g.nseg; ++sgi) {
-        const bool fx = g.src[sgi] != SRC_H;
-        const int kk = g.k[sgi] + ((bias_mma && !fx) ? g.kext : 0);
-        n += fx ? (kk + kPPXCols - 1) / kPPXCols : (kk + kPPSlabCols - 1) / kPPSlabCols;
-    }
+    for (int sgi = 0; sgi < g.nseg; ++sgi)
+        n += g.src[sgi] != SRC_H ? (g.k[sgi] + kPPXCols - 1) / kPPXCols : (g.k[sgi] + kPPSlabCols - 1) / kPPSlabCols;
     return n;
 }
-__host__ __device__ inline int pp_prog_entries(const TcPlan& p, int n_gemm, bool bias_mma) {
+__host__ __device__ inline int pp_prog_entries(const TcPlan& p, int n_gemm) {
     int n = 0;
-    for (int gi = 0; gi < n_gemm; ++gi) n += 2 * pp_gemm_stages(p.g[gi], bias_mma);
+    for (int gi = 0; gi < n_gemm; ++gi) n += 2 * pp_gemm_stages(p.g[gi]);
     return n;
 }
 
-// kBiasMma: every bias except the rgb head's is part of its GEMM (TcGemm::bias_row / kext): the epilogue neither loads nor
-// adds biases - in the ncu capture of the previous version those broadcast loads were as many shared-memory wavefronts as
-// the activation stores, on a kernel whose shared-memory pipe (tensor-core operand reads + TMA fills + LSU) was 100 % busy.
-template <bool kBiasMma>
+// Ping-pong kernel (see the header of this section).  Warps 0..15 epilogue, 16 TMA producer, 17 MMA issuer.
 __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
-    const PPLayout SL = pp_layout(P, kBiasMma);
+    const PPLayout SL = pp_layout(P);
     const int kPPStages = SL.stages;
     unsigned char* ring = smem + SL.ring;
     unsigned char* Hs = smem + SL.h;
@@ -1139,15 +1034,14 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
     const int64_t n_slots = A.m.counters ? A.m.counters[CNT_NSLOTS] : A.m.B;
     const int64_t n_tiles = (n_slots + kTileM - 1) / kTileM;
     const int n_gemm = A.m.sigma_only ? P.n_trunk : P.n_gemm;
-    const int h_bytes = pp_h_bytes(P, kBiasMma);
-    // fp32 block in shared memory: the packed block as is, or (kBiasMma) [sigma_w | sigma_b | rgb bias]
-    const float* SW = kBiasMma ? F32 : F32 + P.sigma_w_off;
-    const float* RGBB = kBiasMma ? F32 + P.L + 4 : F32 + P.g[P.n_gemm - 1].bias_off;
+    const int h_bytes = P.L * kTileM * 2;
+    const float* SW = F32 + P.sigma_w_off;
+    const float* RGBB = F32 + P.g[P.n_gemm - 1].bias_off;
 
     // ---- stage program (see kPPMaxProg): entries in the order both roles walk a tile pair: GEMM, slot, segment, K
     uint4* PROG = reinterpret_cast<uint4*>(smem + SL.prog);
-    auto stages_of = [&](const TcGemm& g) -> int { return pp_gemm_stages(g, kBiasMma); };
-    const int n_prog = pp_prog_entries(P, n_gemm, kBiasMma);       // <= kPPMaxProg: checked by the launcher
+    auto stages_of = [&](const TcGemm& g) -> int { return pp_gemm_stages(g); };
+    const int n_prog = pp_prog_entries(P, n_gemm);       // <= kPPMaxProg: checked by the launcher
     if (threadIdx.x >= 64 && threadIdx.x < 66) PROG[n_prog + (threadIdx.x - 64)] = make_uint4(0u, 0u, 0u, 0u);   // read-ahead padding
     if ((int)threadIdx.x < 2 * n_gemm) {
         const int gi = threadIdx.x >> 1, sl = threadIdx.x & 1;
@@ -1159,7 +1053,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
         int kbase = 0, cnt = 0;
         for (int sgi = 0; sgi < g.nseg; ++sgi) {
             const bool fx = g.src[sgi] != SRC_H;
-            const int kk = g.k[sgi] + ((kBiasMma && !fx) ? g.kext : 0);
+            const int kk = g.k[sgi];
             const int step = fx ? kPPXCols : kPPSlabCols;
             for (int k0 = 0; k0 < kk; k0 += step, ++cnt, ++e) {
                 const int kc = min(step, kk - k0);
@@ -1172,13 +1066,6 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
             }
             kbase += kk;
         }
-    }
-    if (kBiasMma && threadIdx.x < 2 * kTileM) {
-        // constant K columns L .. L+15 of both activation buffers: (1, 1, 0, ..., 0) in every row
-        unsigned char* hx = Hs + (size_t)(threadIdx.x / kTileM) * h_bytes + (size_t)(P.L / 8) * (kTileM * 16) + (size_t)(threadIdx.x % kTileM) * 16;
-        *reinterpret_cast<uint4*>(hx) = make_uint4(0x3C003C00u, 0u, 0u, 0u);          // two fp16 1.0
-        *reinterpret_cast<uint4*>(hx + kTileM * 16) = make_uint4(0u, 0u, 0u, 0u);
-        fence_proxy_async();
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < kPPMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -1234,15 +1121,8 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
                     // the weight stream of consecutive pairs is not interrupted by waiting for the epilogue
                     if (last_sub >= 0) { mbar_wait(&f32_empty[0], fph_e); fph_e ^= 1; }
                     const unsigned char* fsrc = wsub + (size_t)P.plane_bytes * 2;
-                    if (kBiasMma) {
-                        const uint32_t sb = (uint32_t)(P.L + 4) * 4u;
-                        mbar_expect_tx(&f32_full[0], sb + 128u);
-                        bulk_g2s(reinterpret_cast<unsigned char*>(F32), fsrc + (size_t)P.sigma_w_off * 4, sb, &f32_full[0]);
-                        bulk_g2s(reinterpret_cast<unsigned char*>(F32) + sb, fsrc + (size_t)P.g[P.n_gemm - 1].bias_off * 4, 128u, &f32_full[0]);
-                    } else {
-                        mbar_expect_tx(&f32_full[0], f32_bytes);
-                        bulk_g2s(reinterpret_cast<unsigned char*>(F32), fsrc, f32_bytes, &f32_full[0]);
-                    }
+                    mbar_expect_tx(&f32_full[0], f32_bytes);
+                    bulk_g2s(reinterpret_cast<unsigned char*>(F32), fsrc, f32_bytes, &f32_full[0]);
                     last_sub = sub0;
                 }
                 for (int e = 0; e < n_prog; ++e) {
@@ -1329,7 +1209,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
                 E = E1;
             }
         }
-    } else if (A.nofetch < 4) {
+    } else {
         // =========================== epilogue (16 warps) ===========================
         const int q = warp & 3;
         const int part = warp >> 2;
@@ -1370,10 +1250,9 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
                     tc_fence_after();
                     if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 3, sl, gi);   // epilogue: accumulator ready
                     const uint32_t t_acc = t_lane + (uint32_t)sl * 256u;
-                    const float* bias = kBiasMma ? F32 : F32 + g.bias_off;      // kBiasMma: never dereferenced for trunk GEMMs
+                    const float* bias = F32 + g.bias_off;
                     const int64_t row = row_[sl], slot = slot_[sl];
-                    if (A.nofetch >= 3) {
-                    } else if (g.epi == EPI_RGB) {
+                    if (g.epi == EPI_RGB) {
                         if (part == 0) {
                             uint32_t v[32];
                             tmem_ld32(t_acc, v);
@@ -1392,11 +1271,11 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
                             if (c0 < g.n) {
                                 unsigned char* dst = Hsl + (size_t)(c0 >> 3) * (kTileM * 16) + (size_t)r * 16;
                                 if (g.epi == EPI_RELU)
-                                    epi_piece16<false, true, false, !kBiasMma>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
+                                    epi_piece16<false, true, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
                                 else if (g.epi == EPI_LINEAR)
-                                    epi_piece16<false, false, false, !kBiasMma>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
+                                    epi_piece16<false, false, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
                                 else
-                                    sacc += epi_piece16<false, true, true, !kBiasMma>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, publish);
+                                    sacc += epi_piece16<false, true, true>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, publish);
                             }
                         }
                         if (publish) fence_proxy_async();
@@ -1432,35 +1311,11 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
     }
 }
 
-#include "mn_mlp_ts.cuh"
-#include "mn_mlp_c2.cuh"
 #include "mn_mlp_wide.cuh"
 
 }  // namespace
 
 // =================================================================================================
-// Tensor map over a buffer viewed as [rows][256 B] with boxes of box_rows rows.  cuTensorMapEncodeTiled is resolved
-// through the runtime so that the library does not link against libcuda (it must load on GPU-less hosts).
-static bool encode_rows256_map(void* base, uint64_t rows, uint32_t box_rows, void* out128) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn enc = nullptr;
-    if (!enc) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
-        enc = reinterpret_cast<EncodeFn>(fn);
-    }
-    const cuuint64_t gdim[2] = {256, rows};
-    const cuuint64_t gstride[1] = {256};
-    const cuuint32_t estr[2] = {1, 1};
-    const cuuint32_t box[2] = {256, box_rows};
-    return enc(reinterpret_cast<CUtensorMap*>(out128), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 size_t mn_mlp_tc_workspace(const mn_model* m, int64_t n_tiles128, int precision) {
     TcPlan P;
     if (!build_plan(m->nd, &P)) return 0;
@@ -1475,22 +1330,14 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         return MN_OK;  // configuration only served by the fp32 kernel
     }
     const NetDims& nd = m->nd;
-    // [hi plane][lo plane][fp32 block, 256-aligned][half-major hi plane for the TS kernel]
-    const size_t ts_off = (size_t)P.plane_bytes * 2 + (size_t)(((P.f32_floats * 4 + 255) / 256) * 256);
-    const size_t c2_off = ts_off + (size_t)P.plane_bytes;      // [N-half of CTA 0][N-half of CTA 1] images for cta_group::2
+    // per sub-module: [hi plane][lo plane][fp32 block, 256-aligned]
     // 512-wide network: only the wide kernel runs it; its one image ([N half of 256][K/8][256][8]) lives in the hi plane
     const bool wide = nd.L > 256;
-    const size_t sub_bytes = wide ? mn_align(ts_off, 256) : mn_align(c2_off + (size_t)P.plane_bytes, 256);
+    const size_t sub_bytes = mn_align((size_t)P.plane_bytes * 2 + (size_t)(((P.f32_floats * 4 + 255) / 256) * 256), 256);
     if (!m->tc_packed) {
         MN_CUDA(ctx, cudaMalloc(&m->tc_packed, sub_bytes * m->d.n_sub));
         MN_CUDA(ctx, cudaMemsetAsync(m->tc_packed, 0, sub_bytes * m->d.n_sub, st));
         m->tc_sub_bytes = sub_bytes;
-        // tensor maps for the cta_group::2 kernel (its TMA loads must be the .tensor form to signal the peer CTA's barrier)
-        const uint64_t rows = (uint64_t)(sub_bytes * m->d.n_sub / 256);
-        const uint32_t boxes[4] = {64, 32, 8, 4};
-        m->tmap_ready = 1;
-        for (int b = 0; b < 4; ++b)
-            if (!encode_rows256_map(m->tc_packed, rows, boxes[b], m->tmap_w[b])) m->tmap_ready = 0;
     }
     unsigned char* base = (unsigned char*)m->tc_packed + (size_t)sub * sub_bytes;
     const float* Pk = m->packed + (size_t)sub * m->lay.total;
@@ -1508,19 +1355,7 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
             MN_LAUNCH_CHECK(ctx);
             return MN_OK;
         }
-        {
-            // hi / lo planes carry the bias rows and (activation-only GEMMs) the 16-column K extension; the other images do not
-            const int Kx = K + g.kext;
-            const int64_t nx = (int64_t)g.n * Kx;
-            tc_pack_kernel<<<(unsigned)mn_cdiv(nx, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, Kx, k_real0, k_pad0, hi, lo, bias, n_bias,
-                                                                     g.bias_row);
-        }
-        MN_LAUNCH_CHECK(ctx);
-        tc_pack_half_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, g.n < 128 ? g.n : 128, k_real0, k_pad0,
-                                                                    reinterpret_cast<__half*>(base + ts_off + g.w_off));
-        MN_LAUNCH_CHECK(ctx);
-        tc_pack_half_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, g.n / 2, k_real0, k_pad0,
-                                                                    reinterpret_cast<__half*>(base + c2_off + g.w_off));
+        tc_pack_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, k_real0, k_pad0, hi, lo);
         MN_LAUNCH_CHECK(ctx);
         tc_pack_f32_kernel<<<1, 256, 0, st>>>(bias, n_bias, f32 + g.bias_off, 256);
         MN_LAUNCH_CHECK(ctx);
@@ -1571,12 +1406,6 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         desc_swap = (e && e[0] == '1') ? 1 : 0;
     }
     A.desc_swap = desc_swap;
-    static int nofetch = -1;
-    if (nofetch < 0) {
-        const char* e = getenv("MN_TC_NOFETCH");
-        nofetch = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 0;   // 2: MMAs also ignore epi_done; 3: and the epilogue is empty
-    }
-    A.nofetch = nofetch;
     A.n_tiles_cap = n_tiles128;
     const size_t need = mn_mlp_tc_workspace(m, n_tiles128, precision);
     if (ws_bytes < need || !ws) return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_mlp_tc_launch: workspace too small");
@@ -1585,34 +1414,16 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     A.ximg = ximg;
     A.x_plane_halves = (int64_t)n_tiles128 * (P.kpe + P.kaux) * kTileM;
 
-    // ---- kernel selection (environment switches are read once per process; defaults: ping-pong kernel with the biases
-    // folded into the GEMMs for layer_dim <= 256, the wide kernel for 512, the split kernel for tc_f16x3)
-    static int use_pp = -1, bias_mma_env = -1, use_ts = -1, use_c2 = -1, c2_share = -1;
+    // ---- kernel selection: the ping-pong kernel for layer_dim <= 256 (MN_TC_PINGPONG=0: the single-tile kernel, kept as
+    // the cross-check of the variants test), the wide kernel for 512, the split kernel for tc_f16x3
+    static int use_pp = -1;
     if (use_pp < 0) {
         const char* e = getenv("MN_TC_PINGPONG");
         use_pp = (e && e[0] == '0') ? 0 : 1;
-        e = getenv("MN_TC_BIASMMA");
-        bias_mma_env = (e && e[0] == '1') ? 1 : 0;       // opt-in: measured 4 % SLOWER on B200 (907 vs 943 TFLOP/s) - see DESIGN.md §7
-        e = getenv("MN_TC_TS");
-        use_ts = (e && e[0] == '1') ? 1 : 0;
-        e = getenv("MN_TC_C2");
-        use_c2 = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 0;      // 1 pair, 2 + relay handshake, 3 + trailing epilogue
-        e = getenv("MN_TC_C2SHARE");
-        c2_share = (e && e[0] == '1') ? 1 : 0;
     }
-    A.c2_relay = use_c2 == 2 ? 1 : 0;
-    A.c2_share = c2_share;
-    const C2Layout CL = c2_layout(P, c2_share != 0);
-    const TsLayout TL = ts_layout(P);
-    const bool run_c2 = !split && P.L == 256 && use_c2 && !a.nd.affine && m->tmap_ready && CL.total <= kSmemMax &&
-                        CL.stages >= (c2_share ? 10 : 3) && (n_tiles128 % 4) == 0;
-    const bool run_ts = !split && P.L <= 256 && !run_c2 && use_ts && !a.nd.affine && P.L % 128 == 0 && TL.stages >= 4;
-    const bool bias_mma = !split && P.L <= 256 && !run_c2 && !run_ts && use_pp && bias_mma_env && P.bias_mma_ok &&
-                          pp_layout(P, true).total <= kSmemMax && pp_layout(P, true).stages >= 3;
-    const PPLayout PL = pp_layout(P, bias_mma);
-    const bool run_pp = !split && P.L <= 256 && !run_c2 && !run_ts && use_pp && PL.total <= kSmemMax && PL.stages >= 3 &&
-                        pp_prog_entries(P, P.n_gemm, bias_mma) + 2 <= kPPMaxProg;
-    const int ones = (bias_mma && run_pp) ? 1 : 0;     // the feature tiles carry the constant-1 columns only for that kernel
+    const PPLayout PL = pp_layout(P);
+    const bool run_pp = !split && P.L <= 256 && use_pp && PL.total <= kSmemMax && PL.stages >= 3 &&
+                        pp_prog_entries(P, P.n_gemm) + 2 <= kPPMaxProg;
 
     const size_t enc_sm = (size_t)P.x_tile_bytes * (split ? 2 : 1);
     MN_CUDA(ctx, cudaFuncSetAttribute(tc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_sm));
@@ -1620,9 +1431,9 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     const bool fast_shape = !split && ndE.xyz_dim == 3 && ndE.nf_xyz == 12 && ndE.nf_dir == 4 && ndE.app == 48 && ndE.app_in_dira &&
                             (m->lay.emb % 4) == 0;
     if (fast_shape)
-        tc_encode_fast_kernel<3, 12, 4, 48><<<(unsigned)n_tiles128, kTileM, 0, st>>>(a, ximg, ones);
+        tc_encode_fast_kernel<3, 12, 4, 48><<<(unsigned)n_tiles128, kTileM, 0, st>>>(a, ximg);
     else
-        tc_encode_kernel<<<(unsigned)n_tiles128, kTileM, enc_sm, st>>>(a, P.kpe, P.kaux, split, ximg, A.x_plane_halves, ones);
+        tc_encode_kernel<<<(unsigned)n_tiles128, kTileM, enc_sm, st>>>(a, P.kpe, P.kaux, split, ximg, A.x_plane_halves);
     MN_LAUNCH_CHECK(ctx);
 
     if (P.L > 256) {
@@ -1673,38 +1484,11 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         mn_prof_begin(ctx, st);
         tc_mlp_kernel<true><<<grid, kThreads, total, st>>>(A);
     } else {
-        if (run_c2) {
-            C2Maps maps;
-            memcpy(&maps.w64, m->tmap_w[0], 128);
-            memcpy(&maps.w32, m->tmap_w[1], 128);
-            memcpy(&maps.w8, m->tmap_w[2], 128);
-            memcpy(&maps.w4, m->tmap_w[3], 128);
-            const uint64_t xrows = (uint64_t)n_tiles128 * (uint64_t)(P.kpe + P.kaux);
-            if (!encode_rows256_map(ximg, xrows, 32, &maps.x32) || !encode_rows256_map(ximg, xrows, 16, &maps.x16))
-                return mn_fail(ctx, MN_ERR_CUDA, "cuTensorMapEncodeTiled failed for the feature tiles");
-            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_c2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL.total));
-            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_c2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL.total));
-            const int64_t n_quads = n_tiles128 / 4;
-            int64_t n_cl = n_quads < ctx->sm_count / 2 ? n_quads : ctx->sm_count / 2;
-            if (n_cl < 1) n_cl = 1;
-            mn_prof_begin(ctx, st);
-            if (use_c2 == 3) tc_mlp_c2_kernel<true><<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A, maps);
-            else tc_mlp_c2_kernel<false><<<(unsigned)(2 * n_cl), kThreads, CL.total, st>>>(A, maps);
-        } else if (run_ts) {
-            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL.total));
-            mn_prof_begin(ctx, st);
-            tc_mlp_ts_kernel<<<grid, kTsThreads, TL.total, st>>>(A);
-        } else if (run_pp) {
+        if (run_pp) {
             const unsigned grid_pp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
-            if (bias_mma) {
-                MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
-                mn_prof_begin(ctx, st);
-                tc_mlp_pp_kernel<true><<<grid_pp, kPPThreads, PL.total, st>>>(A);
-            } else {
-                MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
-                mn_prof_begin(ctx, st);
-                tc_mlp_pp_kernel<false><<<grid_pp, kPPThreads, PL.total, st>>>(A);
-            }
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
+            mn_prof_begin(ctx, st);
+            tc_mlp_pp_kernel<<<grid_pp, kPPThreads, PL.total, st>>>(A);
         } else {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
             mn_prof_begin(ctx, st);

@@ -164,7 +164,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_wide_kernel(const TcArgs A
                                     unsigned char* st_base = ring + (size_t)stage * kWStageBytes;
                                     const unsigned char* wsrc = wimg + (size_t)(kbase + k0) * nw * 2;
                                     mbar_wait(&empty[stage], phase ^ 1);
-                                    if (A.nofetch) { mbar_arrive(&full[stage]); if (++stage == kWStages) { stage = 0; phase ^= 1; } continue; }
                                     mbar_expect_tx(&full[stage], wbytes + xbytes);
                                     if (CS > 1) {
                                         const uint32_t slice = wbytes / CS;
@@ -182,7 +181,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_wide_kernel(const TcArgs A
                                 const int kc = min(kWSlabCols, kseg - k0);
                                 const uint32_t bytes = (uint32_t)(kc * nw * 2);
                                 mbar_wait(&empty[stage], phase ^ 1);      // CS > 1: released by every CTA of the cluster
-                                if (A.nofetch) { mbar_arrive(&full[stage]); if (++stage == kWStages) { stage = 0; phase ^= 1; } continue; }
                                 mbar_expect_tx(&full[stage], bytes);
                                 if (CS > 1) {
                                     const uint32_t slice = bytes / CS;

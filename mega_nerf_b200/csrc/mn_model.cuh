@@ -62,9 +62,6 @@ struct mn_model {
     void* tc_packed = nullptr;
     size_t tc_sub_bytes = 0;
     int tc_ready = 0;
-    // TMA tensor maps over tc_packed viewed as [rows][256 B] (boxes of 64, 32 and 8 rows); CUtensorMap is 128 B, 64-B aligned
-    alignas(64) unsigned char tmap_w[4][128] = {{0}};
-    int tmap_ready = 0;
 };
 
 // counters_d layout (ints)

@@ -20,12 +20,6 @@ case "${1:-help}" in
                          ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_train.csv python bench.py --mode train --steps 1 --warmup 3 > gpurun_out/l2.log 2>&1; tail -3 gpurun_out/l2.log' ;;
   ncu-mlp)      # full capture of the fine-pass launch of the forward MLP kernel
     $G --timeout 900 -- 'ncu --set full --import-source on --clock-control none -k regex:tc_mlp_pp_kernel -s 5 -c 1 -o gpurun_out/tc_mlp_pp_kernel python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-gpu-incumbent > gpurun_out/n1.log 2>&1; ls -la gpurun_out/*.ncu-rep' ;;
-  c2)           # A/B of the 256-wide kernels on one box: ping-pong (default), CTA pair, + relay handshake, + trailing epilogue
-    $G --timeout 900 -- 'for v in 0 1 2 3; do MN_TC_C2=$v python bench.py --steps 30 --no-cpu-baseline --no-gpu-incumbent > gpurun_out/bench_c2_$v.json 2>/dev/null; python -c "import json;d=json.load(open(\"gpurun_out/bench_c2_$v.json\"));print($v, d[\"ms_per_step\"], d[\"roofline\"][\"achieved\"], d[\"parity\"])"; done' ;;
-  c2-kernel)    # kernel-only timing (scripts/mlp_time.py: one 606k-row launch, single sub-module) of the same four kernels
-    $G --timeout 900 -- 'for v in 0 1 2 3; do echo "MN_TC_C2=$v"; MN_TC_C2=$v python scripts/mlp_time.py 256 32 2>&1 | tail -1; done | tee gpurun_out/c2_kernel_times.txt' ;;
-  ncu-c2)       # same for the CTA-pair kernel (the candidate for the next frac step)
-    $G --timeout 900 -- 'MN_TC_C2=1 ncu --set full --import-source on --clock-control none -k regex:tc_mlp_c2_kernel -s 5 -c 1 -o gpurun_out/tc_mlp_c2_kernel python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-gpu-incumbent > gpurun_out/n2.log 2>&1; ls -la gpurun_out/*.ncu-rep' ;;
   ncu-bwd)      # full capture of the two backward kernels
     $G --timeout 900 -- 'ncu --set full --import-source on --clock-control none -k regex:mlp_bwd -s 4 -c 2 -o gpurun_out/mlp_bwd_kernels python bench.py --mode train --steps 1 --warmup 3 > gpurun_out/n3.log 2>&1; ls -la gpurun_out/*.ncu-rep' ;;
   scale2)       # 2-GPU lines: ray-sharded (graded form) and owner-computes sub-modules

@@ -53,7 +53,7 @@ def num(v, unit):
 
 def main():
     out = []
-    for fn, (wl, prec, what) in sorted(REPORTS.items()):
+    for fn, (wl, prec, what) in sorted(REPORTS.items(), reverse=True):      # latest round first: bench.py takes the first match
         path = os.path.join(PROF, fn)
         if not os.path.exists(path):
             continue
