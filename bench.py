@@ -332,6 +332,7 @@ def run_train(args, rank, local_rank, world):
     spec, net, rays_h, idx_h, opts = workload()
     hp = Namespace(**vars(opts))
     model = build_net(net, dev, trainable=True).train()
+    M.set_train_precision(args.train_precision)
     opt = torch.optim.Adam(model.parameters(), lr=5e-4)
     rgbs_h = torch.rand(N_RAYS, 3, generator=torch.Generator().manual_seed(9))
     rays_pin, idx_pin, rgbs_pin = rays_h.pin_memory(), idx_h.pin_memory(), rgbs_h.pin_memory()
@@ -385,6 +386,15 @@ def run_train(args, rank, local_rank, world):
     clocks = sampler.stop()
     slots, _ = model._native().stats(dev)
     mult = slots / (N_RAYS * FINE)
+    on_tc = model._native().train_on_tensor_cores()
+    other = None
+    if args.train_precision == 'tc_f16':
+        # the fp32 (parity-mode) step on the same box for comparison, a few steps
+        M.set_train_precision('fp32')
+        for _ in range(2):
+            step_resident()
+        other = timed(step_resident, max(2, args.steps // 4)) / max(2, args.steps // 4)
+        M.set_train_precision(args.train_precision)
     pk = peaks()
     samples = N_RAYS * (COARSE + FINE)
     flops_step = 3 * samples * mult * flops_per_row(spec)          # forward + data gradients + weight gradients
@@ -393,19 +403,25 @@ def run_train(args, rank, local_rank, world):
     line = {
         'metric': 'training ray-samples/sec (forward + backward + Adam)', 'value': samples * args.steps / (ms * 1e-3),
         'unit': 'samples/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16 operands / f32 accumulate' if on_tc else 'f32', 'data': 'synthetic',
         'config': {'workload': f'{WL["desc"]}, {N_RAYS} rays x ({COARSE} coarse + {FINE} fine), train() mode (jitter, density '
                                f'noise, random resampling), boundary_margin {MARGIN} (m = {mult:.3f}), MSE vs random colours, Adam',
-                   'parallelism': 'single GPU', 'precision': 'fp32 (CUDA-core kernels; the only backward arithmetic so far)',
+                   'parallelism': 'single GPU',
+                   'precision': ('tc_f16: recording forward, data gradients and weight gradients on tcgen05 (fp16 operands, fp32 accumulate)'
+                                 if on_tc else 'fp32 (CUDA-core kernels, the parity mode)'),
+                   'fp32_parity_mode_ms_per_step': other,
                    'launch': 'eager', 'l2': f'flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)'},
         'e2e': {'value': samples * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': (rays_pin.numel() + idx_pin.numel() + rgbs_pin.numel()) * 4, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches_per_step * args.steps),
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': 'mlp_simt_kernel<SAVE> + mlp_bwd_data_kernel + mlp_bwd_weight_kernel',
+        'roofline': {'bound': 'tensor', 'kernel': ('tc_mlp_pp_kernel<TRAIN_FWD> + tc_mlp_pp_kernel<DGRAD> + tc_wgrad_kernel' if on_tc else
+                                                    'mlp_simt_kernel<SAVE> + mlp_bwd_data_kernel + mlp_bwd_weight_kernel'),
                      'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
                      'peak_source': pk['src'], 'traffic': None, 'kernel_ms_per_step': kms,
-                     'note': 'GEMM-shaped work still on the fp32 FMA pipe: the fraction is against the tensor-core peak on purpose'},
+                     'note': ('forward + backward MLP kernels timed by CUDA events on the launching stream; 3 x forward FLOPs'
+                              if on_tc else 'GEMM-shaped work on the fp32 FMA pipe: the fraction is against the tensor-core peak on purpose')},
     }
     print(json.dumps(line), flush=True)
 
@@ -504,6 +520,8 @@ def main():
     ap.add_argument('--gather', default='nccl', choices=['nccl', 'peer'],
                     help="N > 1: how the per-ray results are exchanged: 'nccl' = torch.cat + all_gather_into_tensor (default, graded); "
                          "'peer' = one kernel of ours storing into every rank's symmetric buffer over NVLink (mega_nerf_b200.dist.PeerGather)")
+    ap.add_argument('--train-precision', default='tc_f16', choices=['fp32', 'tc_f16'], help="--mode train: arithmetic of the recording forward "
+                    "and the backward pass ('fp32' = CUDA-core parity mode)")
     ap.add_argument('--mode', default='render', choices=['render', 'train', 'cluster'],
                     help="'render' = the graded line; 'train' = one optimisation step (forward + backward + Adam) of the same "
                          "workload through the recording path (SURVEY.md §8f-1); 'cluster' = the cluster-mask kernel on one "

@@ -292,6 +292,24 @@ int mn_model_param_offsets(const mn_model* m, int64_t* out, int n);
 int mn_model_backward(mn_ctx* ctx, mn_model* m, int64_t B, int use_coarse, const float* grad_out_d, const void* tape_d,
                       size_t tape_bytes, float* param_grads_d, void* workspace_d, size_t workspace_bytes, void* stream);
 
+/* ---- the same two passes on the tensor cores (precision tc_f16) --------------------------------------------------
+ * What the reference does on a GPU: Linear layers in fp16 with fp32 accumulation under autocast, gradients scaled into
+ * fp16 range (runner.py:243-274, opts.py:99).  Forward = the tc_f16 inference kernel writing every layer's fp16
+ * activations to the tape; backward = data gradients on transposed fp16 weight images (ReLU masks from the tape, gradient
+ * images scaled by a power of two chosen from max|grad_out|), weight gradients as tcgen05 contractions of the two tapes
+ * over the slot axis, fp32 accumulation, fp32 atomics into param_grads_d.  Same argument meaning as the fp32 entry points
+ * above; covers layer_dim 256 with a direction / appearance head and rgb_dim 3 (mn_model_train_tc_supported), everything
+ * else returns MN_ERR_UNSUPPORTED - use the fp32 entry points.  Gradients agree with the fp32 path to ~1e-2 of each
+ * tensor's scale (fp16 operands, like the reference under autocast); the fp32 entry points remain the parity mode. */
+int mn_model_train_tc_supported(const mn_model* m);
+size_t mn_model_tape_bytes_tc(const mn_model* m, int64_t B);
+int mn_model_forward_train_tc(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int use_coarse,
+                              const float* sigma_noise_d, float* out_d, void* tape_d, size_t tape_bytes, void* workspace_d,
+                              size_t workspace_bytes, void* stream);
+size_t mn_model_backward_workspace_bytes_tc(const mn_model* m, int64_t B);
+int mn_model_backward_tc(mn_ctx* ctx, mn_model* m, int64_t B, int use_coarse, const float* grad_out_d, const void* tape_d,
+                         size_t tape_bytes, float* param_grads_d, void* workspace_d, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,11 @@ SIGNATURES = {
     'mn_model_grad_floats': (_L, [_P]),
     'mn_model_param_offsets': (_I, [_P, C.POINTER(_L), _I]),
     'mn_model_backward': (_I, [_P, _P, _L, _I, _P, _P, _Z, _P, _P, _Z, _P]),
+    'mn_model_train_tc_supported': (_I, [_P]),
+    'mn_model_tape_bytes_tc': (_Z, [_P, _L]),
+    'mn_model_forward_train_tc': (_I, [_P, _P, C.POINTER(Rows), _L, _I, _P, _P, _P, _Z, _P, _Z, _P]),
+    'mn_model_backward_workspace_bytes_tc': (_Z, [_P, _L]),
+    'mn_model_backward_tc': (_I, [_P, _P, _L, _I, _P, _P, _Z, _P, _P, _Z, _P]),
 }
 MN_PARAM_OFFSETS = 44
 

@@ -234,6 +234,7 @@ void mn_model_destroy(mn_model* m) {
     if (m->centroids_d) cudaFree(m->centroids_d);
     if (m->counters_d) cudaFree(m->counters_d);
     if (m->tc_packed) cudaFree(m->tc_packed);
+    if (m->tc_dgrad) cudaFree(m->tc_dgrad);
     delete m;
 }
 
@@ -331,9 +332,12 @@ size_t mn_model_workspace_bytes(const mn_model* m, int64_t B, int precision) {
 #define MN_TAPE_HEADER 1024
 static_assert(CNT_TOTAL * sizeof(int) <= MN_TAPE_HEADER, "tape header too small");
 
+static size_t tape_bytes_tc(const mn_model* m, int64_t B);
+
+// train_tc != 0: recording forward on the tensor cores (precision tc_f16): tape layout of mn_model_tape_bytes_tc
 static int model_forward_impl(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int use_coarse, int sigma_only,
                               const float* sigma_noise_d, int precision, float* out_d, void* workspace_d,
-                              size_t workspace_bytes, void* tape_d, size_t tape_bytes, void* stream) {
+                              size_t workspace_bytes, void* tape_d, size_t tape_bytes, void* stream, int train_tc = 0) {
     if (!ctx || !m || !rows || B < 0) return MN_ERR_INVALID;
     const mn_model_desc& d = m->d;
     const NetDims& nd = m->nd;
@@ -408,7 +412,8 @@ static int model_forward_impl(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int
     auto tcarve = [&](size_t n) { char* p = tp; tp += mn_align(n); return p; };
     int* tape_counters = nullptr;
     if (tape_d) {
-        if (tape_bytes < mn_model_tape_bytes(m, B)) return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_model_forward_train: tape too small");
+        if (tape_bytes < (train_tc ? tape_bytes_tc(m, B) : mn_model_tape_bytes(m, B)))
+            return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_model_forward_train: tape too small");
         tape_counters = (int*)tcarve(MN_TAPE_HEADER);
     }
 
@@ -444,6 +449,15 @@ static int model_forward_impl(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int
     }
 
     const int64_t n_tiles = cap / MN_TILE;
+    if (tape_d && train_tc) {
+        TrainTcTape T;
+        T.xreg = (unsigned char*)tcarve((size_t)n_tiles * mn_train_tc_x_tile_bytes(m));
+        T.act = (unsigned char*)tcarve((size_t)n_tiles * mn_train_tc_act_tile_bytes(m));
+        T.f32 = (float*)tcarve((size_t)n_tiles * 5 * MN_TILE * sizeof(float));
+        if ((rc = mn_mlp_tc_launch_train(ctx, m, a, n_tiles, T, st))) return rc;
+        if (row_slots) return mn_route_combine(ctx, m, B, row_slots, slot_out, a.out_cols, out_d, st);
+        return MN_OK;
+    }
     if (tape_d) {
         a.tape = (float*)tp;
         a.tl = m->tape;
@@ -546,6 +560,80 @@ int mn_model_backward(mn_ctx* ctx, mn_model* m, int64_t B, int use_coarse, const
     a.act = (const float*)tp;
     a.grad = (float*)workspace_d;
     return mn_mlp_bwd_launch(ctx, a, cap / MN_TILE, (cudaStream_t)stream);
+}
+
+// ---- tensor-core training path (precision tc_f16 for the recording forward and the backward pass) ----------------
+static size_t tape_bytes_tc(const mn_model* m, int64_t B) {
+    const int64_t cap = slot_capacity(m, B);
+    const int64_t n_tiles = cap / MN_TILE;
+    size_t bytes = MN_TAPE_HEADER;
+    if (m->d.kind == 2) {
+        bytes += mn_align((size_t)cap * sizeof(int));
+        if (m->d.boundary_margin > 1.0f) bytes += mn_align((size_t)cap * sizeof(float));
+    }
+    bytes += mn_align((size_t)n_tiles * mn_train_tc_x_tile_bytes(m));
+    bytes += mn_align((size_t)n_tiles * mn_train_tc_act_tile_bytes(m));
+    bytes += mn_align((size_t)n_tiles * 5 * MN_TILE * sizeof(float));
+    return bytes;
+}
+
+int mn_model_train_tc_supported(const mn_model* m) { return (m && m->train_tc_ok) ? 1 : 0; }
+
+size_t mn_model_tape_bytes_tc(const mn_model* m, int64_t B) { return m ? tape_bytes_tc(m, B) : 0; }
+
+int mn_model_forward_train_tc(mn_ctx* ctx, mn_model* m, const mn_rows* rows, int64_t B, int use_coarse,
+                              const float* sigma_noise_d, float* out_d, void* tape_d, size_t tape_bytes, void* workspace_d,
+                              size_t workspace_bytes, void* stream) {
+    if (!tape_d) return mn_fail(ctx, MN_ERR_INVALID, "mn_model_forward_train_tc: tape is NULL");
+    if (!m || !m->train_tc_ok)
+        return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core training covers layer_dim 256 with a direction / appearance head, rgb_dim 3, "
+                                                "no affine appearance; use the fp32 training entry points for this model");
+    return model_forward_impl(ctx, m, rows, B, use_coarse, 0, sigma_noise_d, MN_PREC_FP32, out_d, workspace_d, workspace_bytes, tape_d,
+                              tape_bytes, stream, 1);
+}
+
+size_t mn_model_backward_workspace_bytes_tc(const mn_model* m, int64_t B) {
+    if (!m) return 0;
+    return 256 + mn_train_tc_backward_workspace(m, slot_capacity(m, B) / MN_TILE);
+}
+
+int mn_model_backward_tc(mn_ctx* ctx, mn_model* m, int64_t B, int use_coarse, const float* grad_out_d, const void* tape_d,
+                         size_t tape_bytes, float* param_grads_d, void* workspace_d, size_t workspace_bytes, void* stream) {
+    if (!ctx || !m || B < 0 || !grad_out_d || !tape_d || !param_grads_d) return MN_ERR_INVALID;
+    if (B == 0) return MN_OK;
+    if (!m->train_tc_ok) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "mn_model_backward_tc: unsupported network shape");
+    const mn_model_desc& d = m->d;
+    if (tape_bytes < tape_bytes_tc(m, B)) return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_model_backward_tc: tape too small");
+    const int64_t cap = slot_capacity(m, B);
+    const int64_t n_tiles = cap / MN_TILE;
+    const char* tp = (const char*)tape_d;
+    auto tcarve = [&](size_t n) { const char* p = tp; tp += mn_align(n); return p; };
+    const int* counters = (const int*)tcarve(MN_TAPE_HEADER);
+    BwdArgs a{};
+    a.nd = m->nd;
+    a.lay = m->lay;
+    a.blay = m->blay;
+    a.packed = m->packed;
+    a.packed_bwd = m->packed_bwd;
+    a.n_sub = d.n_sub;
+    a.B = B;
+    a.grad_out = grad_out_d;
+    a.grad_rows = B;
+    a.out_cols = m->nd.rgb_dim + 1;
+    a.gw = param_grads_d;
+    if (d.kind == 2) {
+        a.slot_row = (const int*)tcarve((size_t)cap * sizeof(int));
+        if (d.boundary_margin > 1.0f) a.slot_w = (const float*)tcarve((size_t)cap * sizeof(float));
+        a.counters = counters;
+        a.B = cap;
+    } else {
+        a.fixed_sub = (d.kind == 1) ? (use_coarse ? 0 : 1) : 0;
+    }
+    TrainTcTape T;
+    T.xreg = (unsigned char*)tcarve((size_t)n_tiles * mn_train_tc_x_tile_bytes(m));
+    T.act = (unsigned char*)tcarve((size_t)n_tiles * mn_train_tc_act_tile_bytes(m));
+    T.f32 = (float*)tcarve((size_t)n_tiles * 5 * MN_TILE * sizeof(float));
+    return mn_train_tc_backward(ctx, m, a, n_tiles, T, workspace_d, workspace_bytes, (cudaStream_t)stream);
 }
 
 int mn_model_last_stats(mn_ctx* ctx, mn_model* m, int64_t* slots, int64_t* tiles, void* stream) {

@@ -61,7 +61,11 @@ constexpr int kWarpMma = 17;
 constexpr int kPPThreads = kThreads;
 
 enum { SRC_H = 0, SRC_XPE = 1, SRC_XAUX = 2 };
-enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_RGB = 3 };
+enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_RGB = 3,
+       // data-gradient chain (training, mn_train_tc.cuh): plain copy, ReLU mask from the activation tape, mask + sigma-head term
+       EPI_D_LINEAR = 4, EPI_D_MASK = 5, EPI_D_MASK_SIGMA = 6 };
+// kernel modes of tc_mlp_pp_kernel
+enum { PP_INFER = 0, PP_TRAIN_FWD = 1, PP_DGRAD = 2 };
 
 struct TcGemm {
     int n;           // MMA N
@@ -84,6 +88,7 @@ struct TcPlan {
     int x_tile_bytes;      // bytes of one feature tile image (one plane)
     int L;
     int bstride;           // floats reserved per GEMM bias in the fp32 block (256; 512 for the 512-wide network)
+    int f32_off;           // byte offset of the fp32 block inside one sub-module's pack (after the hi and lo planes)
 };
 
 int pad16(int x) { return (x + 15) / 16 * 16; }
@@ -127,6 +132,7 @@ bool build_plan(const NetDims& nd, TcPlan* p) {
     P.plane_bytes = woff;
     P.sigma_w_off = ng * P.bstride;
     P.f32_floats = ng * P.bstride + nd.L + 4;
+    P.f32_off = woff * 2;
     P.x_tile_bytes = (P.kpe + P.kaux) * kTileM * 2;
     return true;
 }
@@ -237,7 +243,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // two 16-byte stores into the next layer's A operand.  Returns the partial sigma dot product if kSigma.
 template <bool kSplit, bool kRelu, bool kSigma>
 __device__ __forceinline__ float epi_piece16(uint32_t taddr, const float* __restrict__ bias16, const float* __restrict__ sw16,
-                                             unsigned char* dst, size_t lo_off, bool store) {
+                                             unsigned char* dst, size_t lo_off, bool store, unsigned char* gdst = nullptr) {
     uint32_t v[16];
     tmem_ld16(taddr, v);
     const float4* b4 = reinterpret_cast<const float4*>(bias16);
@@ -276,6 +282,10 @@ __device__ __forceinline__ float epi_piece16(uint32_t taddr, const float* __rest
         }
         *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(dst + kTileM * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        if (gdst) {     // training forward: the same two 16-byte pieces go to the activation tape (same image layout)
+            *reinterpret_cast<uint4*>(gdst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(gdst + kTileM * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        }
         if (kSplit) {
             uint32_t lo[8];
 #pragma unroll
@@ -294,7 +304,7 @@ __device__ __forceinline__ float epi_piece16(uint32_t taddr, const float* __rest
 // transform (3x4 matrix = affine(embedding_a[idx]), nerf.py:156-158), sigmoid when rgb_dim == 3, blend weight.
 // v = the row's raw fp32 accumulators of the rgb GEMM.
 __device__ __forceinline__ void tc_emit_rgb(const MlpArgs& m, int sub, int64_t row, int64_t slot, const uint32_t* v,
-                                            const float* bias, float sigma) {
+                                            const float* bias, float sigma, float* tape_rgb = nullptr) {
     const NetDims& nd = m.nd;
     const int64_t o = (m.scatter ? row : slot) * m.out_cols;
     const float w = m.slot_w ? m.slot_w[slot] : 1.0f;
@@ -324,6 +334,7 @@ __device__ __forceinline__ void tc_emit_rgb(const MlpArgs& m, int sub, int64_t r
             if (c < nd.rgb_dim) {
                 float x = __uint_as_float(v[c]) + bias[c];
                 if (nd.rgb_dim == 3) x = mn_sigmoid(x);
+                if (tape_rgb && c < 3) tape_rgb[c * kTileM] = x;      // training forward: colour before the blend weight
                 m.out[o + c] = m.slot_w ? x * w : x;
             }
         }
@@ -677,6 +688,17 @@ struct TcArgs {
     int split;                    // 1: three MMA passes (hi*hi + hi*lo + lo*hi)
     int desc_swap;                // debug: 1 = record the in-kernel timeline (MN_TC_TRACE)
     int64_t n_tiles_cap;
+    // ---- training (tc_f16 training path, mn_train_tc.cuh).  Tapes hold, per 128-slot tile, fp16 tile images in the layout of
+    // the activation buffer ([cols/8][128][8]): activations H_0 .. H_{layers-1}, F (xyz_encoding_final), G (dir_a_encoding).
+    unsigned char* tape_act;      // PP_TRAIN_FWD: written;  PP_DGRAD: read (ReLU masks)
+    float* tape_f32;              // per tile [4][128]: sigma pre-activation, rgb (3)     (written / read)
+    unsigned char* tape_dz;       // PP_DGRAD: gradient images dZ_0 .. dZ_{layers-1}, dZ_final, dZ_dira (same layout, scaled fp16)
+    float* tape_gf32;             // PP_DGRAD: per tile [4][128]: d sigma pre-activation, d rgb pre-activation (3), UNscaled fp32
+    const float* grad_out;        // PP_DGRAD: [rows][rgb_dim + 1] upstream gradient
+    float* emb_sum;               // PP_DGRAD: [n_sub][app_count][L/2] per-image sums of dZ_dira rows (appearance-embedding gradient)
+    const float* scale;           // PP_DGRAD: device scalar S (power of two): gradient images hold S * dZ
+    int64_t act_tile_bytes;       // bytes of one tile's record in tape_act / tape_dz
+    int layers;
 };
 
 struct SmemLayout {
@@ -1012,6 +1034,7 @@ __host__ __device__ inline int pp_prog_entries(const TcPlan& p, int n_gemm) {
 }
 
 // Ping-pong kernel (see the header of this section).  Warps 0..15 epilogue, 16 TMA producer, 17 MMA issuer.
+template <int kMode>
 __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
@@ -1120,7 +1143,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
                     // the bias / sigma block is re-staged only when the sub-module changes (a handful of times per launch):
                     // the weight stream of consecutive pairs is not interrupted by waiting for the epilogue
                     if (last_sub >= 0) { mbar_wait(&f32_empty[0], fph_e); fph_e ^= 1; }
-                    const unsigned char* fsrc = wsub + (size_t)P.plane_bytes * 2;
+                    const unsigned char* fsrc = wsub + (size_t)P.f32_off;
                     mbar_expect_tx(&f32_full[0], f32_bytes);
                     bulk_g2s(reinterpret_cast<unsigned char*>(F32), fsrc, f32_bytes, &f32_full[0]);
                     last_sub = sub0;
@@ -1150,7 +1173,8 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
         // =========================== MMA issuer (whole warp, one elected lane issues): table-driven (PROG) ===========================
         uint32_t stage = 0, phase = 0, eph0 = 0, eph1 = 0;
         uint32_t ahead = 0;              // the look-ahead probe of the CURRENT stage's full barrier already succeeded
-        bool started0 = false, started1 = false;
+        // data-gradient mode: the first GEMM of every pair waits for the head stage the epilogue warps run first
+        bool started0 = kMode == PP_DGRAD, started1 = kMode == PP_DGRAD;
         const uint32_t h_base = smem_u32(Hs), ring_base = smem_u32(ring);
         const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
         const uint32_t acc_full_a = smem_u32(acc_full), epi_done_a = smem_u32(epi_done);
@@ -1240,6 +1264,87 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
                 slot_[sl] = (t0 + sl) * kTileM + r;
                 if (slot_[sl] < n_slots) row_[sl] = A.m.slot_row ? (int64_t)A.m.slot_row[slot_[sl]] : slot_[sl];
             }
+            float dsig_[2] = {0.0f, 0.0f};       // PP_DGRAD: S * d(sigma pre-activation) of this thread's row, per tile slot
+            if (kMode == PP_DGRAD) {
+                // ---- head stage of the data-gradient chain (nerf.py:132-160 backwards): upstream gradient x blend weight ->
+                // sigmoid' / softplus' -> rgb Linear transposed (3 -> L/2, CUDA cores) -> ReLU mask of dir_a_encoding -> dZ_dira
+                // as the first A operand (columns 0 .. L/2-1 of the activation buffer) and on the gradient tape; per-image sums
+                // of its rows for the appearance-embedding gradient; head pre-activation gradients in fp32 for their own Linears.
+                const float S = *A.scale;
+                const int sub0 = last_sub;
+                const float* Wr = F32 + L;                                  // [3][L/2] rgb weights (fp32 block of the data-gradient plan)
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (sl == 1 && !valid1) continue;
+                    const int64_t tile = t0 + sl;
+                    const int64_t row = row_[sl];
+                    const float* tf = A.tape_f32 + (size_t)tile * 5 * kTileM + r;
+                    float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
+                    if (row >= 0) {
+                        const float4 g = *reinterpret_cast<const float4*>(A.grad_out + row * 4);
+                        const float w = A.m.slot_w ? A.m.slot_w[slot_[sl]] : 1.0f;
+                        g0 = g.x * w; g1 = g.y * w; g2 = g.z * w; g3 = g.w * w;
+                    }
+                    const float c0v = tf[1 * kTileM], c1v = tf[2 * kTileM], c2v = tf[3 * kTileM], pre = tf[0];
+                    const float d0 = (g0 * (1.0f - c0v)) * c0v, d1 = (g1 * (1.0f - c1v)) * c1v, d2 = (g2 * (1.0f - c2v)) * c2v;
+                    float dsp;
+                    if (A.m.nd.softplus) { const float y = pre - 1.0f; dsp = y > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-y)); }
+                    else dsp = pre > 0.0f ? 1.0f : 0.0f;
+                    const float ds = g3 * dsp;
+                    dsig_[sl] = ds * S;
+                    if (part == 0) {
+                        float* tg = A.tape_gf32 + (size_t)tile * 4 * kTileM + r;
+                        tg[0] = ds; tg[1 * kTileM] = d0; tg[2 * kTileM] = d1; tg[3 * kTileM] = d2;
+                    }
+                    const int id = (int)tf[4 * kTileM];
+                    const unsigned char* gimg = A.tape_act + (size_t)tile * A.act_tile_bytes + (size_t)(A.layers + 1) * L * kTileM * 2;
+                    unsigned char* dimg = A.tape_dz + (size_t)tile * A.act_tile_bytes + (size_t)(A.layers + 1) * L * kTileM * 2;
+                    unsigned char* Hsl = Hs + (size_t)sl * h_bytes;
+                    const int half = L / 2, per = half / 4;                 // columns of dZ_dira handled by this thread (32 for L = 256)
+                    for (int kk = 0; kk < per; kk += 8) {
+                        const int k0 = part * per + kk;
+                        const uint4 gm = *reinterpret_cast<const uint4*>(gimg + (size_t)(k0 >> 3) * (kTileM * 16) + (size_t)r * 16);
+                        const __half2* gh = reinterpret_cast<const __half2*>(&gm);
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int k = k0 + e;
+                            float acc = Wr[k] * d0;
+                            acc = fmaf(Wr[half + k], d1, acc);
+                            acc = fmaf(Wr[2 * half + k], d2, acc);
+                            const float gv = (e & 1) ? __high2float(gh[e >> 1]) : __low2float(gh[e >> 1]);
+                            v[e] = gv > 0.0f ? acc : 0.0f;
+                        }
+                        // appearance-embedding gradient, step 1: per-image sums of dZ_dira rows (fp32, unscaled); the lanes of a warp
+                        // are consecutive slots, i.e. mostly samples of one ray = one image id
+                        if (A.emb_sum) {
+                            unsigned todo = __ballot_sync(0xffffffffu, row >= 0);
+                            while (todo) {
+                                const int leader = __ffs(todo) - 1;
+                                const int cur = __shfl_sync(0xffffffffu, id, leader);
+                                const bool mine = row >= 0 && id == cur;
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    float t = mine ? v[e] : 0.0f;
+#pragma unroll
+                                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                                    if (lane == leader) atomicAdd(A.emb_sum + ((size_t)sub0 * A.m.nd.app_count + cur) * half + k0 + e, t);
+                                }
+                                todo &= ~__ballot_sync(0xffffffffu, mine);
+                            }
+                        }
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) pk[e] = pack_h2(v[2 * e] * S, v[2 * e + 1] * S);
+                        const uint4 outv = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(Hsl + (size_t)(k0 >> 3) * (kTileM * 16) + (size_t)r * 16) = outv;
+                        *reinterpret_cast<uint4*>(dimg + (size_t)(k0 >> 3) * (kTileM * 16) + (size_t)r * 16) = outv;
+                    }
+                    fence_proxy_async();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&epi_done[sl]);
+                }
+            }
             for (int gi = 0; gi < n_gemm; ++gi) {
                 const TcGemm& g = P.g[gi];
 #pragma unroll
@@ -1252,30 +1357,94 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
                     const uint32_t t_acc = t_lane + (uint32_t)sl * 256u;
                     const float* bias = F32 + g.bias_off;
                     const int64_t row = row_[sl], slot = slot_[sl];
+                    unsigned char* Hsl = Hs + (size_t)sl * h_bytes;
+                    if (kMode == PP_DGRAD) {
+                        // dH = accumulator (scaled by S) [+ S dsigma x w_sigma] -> ReLU mask from the activation tape -> fp16 ->
+                        // next A operand + gradient tape.  g.bias_off holds the image index (the mask image and the target image
+                        // coincide: dZ_l = dH_l where H_l > 0).
+                        const int img = g.bias_off;
+                        const size_t ioff = (size_t)(t0 + sl) * A.act_tile_bytes + (size_t)img * L * kTileM * 2;
+                        const unsigned char* mimg = A.tape_act + ioff;
+                        unsigned char* dimg = A.tape_dz + ioff;
+                        const float dss = dsig_[sl];
+                        const int nslab = (g.n + 63) >> 6;
+                        for (int j = 0; j < nslab; ++j) {
+                            const int c0 = 64 * j + 16 * part;
+                            if (c0 >= g.n) continue;
+                            uint32_t v[16];
+                            tmem_ld16(t_acc + (uint32_t)c0, v);
+                            const size_t po = (size_t)(c0 >> 3) * (kTileM * 16) + (size_t)r * 16;
+                            uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+                            if (g.epi != EPI_D_LINEAR) {
+                                m0 = *reinterpret_cast<const uint4*>(mimg + po);
+                                m1 = *reinterpret_cast<const uint4*>(mimg + po + kTileM * 16);
+                            }
+                            tmem_ld_wait();
+                            float f[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                            if (g.epi == EPI_D_MASK_SIGMA) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) f[i] = fmaf(dss, F32[c0 + i], f[i]);      // F32[0..L) = sigma weights
+                            }
+                            if (g.epi != EPI_D_LINEAR) {
+                                const __half2* h0 = reinterpret_cast<const __half2*>(&m0);
+                                const __half2* h1 = reinterpret_cast<const __half2*>(&m1);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float hv = (i & 1) ? __high2float(h0[i >> 1]) : __low2float(h0[i >> 1]);
+                                    const float hw = (i & 1) ? __high2float(h1[i >> 1]) : __low2float(h1[i >> 1]);
+                                    if (!(hv > 0.0f)) f[i] = 0.0f;
+                                    if (!(hw > 0.0f)) f[8 + i] = 0.0f;
+                                }
+                            }
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) pk[e] = pack_h2(f[2 * e], f[2 * e + 1]);
+                            const uint4 o0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), o1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            *reinterpret_cast<uint4*>(Hsl + po) = o0;
+                            *reinterpret_cast<uint4*>(Hsl + po + kTileM * 16) = o1;
+                            *reinterpret_cast<uint4*>(dimg + po) = o0;
+                            *reinterpret_cast<uint4*>(dimg + po + kTileM * 16) = o1;
+                        }
+                        fence_proxy_async();
+                        tc_fence_before();
+                        __syncwarp();
+                        // the last GEMM's epilogue is followed by this slot's next head stage (same warps): nobody waits for it
+                        if (lane == 0 && gi + 1 < n_gemm) mbar_arrive(&epi_done[sl]);
+                        continue;
+                    }
+                    // training forward: tape image of this GEMM's output (trunk layer gi; then F, then G)
+                    unsigned char* timg = nullptr;
+                    if (kMode == PP_TRAIN_FWD && g.epi != EPI_RGB)
+                        timg = A.tape_act + (size_t)(t0 + sl) * A.act_tile_bytes + (size_t)gi * L * kTileM * 2;
                     if (g.epi == EPI_RGB) {
                         if (part == 0) {
                             uint32_t v[32];
                             tmem_ld32(t_acc, v);
                             tmem_ld_wait();
-                            if (row >= 0) tc_emit_rgb(A.m, A.m.nd.affine ? sub_of(t0 + sl) : 0, row, slot, v, RGBB, sigma_[sl]);
+                            float* tr = kMode == PP_TRAIN_FWD ? A.tape_f32 + (size_t)(t0 + sl) * 5 * kTileM + kTileM + r : nullptr;
+                            if (row >= 0) tc_emit_rgb(A.m, A.m.nd.affine ? sub_of(t0 + sl) : 0, row, slot, v, RGBB, sigma_[sl], tr);
+                            else if (tr) { tr[0] = 0.5f; tr[kTileM] = 0.5f; tr[2 * kTileM] = 0.5f; }
                         }
                     } else {
                         const bool want_sigma = g.epi == EPI_RELU_SIGMA;
                         const bool publish = !(want_sigma && A.m.sigma_only);
                         const float* sw = SW;
-                        unsigned char* Hsl = Hs + (size_t)sl * h_bytes;
                         float sacc = 0.0f;
                         const int nslab = (g.n + 63) >> 6;
                         for (int j = 0; j < nslab; ++j) {
                             const int c0 = 64 * j + 16 * part;
                             if (c0 < g.n) {
-                                unsigned char* dst = Hsl + (size_t)(c0 >> 3) * (kTileM * 16) + (size_t)r * 16;
+                                const size_t po = (size_t)(c0 >> 3) * (kTileM * 16) + (size_t)r * 16;
+                                unsigned char* dst = Hsl + po;
+                                unsigned char* gd = timg ? timg + po : nullptr;
                                 if (g.epi == EPI_RELU)
-                                    epi_piece16<false, true, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
+                                    epi_piece16<false, true, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true, gd);
                                 else if (g.epi == EPI_LINEAR)
-                                    epi_piece16<false, false, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true);
+                                    epi_piece16<false, false, false>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, true, gd);
                                 else
-                                    sacc += epi_piece16<false, true, true>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, publish);
+                                    sacc += epi_piece16<false, true, true>(t_acc + (uint32_t)c0, bias + c0, sw + c0, dst, 0, publish, gd);
                             }
                         }
                         if (publish) fence_proxy_async();
@@ -1287,6 +1456,11 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
                                 if (A.m.sigma_noise && row >= 0) s = s + A.m.sigma_noise[row];
                                 const float sg = A.m.nd.softplus ? mn_softplus_shifted(s) : fmaxf(s, 0.0f);
                                 sigma_[sl] = sg;
+                                if (kMode == PP_TRAIN_FWD) {
+                                    float* tf = A.tape_f32 + (size_t)(t0 + sl) * 5 * kTileM + r;
+                                    tf[0] = s;                                                  // pre-activation (with the density noise)
+                                    tf[4 * kTileM] = (row >= 0 && A.m.nd.app > 0) ? A.m.src.index(row) : 0.0f;   // image id of the row
+                                }
                                 if (A.m.sigma_only && row >= 0) {
                                     const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
                                     A.m.out[o] = A.m.slot_w ? sg * A.m.slot_w[slot] : sg;
@@ -1312,6 +1486,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
 }
 
 #include "mn_mlp_wide.cuh"
+#include "mn_train_tc.cuh"
 
 }  // namespace
 
@@ -1379,6 +1554,36 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
     tc_pack_f32_kernel<<<1, 32, 0, st>>>(Pk + m->lay.sigma_b, 1, f32 + P.sigma_w_off + nd.L, 4);
     MN_LAUNCH_CHECK(ctx);
     m->tc_ready = 1;
+
+    // ---- data-gradient images of the tensor-core training path (transposed weights, single fp16 plane + fp32 block)
+    TcPlan D;
+    m->train_tc_ok = 0;
+    if (!wide && build_dgrad_plan(nd, &D)) {
+        if (!m->tc_dgrad) {
+            MN_CUDA(ctx, cudaMalloc(&m->tc_dgrad, (size_t)D.sub_bytes * m->d.n_sub));
+            MN_CUDA(ctx, cudaMemsetAsync(m->tc_dgrad, 0, (size_t)D.sub_bytes * m->d.n_sub, st));
+            m->tc_dgrad_sub_bytes = (size_t)D.sub_bytes;
+        }
+        unsigned char* db = (unsigned char*)m->tc_dgrad + (size_t)sub * D.sub_bytes;
+        const float* Q = m->packed_bwd + (size_t)sub * m->blay.total;
+        auto packd = [&](const TcGemm& g, const float* wd, int ld) -> int {
+            const int64_t n = (int64_t)g.n * g.k[0];
+            tc_pack_dgrad_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wd, ld, g.n, g.k[0], reinterpret_cast<__half*>(db + g.w_off));
+            MN_LAUNCH_CHECK(ctx);
+            return MN_OK;
+        };
+        int di = 0;
+        if ((rc = packd(D.g[di++], Q + m->blay.dira_f, nd.L))) return rc;         // [L/2][L]
+        if ((rc = packd(D.g[di++], Q + m->blay.final_w, nd.L))) return rc;        // [L][L]
+        for (int l = nd.layers - 1; l >= 1; --l)
+            if ((rc = packd(D.g[di++], Q + m->blay.w[l], nd.L))) return rc;       // [L][L]: hidden-part columns of layer l
+        float* df32 = reinterpret_cast<float*>(db + D.f32_off);
+        tc_pack_f32_kernel<<<(unsigned)mn_cdiv(nd.L, 256), 256, 0, st>>>(Pk + m->lay.sigma_w, nd.L, df32, nd.L);
+        MN_LAUNCH_CHECK(ctx);
+        tc_pack_rgbw_kernel<<<(unsigned)mn_cdiv(3 * (nd.L / 2), 256), 256, 0, st>>>(Pk + m->lay.rgb_w, nd.L / 2, 3, df32 + nd.L);
+        MN_LAUNCH_CHECK(ctx);
+        m->train_tc_ok = 1;
+    }
     return MN_OK;
 }
 
@@ -1486,9 +1691,9 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     } else {
         if (run_pp) {
             const unsigned grid_pp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
-            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<PP_INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
             mn_prof_begin(ctx, st);
-            tc_mlp_pp_kernel<<<grid_pp, kPPThreads, PL.total, st>>>(A);
+            tc_mlp_pp_kernel<PP_INFER><<<grid_pp, kPPThreads, PL.total, st>>>(A);
         } else {
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
             mn_prof_begin(ctx, st);
@@ -1497,6 +1702,200 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     }
     mn_prof_end(ctx, st);
     MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}
+
+// =================================================================================================
+// tensor-core training path: host side (kernels in mn_train_tc.cuh)
+// =================================================================================================
+size_t mn_train_tc_x_tile_bytes(const mn_model* m) {
+    TcPlan P;
+    return build_plan(m->nd, &P) ? (size_t)P.x_tile_bytes : 0;
+}
+size_t mn_train_tc_act_tile_bytes(const mn_model* m) {
+    const NetDims& nd = m->nd;
+    return (size_t)(nd.layers + 1) * nd.L * kTileM * 2 + (size_t)(nd.L / 2) * kTileM * 2;
+}
+
+// recording forward: encoder tiles and every layer's activations land in the caller's tape
+int mn_mlp_tc_launch_train(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles128, const TrainTcTape& tape, cudaStream_t st) {
+    TcArgs A{};
+    if (!m->train_tc_ok || !build_plan(a.nd, &A.plan) || !m->tc_ready)
+        return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core training covers layer_dim 256 with a direction / appearance head and rgb_dim 3; use train precision 'fp32'");
+    if (n_tiles128 <= 0) return MN_OK;
+    TcPlan& P = A.plan;
+    P.sub_bytes = (int)m->tc_sub_bytes;
+    A.m = a;
+    A.wpack = (const unsigned char*)m->tc_packed;
+    A.ximg = reinterpret_cast<const __half*>(tape.xreg);
+    A.x_plane_halves = 0;
+    A.n_tiles_cap = n_tiles128;
+    A.tape_act = tape.act;
+    A.tape_f32 = tape.f32;
+    A.act_tile_bytes = (int64_t)mn_train_tc_act_tile_bytes(m);
+    A.layers = a.nd.layers;
+    const size_t enc_sm = (size_t)P.x_tile_bytes;
+    MN_CUDA(ctx, cudaFuncSetAttribute(tc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_sm));
+    const NetDims& ndE = a.nd;
+    const bool fast_shape = ndE.xyz_dim == 3 && ndE.nf_xyz == 12 && ndE.nf_dir == 4 && ndE.app == 48 && ndE.app_in_dira && (m->lay.emb % 4) == 0;
+    __half* ximg = reinterpret_cast<__half*>(tape.xreg);
+    if (fast_shape) tc_encode_fast_kernel<3, 12, 4, 48><<<(unsigned)n_tiles128, kTileM, 0, st>>>(a, ximg);
+    else tc_encode_kernel<<<(unsigned)n_tiles128, kTileM, enc_sm, st>>>(a, P.kpe, P.kaux, 0, ximg, 0);
+    MN_LAUNCH_CHECK(ctx);
+    const PPLayout PL = pp_layout(P);
+    if (PL.total > kSmemMax || PL.stages < 3 || pp_prog_entries(P, P.n_gemm) + 2 > kPPMaxProg)
+        return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core training forward: shared-memory budget exceeded");
+    const unsigned grid = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
+    MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<PP_TRAIN_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
+    mn_prof_begin(ctx, st);
+    tc_mlp_pp_kernel<PP_TRAIN_FWD><<<grid, kPPThreads, PL.total, st>>>(A);
+    mn_prof_end(ctx, st);
+    MN_LAUNCH_CHECK(ctx);
+    return MN_OK;
+}
+
+// backward workspace: [gradient records][head gradients fp32 [n_tiles][4][128]][embedding sums][scale]
+static size_t train_tc_emb_floats(const mn_model* m) {
+    return m->nd.app_in_dira ? (size_t)m->d.n_sub * m->nd.app_count * (m->nd.L / 2) : 0;
+}
+size_t mn_train_tc_backward_workspace(const mn_model* m, int64_t n_tiles128) {
+    return mn_align((size_t)n_tiles128 * mn_train_tc_act_tile_bytes(m)) + mn_align((size_t)n_tiles128 * 4 * kTileM * sizeof(float)) +
+           mn_align(train_tc_emb_floats(m) * sizeof(float) + 256) + 1024;
+}
+
+int mn_train_tc_backward(mn_ctx* ctx, mn_model* m, const BwdArgs& a, int64_t n_tiles128, const TrainTcTape& tape, void* ws, size_t ws_bytes,
+                         cudaStream_t st) {
+    TcArgs A{};
+    const NetDims& nd = a.nd;
+    if (!m->train_tc_ok || !build_dgrad_plan(nd, &A.plan)) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core backward: unsupported network shape");
+    if (n_tiles128 <= 0) return MN_OK;
+    if (!ws || ws_bytes < mn_train_tc_backward_workspace(m, n_tiles128)) return mn_fail(ctx, MN_ERR_WORKSPACE, "mn_train_tc_backward: workspace too small");
+    const size_t act_tile = mn_train_tc_act_tile_bytes(m);
+    char* wp = (char*)(((uintptr_t)ws + 255) / 256 * 256);
+    unsigned char* dz = (unsigned char*)wp;               wp += mn_align((size_t)n_tiles128 * act_tile);
+    float* gf32 = (float*)wp;                             wp += mn_align((size_t)n_tiles128 * 4 * kTileM * sizeof(float));
+    float* emb_sum = (float*)wp;                          wp += mn_align(train_tc_emb_floats(m) * sizeof(float) + 256) - 256;
+    float* scale = (float*)wp;
+    if (train_tc_emb_floats(m)) MN_CUDA(ctx, cudaMemsetAsync(emb_sum, 0, train_tc_emb_floats(m) * sizeof(float), st));
+
+    mn_prof_begin(ctx, st);   // bench.py --mode train: the whole backward of the MLP stage timed as one span
+    // ---- gradient scale (power of two) from the upstream gradient
+    tc_grad_scale_kernel<<<1, 1024, 0, st>>>(a.grad_out, a.grad_rows * a.out_cols, scale);
+    MN_LAUNCH_CHECK(ctx);
+
+    // ---- data gradients
+    TcPlan& D = A.plan;
+    A.m = MlpArgs{};
+    A.m.nd = nd;
+    A.m.slot_row = a.slot_row;
+    A.m.slot_w = a.slot_w;
+    A.m.counters = a.counters;
+    A.m.n_sub = a.n_sub;
+    A.m.fixed_sub = a.fixed_sub;
+    A.m.B = a.B;
+    A.m.out_cols = a.out_cols;
+    A.wpack = (const unsigned char*)m->tc_dgrad;
+    A.n_tiles_cap = n_tiles128;
+    A.tape_act = tape.act;
+    A.tape_f32 = tape.f32;
+    A.tape_dz = dz;
+    A.tape_gf32 = gf32;
+    A.grad_out = a.grad_out;
+    A.emb_sum = nd.app_in_dira ? emb_sum : nullptr;
+    A.scale = scale;
+    A.act_tile_bytes = (int64_t)act_tile;
+    A.layers = nd.layers;
+    const PPLayout PL = pp_layout(D);
+    if (PL.total > kSmemMax || PL.stages < 3 || pp_prog_entries(D, D.n_gemm) + 2 > kPPMaxProg)
+        return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core backward: shared-memory budget exceeded");
+    const unsigned grid = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
+    MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<PP_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
+    tc_mlp_pp_kernel<PP_DGRAD><<<grid, kPPThreads, PL.total, st>>>(A);
+    MN_LAUNCH_CHECK(ctx);
+
+    // ---- weight gradients: one item per (Linear input segment, 128-channel output half)
+    WgArgs W{};
+    const int L = nd.L;
+    const int img_bytes = L * kTileM * 2;
+    TcPlan F;
+    build_plan(nd, &F);
+    int ni = 0;
+    auto item = [&](int dz_img, int half, int x_region, int x_off, int n, int n_real, int w_off, int k_in, int in0, int b_off) {
+        WgItem& it = W.item[ni++];
+        it.dz_off = dz_img * img_bytes + half * 16 * (kTileM * 16);
+        it.x_region = x_region;
+        it.x_off = x_off;
+        it.n = n;
+        it.n_real = n_real;
+        it.w_off = w_off + half * 128 * k_in + in0;
+        it.k_in = k_in;
+        it.b_off = b_off >= 0 ? b_off + half * 128 : -1;
+    };
+    for (int i = 0; i < nd.layers; ++i) {
+        const bool skip = i > 0 && ((nd.skip_mask >> i) & 1);
+        const int k_in = a.lay.kin[i];
+        for (int h = 0; h < L / 128; ++h) {
+            if (i == 0) item(i, h, 1, 0, F.kpe, nd.in_xyz, a.lay.w[i], k_in, 0, a.lay.b[i]);
+            else if (skip) {
+                item(i, h, 1, 0, F.kpe, nd.in_xyz, a.lay.w[i], k_in, 0, a.lay.b[i]);                       // cat[PE, h]: PE columns first
+                item(i, h, 0, (i - 1) * img_bytes, L, L, a.lay.w[i], k_in, nd.in_xyz, -1);
+            } else item(i, h, 0, (i - 1) * img_bytes, L, L, a.lay.w[i], k_in, 0, a.lay.b[i]);
+        }
+    }
+    for (int h = 0; h < L / 128; ++h) item(nd.layers, h, 0, (nd.layers - 1) * img_bytes, L, L, a.lay.final_w, L, 0, a.lay.final_b);
+    // dir_a_encoding: L/2 = 128 output channels (one half); input = cat[final (L), dir PE + embedding (aux)]
+    item(nd.layers + 1, 0, 0, nd.layers * img_bytes, L, L, a.lay.dira_w, L + nd.aux, 0, a.lay.dira_b);
+    item(nd.layers + 1, 0, 1, (F.kpe / 8) * (kTileM * 16), F.kaux, nd.aux, a.lay.dira_w, L + nd.aux, L, -1);
+    if (ni > kWgMaxItems) return mn_fail(ctx, MN_ERR_UNSUPPORTED, "tensor-core backward: too many weight-gradient items");
+    W.n_items = ni;
+    W.act = tape.act;
+    W.dz = dz;
+    W.xreg = tape.xreg;
+    W.act_tile_bytes = (int64_t)act_tile;
+    W.x_tile_bytes = (int64_t)F.x_tile_bytes;
+    // tiles the forward pass really wrote: all bucketed tiles when routed, ceil(rows / 128) otherwise
+    const int64_t tiles_used = a.counters ? n_tiles128 : mn_cdiv(a.B, (int64_t)kTileM);
+    W.counters = a.counters;
+    W.n_tiles = tiles_used;
+    W.fixed_sub = a.fixed_sub;
+    W.gw = a.gw;
+    W.sub_stride = a.lay.total;
+    W.scale = scale;
+    // chunks: enough CTAs to fill the machine about three times over (each streams its tiles once; results are fp32 atomics)
+    const int n_sub = a.counters ? a.n_sub : 1;
+    int64_t chunks = mn_cdiv((int64_t)ctx->sm_count * 3, (int64_t)ni * n_sub);
+    if (chunks < 1) chunks = 1;
+    int64_t chunk_tiles = mn_cdiv(mn_cdiv(tiles_used, n_sub), chunks);
+    if (chunk_tiles < 8) chunk_tiles = 8;
+    W.chunk_tiles = (int)chunk_tiles;
+    const unsigned gx = (unsigned)mn_cdiv(tiles_used, chunk_tiles);
+    const int wg_smem = 2 * kWgStageBytes + 6144 + 256;
+    MN_CUDA(ctx, cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem));
+    tc_wgrad_kernel<<<dim3(gx, (unsigned)ni, (unsigned)n_sub), kWgThreads, wg_smem, st>>>(W);
+    MN_LAUNCH_CHECK(ctx);
+
+    // ---- sigma / rgb heads and the appearance embedding
+    HeadsArgs H{};
+    H.act = tape.act;
+    H.gf32 = gf32;
+    H.act_tile_bytes = (int64_t)act_tile;
+    H.L = L;
+    H.layers = nd.layers;
+    H.counters = a.counters;
+    H.n_tiles = tiles_used;
+    H.fixed_sub = a.fixed_sub;
+    H.chunk_tiles = 16;
+    H.gw = a.gw;
+    H.sub_stride = a.lay.total;
+    H.sigma_w = a.lay.sigma_w; H.sigma_b = a.lay.sigma_b; H.rgb_w = a.lay.rgb_w; H.rgb_b = a.lay.rgb_b;
+    tc_heads_wgrad_kernel<<<dim3((unsigned)mn_cdiv(tiles_used, 16), (unsigned)n_sub), 256, 0, st>>>(H);
+    MN_LAUNCH_CHECK(ctx);
+    if (nd.app_in_dira) {
+        tc_emb_grad_kernel<<<dim3((unsigned)nd.app_count, (unsigned)a.n_sub), 64, 0, st>>>(emb_sum, a.packed_bwd, a.blay.total, a.blay.dira_e, L / 2, nd.app,
+                                                                                          nd.app_count, a.gw, a.lay.total, a.lay.emb);
+        MN_LAUNCH_CHECK(ctx);
+    }
+    mn_prof_end(ctx, st);
     return MN_OK;
 }
 

@@ -62,6 +62,10 @@ struct mn_model {
     void* tc_packed = nullptr;
     size_t tc_sub_bytes = 0;
     int tc_ready = 0;
+    // transposed fp16 weight images of the tensor-core data-gradient chain (mn_train_tc.cuh); NULL if the shape is not covered
+    void* tc_dgrad = nullptr;
+    size_t tc_dgrad_sub_bytes = 0;
+    int train_tc_ok = 0;
 };
 
 // counters_d layout (ints)
@@ -108,6 +112,7 @@ struct BwdArgs {
     int fixed_sub;
     int64_t B;                 // rows (identity mode) / slot capacity (routed mode)
     const float* grad_out;     // [rows, out_cols]
+    int64_t grad_rows;         // rows of grad_out (the model call's B)
     int out_cols;
     const float* act;          // activation tape
     float* grad;               // gradient tape
@@ -125,3 +130,15 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
                      size_t ws_bytes, cudaStream_t st);
 size_t mn_mlp_tc_workspace(const mn_model* m, int64_t n_tiles128, int precision);
 int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st);
+// ---- tensor-core training path (csrc/mn_train_tc.cuh): per-tile tape records and the two passes
+struct TrainTcTape {
+    unsigned char* xreg;      // encoder feature tiles        [n_tiles][x_tile_bytes]
+    unsigned char* act;       // activation records           [n_tiles][act_tile_bytes]
+    float* f32;               // [n_tiles][5][128]: sigma pre-activation, rgb (3), image id
+};
+size_t mn_train_tc_x_tile_bytes(const mn_model* m);
+size_t mn_train_tc_act_tile_bytes(const mn_model* m);
+int mn_mlp_tc_launch_train(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles128, const TrainTcTape& tape, cudaStream_t st);
+size_t mn_train_tc_backward_workspace(const mn_model* m, int64_t n_tiles128);
+int mn_train_tc_backward(mn_ctx* ctx, mn_model* m, const BwdArgs& a, int64_t n_tiles128, const TrainTcTape& tape, void* ws, size_t ws_bytes,
+                         cudaStream_t st);

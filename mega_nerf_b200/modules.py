@@ -37,6 +37,25 @@ def get_precision() -> str:
     return _precision
 
 
+_train_precision = os.environ.get('MN_B200_TRAIN_PRECISION', 'fp32')
+
+
+def set_train_precision(name: str) -> None:
+    """Arithmetic of a RECORDING call (parameters require grad) and of its backward pass:
+    'fp32'   CUDA-core kernels - the parity mode (gradients equal the reference's fp32 autograd to its own noise level);
+    'tc_f16' tensor cores: fp16 operands, fp32 accumulation, gradient images scaled by a power of two - what the reference
+             does on a GPU under autocast + GradScaler (runner.py:243-274).  Networks the tensor-core training kernels do not
+             cover (layer_dim != 256, SH / affine heads) silently use the fp32 kernels."""
+    global _train_precision
+    if name not in ('fp32', 'tc_f16'):
+        raise ValueError(f"unknown train precision {name!r}; choose 'fp32' or 'tc_f16'")
+    _train_precision = name
+
+
+def get_train_precision() -> str:
+    return _train_precision
+
+
 class Embedding(nn.Module):
     """(x, sin(2^k x), cos(2^k x), ...)  — models/nerf.py:8-25."""
 
@@ -243,17 +262,26 @@ class _Native:
             off[k] = v[1 + 2 * K.MN_MAX_LAYERS + j]
         return off
 
+    def train_on_tensor_cores(self) -> bool:
+        """True iff a recording call of this model runs the tc_f16 training kernels (set_train_precision + shape coverage)."""
+        return _train_precision == 'tc_f16' and self.handle is not None and bool(K.lib().mn_model_train_tc_supported(self.handle))
+
     def forward_train(self, rows: K.Rows, B: int, device: torch.device, use_coarse: bool,
                       sigma_noise: Optional[torch.Tensor], out_cols: int):
-        """-> (out [B, out_cols], tape).  The tape holds this call's routing tables and activations."""
+        """-> (out [B, out_cols], tape).  The tape holds this call's routing tables and activations; `tape.tc` tells the
+        backward pass which pair of kernels wrote it."""
         L = K.lib()
         h = self.sync(device)
+        tc = self.train_on_tensor_cores()
         out = torch.empty(B, out_cols, device=device, dtype=torch.float32)
         ws = torch.empty(max(int(L.mn_model_workspace_bytes(self.handle, B, K.PREC_FP32)), 256), device=device, dtype=torch.uint8)
-        tape = torch.empty(max(int(L.mn_model_tape_bytes(self.handle, B)), 256), device=device, dtype=torch.uint8)
+        nbytes = L.mn_model_tape_bytes_tc(self.handle, B) if tc else L.mn_model_tape_bytes(self.handle, B)
+        tape = torch.empty(max(int(nbytes), 256), device=device, dtype=torch.uint8)
+        tape.tc = tc
         noise = K.f32c(sigma_noise).view(-1) if sigma_noise is not None else None
-        K.check(L.mn_model_forward_train(h, self.handle, C.byref(rows), B, int(use_coarse), K.ptr(noise), K.ptr(out),
-                                         K.ptr(tape), tape.numel(), K.ptr(ws), ws.numel(), K.stream_of(device)), h)
+        fn = L.mn_model_forward_train_tc if tc else L.mn_model_forward_train
+        K.check(fn(h, self.handle, C.byref(rows), B, int(use_coarse), K.ptr(noise), K.ptr(out),
+                   K.ptr(tape), tape.numel(), K.ptr(ws), ws.numel(), K.stream_of(device)), h)
         return out, tape
 
     def backward(self, B: int, device: torch.device, use_coarse: bool, grad_out: torch.Tensor, tape: torch.Tensor,
@@ -263,10 +291,13 @@ class _Native:
         h = K.ctx(device)
         n = int(L.mn_model_grad_floats(self.handle))
         gbuf = torch.zeros(n, device=device, dtype=torch.float32)
-        ws = torch.empty(max(int(L.mn_model_backward_workspace_bytes(self.handle, B)), 256), device=device, dtype=torch.uint8)
+        tc = bool(getattr(tape, 'tc', False))
+        nws = L.mn_model_backward_workspace_bytes_tc(self.handle, B) if tc else L.mn_model_backward_workspace_bytes(self.handle, B)
+        ws = torch.empty(max(int(nws), 256), device=device, dtype=torch.uint8)
         g = K.f32c(grad_out)
-        K.check(L.mn_model_backward(h, self.handle, B, int(use_coarse), K.ptr(g), K.ptr(tape), tape.numel(), K.ptr(gbuf),
-                                    K.ptr(ws), ws.numel(), K.stream_of(device)), h)
+        fn = L.mn_model_backward_tc if tc else L.mn_model_backward
+        K.check(fn(h, self.handle, B, int(use_coarse), K.ptr(g), K.ptr(tape), tape.numel(), K.ptr(gbuf),
+                   K.ptr(ws), ws.numel(), K.stream_of(device)), h)
         off = self._offsets()
         stride = off['stride']
         grads = []
