@@ -810,7 +810,18 @@ def main():
             log(f'gpu incumbent: {line["gpu_incumbent"]}')
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The per-step all-gather lives inside a captured CUDA graph; tearing the NCCL communicator down while graphs that
+        # reference it are alive blocked in destroy_process_group() for minutes on the 2-GPU box.  Drop the graph, drain the
+        # device, agree that everybody is done, then leave without the collective teardown (the line is already printed).
+        graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
