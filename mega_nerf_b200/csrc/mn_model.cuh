@@ -74,6 +74,7 @@ struct mn_model {
 #define CNT_CURSOR (2 * MN_MAX_SUB + 1)    // [MN_MAX_SUB]
 #define CNT_NSLOTS (3 * MN_MAX_SUB + 1)    // [1] padded slot count (end of last bucket)
 #define CNT_NPAIRS (3 * MN_MAX_SUB + 2)    // [1] routed (row, sub) pairs
+#define CNT_TICKET (3 * MN_MAX_SUB + 3)    // [1] blocks of the count pass that have finished (the last one scans)
 #define CNT_TOTAL (3 * MN_MAX_SUB + 4)
 
 // Arguments common to both MLP kernels.

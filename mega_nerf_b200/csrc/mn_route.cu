@@ -10,9 +10,13 @@
 
 namespace {
 
+// `prune` > 0 (the routing kernels; = max(boundary_margin, 1)^2): centroids whose SQUARED distance exceeds prune x (1 + 1e-5) x the
+// smallest squared distance can neither be the nearest nor fall inside the margin - sqrt is monotone and the slack covers its
+// rounding 50 times over - so their distance is reported as +inf without the IEEE sqrt (and, downstream, without the two IEEE
+// divisions of the blend weight).  Every value that takes part in a comparison or a weight is computed exactly as before.
 template <int KMAX>
 __device__ __forceinline__ void distances(const RowSrc& src, int64_t row, const float* __restrict__ cent, int K,
-                                          int s, bool direct, float* d) {
+                                          int s, bool direct, float* d, float prune = 0.0f) {
     float x[3];
     for (int j = s; j < 3; ++j) x[j] = src.route_xyz(row, j);
     if (direct) {
@@ -30,6 +34,7 @@ __device__ __forceinline__ void distances(const RowSrc& src, int64_t row, const 
     }
     float xn = x[s] * x[s];
     for (int j = s + 1; j < 3; ++j) xn = xn + x[j] * x[j];
+    float amin = INFINITY;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         if (k >= K) break;
@@ -39,7 +44,15 @@ __device__ __forceinline__ void distances(const RowSrc& src, int64_t row, const 
         for (int j = s; j < 3; ++j) acc = fmaf(-2.0f * x[j], cent[k * 3 + j], acc);
         acc = fmaf(xn, 1.0f, acc);
         acc = fmaf(1.0f, cn, acc);
-        d[k] = sqrtf(fmaxf(acc, 0.0f));
+        acc = fmaxf(acc, 0.0f);
+        d[k] = acc;
+        amin = fminf(amin, acc);
+    }
+    const float bound = prune > 0.0f ? fmaf(prune * 1.00001f, amin, 1e-30f) : INFINITY;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k >= K) break;
+        d[k] = d[k] > bound ? INFINITY : sqrtf(d[k]);
     }
 }
 
@@ -58,8 +71,8 @@ __device__ __forceinline__ uint64_t route_row(const float* d, int K, float margi
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
-            float inv = 1.0f / (d[k] + 1e-8f);
-            if (d[k] > thr) inv = 0.0f;
+            float inv = 0.0f;
+            if (!(d[k] > thr)) inv = 1.0f / (d[k] + 1e-8f);       // the reference masks 1/(d + 1e-8) with d > thr: same values, fewer divisions
             w[k] = inv;
             sum = sum + inv;
         }
@@ -67,7 +80,7 @@ __device__ __forceinline__ uint64_t route_row(const float* d, int K, float margi
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
-            w[k] = w[k] / sum;
+            if (w[k] != 0.0f) w[k] = w[k] / sum;                   // 0 / sum == 0
             if (w[k] > 0.0f) mask |= 1ull << k;
         }
     }
@@ -89,7 +102,7 @@ __global__ void route_count_kernel(RowSrc src, int64_t B, const float* __restric
     uint64_t mask = 0;
     if (row < B) {
         float d[KMAX], w[KMAX];
-        distances<KMAX>(src, row, sc, K, s, direct, d);
+        distances<KMAX>(src, row, sc, K, s, direct, d, margin > 1.0f ? margin * margin : 1.0f);
         mask = route_row<KMAX>(d, K, margin, w);
         mask_out[row] = mask;
         if (w_out) {
@@ -107,14 +120,18 @@ __global__ void route_count_kernel(RowSrc src, int64_t B, const float* __restric
     __syncthreads();
     for (int i = threadIdx.x; i < K; i += blockDim.x)
         if (hist[i]) atomicAdd(&counters[CNT_COUNT + i], hist[i]);
-}
-
-__global__ void route_scan_kernel(int* counters, int K) {
-    if (threadIdx.x == 0) {
+    // the last block to finish turns the counts into bucket offsets (was a separate 1-thread launch)
+    __shared__ int last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&counters[CNT_TICKET], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
         int off = 0, pairs = 0;
         for (int k = 0; k < K; ++k) {
             counters[CNT_START + k] = off;
-            const int c = counters[CNT_COUNT + k];
+            const int c = *(volatile int*)&counters[CNT_COUNT + k];
             pairs += c;
             off += (c + MN_BUCKET - 1) / MN_BUCKET * MN_BUCKET;
             counters[CNT_CURSOR + k] = 0;
@@ -200,7 +217,7 @@ __global__ void route_only_kernel(RowSrc src, int64_t B, const float* __restrict
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= B) return;
     float d[KMAX], w[KMAX];
-    distances<KMAX>(src, row, cent, K, s, direct, d);
+    distances<KMAX>(src, row, cent, K, s, direct, d, margin > 1.0f ? margin * margin : 1.0f);
     const uint64_t mask = route_row<KMAX>(d, K, margin, w);
     if (margin > 1.0f) {
 #pragma unroll
@@ -309,8 +326,6 @@ int mn_route_build(mn_ctx* ctx, mn_model* m, const RowSrc& src, int64_t B, int64
     } while (0)
     MN_ROUTE_DISPATCH(route_count_kernel, blocks, 256, src, B, m->centroids_d, K, m->d.cluster_dim_start, m->d.boundary_margin,
                       direct, m->counters_d, mask_buf, w_buf);
-    MN_LAUNCH_CHECK(ctx);
-    route_scan_kernel<<<1, 32, 0, st>>>(m->counters_d, K);
     MN_LAUNCH_CHECK(ctx);
     MN_ROUTE_DISPATCH(route_scatter_kernel, blocks, 256, B, K, m->counters_d, cap, mask_buf, w_buf, slot_row, slot_w, row_slots,
                       ctx->status_d);

@@ -19,7 +19,8 @@ DEV = torch.device('cuda:0')
 # tc_f16 rounds both operands of every layer to fp16 (2^-11): raw MLP rows land at 0.6-3.5e-4 (raw SH coefficients worst), rendered rgb
 # (averaged by compositing) below 1e-4; tc_f16x3 (hi/lo split, 3 passes) is the parity-grade tensor mode.
 MLP_TOL = {'fp32': 1e-5, 'tc_f16': 5e-4, 'tc_f16x3': 1e-5}
-RENDER_TOL = {'fp32': 1e-4, 'tc_f16': 2e-4, 'tc_f16x3': 1e-4}
+# rendered rgb / depth: the north-star tolerance (1e-4 relative) in every precision mode; variances 5x (they are second moments)
+RENDER_TOL = {'fp32': 1e-4, 'tc_f16': 1e-4, 'tc_f16x3': 1e-4}
 PRECS = ['fp32', 'tc_f16', 'tc_f16x3']
 # the 512-wide network runs on tensor cores in single-pass fp16 only (mn_mlp_wide.cuh); 'tc_f16x3' covers <= 256
 TC_UNSUPPORTED_NERF = {'tc_f16x3': {'fg512'}}
@@ -359,6 +360,35 @@ def test_render_rays(golden, rname, prec):
         assert res[k].shape == v.shape and res[k].dtype == torch.float32 and res[k].device.type == 'cuda'
         e = relerr(res[k], v)
         assert e <= (5 * tol if 'variance' in k else tol), (k, e)
+
+
+def test_trained_like_weights_stress():
+    """Random-init weights are benign for 16-bit operands; trained networks are sharper.  Stress case: the C2 network
+    with the high-frequency bands of every first-layer / skip-layer weight matrix amplified x4 and the density head x2.  The
+    parity-grade tensor mode (tc_f16x3) and fp32 must hold the 1e-4 north-star tolerance; the single-pass fp16 mode (what the
+    reference itself runs on a GPU under autocast) is REPORTED and gated at 10x - its headroom on such weights is the point."""
+    from argparse import Namespace
+    m = M()
+    net, _, rays, idx, opts, _, _ = C.render_case('c2_mega8_blend')
+    spec = net.spec
+    hi0 = spec.xyz_dim + 2 * spec.xyz_dim * 8                    # first PE column of band 2^8
+    for w in net.weights:
+        for name in ('xyz_encodings.0.0.weight', f'xyz_encodings.{spec.skip_layers[0]}.0.weight'):
+            w[name] = w[name].clone()
+            w[name][:, hi0:spec.in_xyz] *= 4.0
+        w['sigma.weight'] = w['sigma.weight'] * 2.0
+    hp = Namespace(**vars(opts))
+    with torch.inference_mode():
+        ref, _ = O.render_rays(net, None, rays, idx, opts, None, None, True, False, False)
+    pn = product_net(net)
+    errs = {}
+    for prec in PRECS:
+        m.set_precision(prec)
+        res, _ = m.render_rays(pn, None, rays.to(DEV), idx.to(DEV), hp, None, None, True, False, False)
+        errs[prec] = max(relerr(res[k], ref[k]) for k in ('rgb_fine', 'depth_fine'))
+    print('trained-like stress case, max rel err of rgb_fine / depth_fine:', {k: f'{v:.2e}' for k, v in errs.items()})
+    assert errs['fp32'] <= 1e-4 and errs['tc_f16x3'] <= 1e-4, errs
+    assert errs['tc_f16'] <= 1e-3, errs
 
 
 def test_graphed_render_rays_matches_eager():
