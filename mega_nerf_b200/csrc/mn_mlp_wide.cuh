@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_wide_kernel(const TcArgs A
         // =========================== TMA producer ===========================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, p_ahead = 0;
+            const uint32_t empty_pa = smem_u32(empty);
             for (int64_t grp = g_first; grp < n_groups; grp += g_stride) {
                 const int64_t tile_raw = grp * CS + rank;
                 const int64_t tile = tile_raw < n_tiles ? tile_raw : grp * CS;   // padding CTA: any valid feature tile will do
@@ -161,18 +162,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_wide_kernel(const TcArgs A
                                                    (g.src[sgi] == SRC_XAUX ? (int64_t)P.kpe * kTileM : 0);
                                 const uint32_t wbytes = (uint32_t)(kPPXCols * nw * 2), xbytes = (uint32_t)(kPPXCols * kTileM * 2);
                                 for (int k0 = 0; k0 < kseg; k0 += kPPXCols) {
-                                    unsigned char* st_base = ring + (size_t)stage * kWStageBytes;
+                                    const int cur = stage;
+                                    unsigned char* st_base = ring + (size_t)cur * kWStageBytes;
                                     const unsigned char* wsrc = wimg + (size_t)(kbase + k0) * nw * 2;
-                                    mbar_wait(&empty[stage], phase ^ 1);
-                                    mbar_expect_tx(&full[stage], wbytes + xbytes);
+                                    if (!p_ahead) mbar_wait(&empty[cur], phase ^ 1);
+                                    if (++stage == kWStages) { stage = 0; phase ^= 1; }
+                                    p_ahead = mbar_test_a(empty_pa + 8u * (uint32_t)stage, phase ^ 1);   // look-ahead probe (see mn_mlp_tc.cu)
+                                    mbar_expect_tx(&full[cur], wbytes + xbytes);
                                     if (CS > 1) {
                                         const uint32_t slice = wbytes / CS;
-                                        bulk_g2s_mc(st_base + (size_t)rank * slice, wsrc + (size_t)rank * slice, slice, &full[stage], cta_mask);
+                                        bulk_g2s_mc(st_base + (size_t)rank * slice, wsrc + (size_t)rank * slice, slice, &full[cur], cta_mask);
                                     } else {
-                                        bulk_g2s(st_base, wsrc, wbytes, &full[stage]);
+                                        bulk_g2s(st_base, wsrc, wbytes, &full[cur]);
                                     }
-                                    bulk_g2s(st_base + kPPXOff, xt + (size_t)k0 * kTileM, xbytes, &full[stage]);
-                                    if (++stage == kWStages) { stage = 0; phase ^= 1; }
+                                    bulk_g2s(st_base + kPPXOff, xt + (size_t)k0 * kTileM, xbytes, &full[cur]);
                                 }
                                 kbase += kseg;
                                 continue;
@@ -180,16 +183,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_wide_kernel(const TcArgs A
                             for (int k0 = 0; k0 < kseg; k0 += kWSlabCols) {
                                 const int kc = min(kWSlabCols, kseg - k0);
                                 const uint32_t bytes = (uint32_t)(kc * nw * 2);
-                                mbar_wait(&empty[stage], phase ^ 1);      // CS > 1: released by every CTA of the cluster
-                                mbar_expect_tx(&full[stage], bytes);
+                                const int cur = stage;
+                                if (!p_ahead) mbar_wait(&empty[cur], phase ^ 1);      // CS > 1: released by every CTA of the cluster
+                                if (++stage == kWStages) { stage = 0; phase ^= 1; }
+                                p_ahead = mbar_test_a(empty_pa + 8u * (uint32_t)stage, phase ^ 1);
+                                mbar_expect_tx(&full[cur], bytes);
                                 if (CS > 1) {
                                     const uint32_t slice = bytes / CS;
-                                    bulk_g2s_mc(ring + (size_t)stage * kWStageBytes + (size_t)rank * slice,
-                                                wimg + (size_t)(kbase + k0) * nw * 2 + (size_t)rank * slice, slice, &full[stage], cta_mask);
+                                    bulk_g2s_mc(ring + (size_t)cur * kWStageBytes + (size_t)rank * slice,
+                                                wimg + (size_t)(kbase + k0) * nw * 2 + (size_t)rank * slice, slice, &full[cur], cta_mask);
                                 } else {
-                                    bulk_g2s(ring + (size_t)stage * kWStageBytes, wimg + (size_t)(kbase + k0) * nw * 2, bytes, &full[stage]);
+                                    bulk_g2s(ring + (size_t)cur * kWStageBytes, wimg + (size_t)(kbase + k0) * nw * 2, bytes, &full[cur]);
                                 }
-                                if (++stage == kWStages) { stage = 0; phase ^= 1; }
                             }
                             kbase += kseg;
                         }
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_wide_kernel(const TcArgs A
     } else if (warp == kWarpMma) {
         // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
         int stage = 0;
-        uint32_t phase = 0, eph0 = 0, eph1 = 0;
+        uint32_t phase = 0, eph0 = 0, eph1 = 0, ahead = 0;
         bool pend0 = false, pend1 = false;   // an epilogue of that N half is outstanding (TMEM half + activation columns busy)
         const uint32_t h_base = smem_u32(Hs), ring_base = smem_u32(ring);
         const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
@@ -230,14 +235,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_wide_kernel(const TcArgs A
                         if (from_x) {
                             for (int rem = g.k[sgi]; rem > 0; rem -= kPPXCols) {
                                 const uint64_t so = (uint64_t)stage * st_step;
-                                mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
+                                const uint32_t cur = (uint32_t)stage;
+                                if (!ahead) mbar_wait_a(full_a + 8u * cur, phase);
                                 tc_fence_after();
-                                if (CS > 1)
-                                    mma_stage_mc(d_tmem, xd0 + so, bd0 + so, 0, 0, idesc, accum, 0u, empty_a + 8u * (uint32_t)stage, cta_mask);
-                                else
-                                    mma_stage(d_tmem, xd0 + so, bd0 + so, 0, 0, idesc, accum, 0u, empty_a + 8u * (uint32_t)stage);
-                                accum = 1;
                                 if (++stage == kWStages) { stage = 0; phase ^= 1; }
+                                ahead = mbar_test_a(full_a + 8u * (uint32_t)stage, phase);      // look-ahead probe (see mn_mlp_tc.cu)
+                                if (CS > 1)
+                                    mma_stage_mc(d_tmem, xd0 + so, bd0 + so, 0, 0, idesc, accum, 0u, empty_a + 8u * cur, cta_mask);
+                                else
+                                    mma_stage(d_tmem, xd0 + so, bd0 + so, 0, 0, idesc, accum, 0u, empty_a + 8u * cur);
+                                accum = 1;
                             }
                             continue;
                         }
@@ -253,16 +260,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_wide_kernel(const TcArgs A
                             }
                             const uint32_t two = rem >= 32 ? 1u : 0u;
                             const uint64_t bd = bd0 + (uint64_t)stage * st_step;
-                            mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
+                            const uint32_t cur = (uint32_t)stage;
+                            if (!ahead) mbar_wait_a(full_a + 8u * cur, phase);
                             tc_fence_after();
+                            if (++stage == kWStages) { stage = 0; phase ^= 1; }
+                            ahead = mbar_test_a(full_a + 8u * (uint32_t)stage, phase);
                             if (CS > 1)
-                                mma_stage_mc(d_tmem, ad, bd, ad + a_step, bd + b_step, idesc, accum, two, empty_a + 8u * (uint32_t)stage, cta_mask);
+                                mma_stage_mc(d_tmem, ad, bd, ad + a_step, bd + b_step, idesc, accum, two, empty_a + 8u * cur, cta_mask);
                             else
-                                mma_stage(d_tmem, ad, bd, ad + a_step, bd + b_step, idesc, accum, two, empty_a + 8u * (uint32_t)stage);
+                                mma_stage(d_tmem, ad, bd, ad + a_step, bd + b_step, idesc, accum, two, empty_a + 8u * cur);
                             accum = 1;
                             ad += two ? 2 * a_step : a_step;
                             kdone += kWSlabCols;
-                            if (++stage == kWStages) { stage = 0; phase ^= 1; }
                             // half 0's accumulator is complete and nothing issued later reads activation columns 0..255:
                             // its epilogue may overwrite them while the rest of half 1 is still running
                             if (nh == 2 && half == 1 && !from_x && (kdone == kWHalf || (rem <= kWSlabCols && kdone < kWHalf)))
