@@ -1,38 +1,88 @@
 // Context / model management and the nn.Module-level forward entry point of the C ABI.
+#include <cuda_fp16.h>
+
 #include <vector>
 
 #include "mn_model.cuh"
 
 namespace {
 
-__global__ void transpose_kernel(const float* __restrict__ src, int N, int K, float* __restrict__ dst) {
-    // src [N][K] (nn.Linear weight, [out,in]) -> dst [K][N]
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)N * K) return;
-    const int k = (int)(i / N), n = (int)(i % N);
-    dst[i] = src[(int64_t)n * K + k];
+__global__ void __launch_bounds__(256) pack_ops_kernel(const PackOp* __restrict__ ops) {
+    const PackOp op = ops[blockIdx.y];
+    const float* __restrict__ src = op.src;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < op.count; i += (long long)gridDim.x * blockDim.x) {
+        switch (op.kind) {
+            case PK_COPY:
+                reinterpret_cast<float*>(op.dst)[i] = src[i];
+                break;
+            case PK_TRANSPOSE: {      // src [N][K] (nn.Linear weight, [out,in]) -> dst [K][N]
+                const int N = op.p[0], K = op.p[1];
+                const int k = (int)(i / N), n = (int)(i % N);
+                reinterpret_cast<float*>(op.dst)[i] = src[(long long)n * K + k];
+                break;
+            }
+            case PK_SUBMATRIX: {      // src [N][K] -> dst [N][kw] = src[:, koff : koff + kw]
+                const int K = op.p[1], koff = op.p[2], kw = op.p[3];
+                const int n = (int)(i / kw), k = (int)(i % kw);
+                reinterpret_cast<float*>(op.dst)[i] = src[(long long)n * K + koff + k];
+                break;
+            }
+            case PK_TC_IMAGE: {       // K-major Wt[k][n_src] fp32 -> image [K/8][N][8] fp16 (hi) and the fp16 residual (lo)
+                const int n_src = op.p[0], k_src = op.p[1], N = op.p[2], k_real0 = op.p[4], k_pad0 = op.p[5];
+                const int k8 = (int)(i % 8), n = (int)((i / 8) % N), kc = (int)(i / (8 * (long long)N));
+                const int k = kc * 8 + k8;
+                int ks;
+                if (k < k_pad0) ks = k < k_real0 ? k : -1;
+                else ks = k_real0 + (k - k_pad0);
+                float v = 0.0f;
+                if (ks >= 0 && ks < k_src && n < n_src) v = src[(long long)ks * n_src + n];
+                const __half h = __float2half_rn(v);
+                reinterpret_cast<__half*>(op.dst)[i] = h;
+                if (op.dst2) reinterpret_cast<__half*>(op.dst2)[i] = __float2half_rn(v - __half2float(h));
+                break;
+            }
+            case PK_TC_HALF: {        // half-major image [N-half][K/8][nw][8] fp16 (512-wide kernel)
+                const int n_src = op.p[0], k_src = op.p[1], K = op.p[3], k_real0 = op.p[4], k_pad0 = op.p[5], nw = op.p[6];
+                const int k8 = (int)(i % 8), n = (int)((i / 8) % nw);
+                const long long rest = i / (8 * (long long)nw);
+                const int kc = (int)(rest % (K / 8)), hh = (int)(rest / (K / 8));
+                const int k = kc * 8 + k8, ng = hh * nw + n;
+                int ks;
+                if (k < k_pad0) ks = k < k_real0 ? k : -1;
+                else ks = k_real0 + (k - k_pad0);
+                float v = 0.0f;
+                if (ks >= 0 && ks < k_src && ng < n_src) v = src[(long long)ks * n_src + ng];
+                reinterpret_cast<__half*>(op.dst)[i] = __float2half_rn(v);
+                break;
+            }
+            case PK_TC_F32:           // copy with zero padding
+                reinterpret_cast<float*>(op.dst)[i] = i < op.p[0] ? src[i] : 0.0f;
+                break;
+            case PK_DGRAD: {          // image (n, k) = Wd[k * ld + n]: transposed fp16 image of the data-gradient chain
+                const int ld = op.p[0], N = op.p[1];
+                const int k8 = (int)(i % 8), n = (int)((i / 8) % N), kc = (int)(i / (8 * (long long)N));
+                reinterpret_cast<__half*>(op.dst)[i] = __float2half_rn(src[(long long)(kc * 8 + k8) * ld + n]);
+                break;
+            }
+            case PK_RGBW: {           // K-major Wt[k][c] -> [c][k]
+                const int K = op.p[0], Cc = op.p[1];
+                reinterpret_cast<float*>(op.dst)[(i % Cc) * K + i / Cc] = src[i];
+                break;
+            }
+        }
+    }
 }
 
-int pack_T(mn_ctx* ctx, const float* src, int N, int K, float* dst, cudaStream_t st) {
-    const int64_t n = (int64_t)N * K;
-    transpose_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(src, N, K, dst);
-    MN_LAUNCH_CHECK(ctx);
+int pack_T(mn_ctx* ctx, const float* src, int N, int K, float* dst, cudaStream_t) {
+    PackOp op{src, dst, nullptr, (long long)N * K, PK_TRANSPOSE, {N, K, 0, 0, 0, 0, 0}};
+    mn_pack_push(ctx, op);
     return MN_OK;
 }
 
-__global__ void submatrix_kernel(const float* __restrict__ src, int N, int K, int koff, int kw, float* __restrict__ dst) {
-    // src [N][K] (nn.Linear weight) -> dst [N][kw] = src[:, koff : koff + kw]
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)N * kw) return;
-    const int n = (int)(i / kw), k = (int)(i % kw);
-    dst[i] = src[(int64_t)n * K + koff + k];
-}
-
-int pack_sub(mn_ctx* ctx, const float* src, int N, int K, int koff, int kw, float* dst, cudaStream_t st) {
-    const int64_t n = (int64_t)N * kw;
-    if (n == 0) return MN_OK;
-    submatrix_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(src, N, K, koff, kw, dst);
-    MN_LAUNCH_CHECK(ctx);
+int pack_sub(mn_ctx* ctx, const float* src, int N, int K, int koff, int kw, float* dst, cudaStream_t) {
+    if ((long long)N * kw == 0) return MN_OK;
+    PackOp op{src, dst, nullptr, (long long)N * kw, PK_SUBMATRIX, {N, K, koff, kw, 0, 0, 0}};
+    mn_pack_push(ctx, op);
     return MN_OK;
 }
 
@@ -116,6 +166,29 @@ void build_layout(mn_model* m) {
 
 }  // namespace
 
+void mn_pack_push(mn_ctx* ctx, const PackOp& op) { ctx->pack_ops.push_back(op); }
+
+int mn_pack_flush(mn_ctx* ctx, cudaStream_t st) {
+    const size_t n = ctx->pack_ops.size();
+    if (n == 0) return MN_OK;
+    if (n > ctx->pack_ops_cap) {
+        if (ctx->pack_ops_d) {
+            MN_CUDA(ctx, cudaStreamSynchronize(st));      // a previous table may still be read
+            cudaFree(ctx->pack_ops_d);
+        }
+        ctx->pack_ops_cap = n < 128 ? 128 : 2 * n;
+        MN_CUDA(ctx, cudaMalloc(&ctx->pack_ops_d, ctx->pack_ops_cap * 2 * sizeof(PackOp)));
+    }
+    // two alternating halves of the table: the launch of the previous flush may still be reading its half
+    static thread_local unsigned flip = 0;
+    PackOp* tab = ctx->pack_ops_d + (flip++ & 1u) * ctx->pack_ops_cap;
+    MN_CUDA(ctx, cudaMemcpyAsync(tab, ctx->pack_ops.data(), n * sizeof(PackOp), cudaMemcpyHostToDevice, st));
+    pack_ops_kernel<<<dim3(48, (unsigned)n), 256, 0, st>>>(tab);
+    MN_LAUNCH_CHECK(ctx);
+    ctx->pack_ops.clear();
+    return MN_OK;
+}
+
 extern "C" {
 
 int mn_abi_version(void) { return MN_ABI_VERSION; }
@@ -145,6 +218,7 @@ void mn_destroy(mn_ctx* ctx) {
     if (!ctx) return;
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->status_d) cudaFree(ctx->status_d);
+    if (ctx->pack_ops_d) cudaFree(ctx->pack_ops_d);
     delete ctx;
 }
 
@@ -259,9 +333,11 @@ int mn_model_set_weights(mn_model* m, int sub, const mn_nerf_weights* w, void* s
     const NetDims& nd = m->nd;
     const PackedLayout& l = m->lay;
     float* P = m->packed + (size_t)sub * l.total;
+    ctx->pack_ops.clear();
     auto copy = [&](float* dst, const float* src, size_t n) -> int {
         if (!src) return mn_fail(ctx, MN_ERR_INVALID, "mn_model_set_weights: missing tensor");
-        MN_CUDA(ctx, cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        PackOp op{src, dst, nullptr, (long long)n, PK_COPY, {0, 0, 0, 0, 0, 0, 0}};
+        mn_pack_push(ctx, op);
         return MN_OK;
     };
     int rc;
@@ -303,7 +379,10 @@ int mn_model_set_weights(mn_model* m, int sub, const mn_nerf_weights* w, void* s
                     return rc;
         }
     }
-    return mn_mlp_tc_pack(ctx, m, sub, st);
+    // launch 1: the fp32 layouts; launch 2 (queued by mn_mlp_tc_pack): the fp16 images that read them
+    if ((rc = mn_pack_flush(ctx, st))) return rc;
+    if ((rc = mn_mlp_tc_pack(ctx, m, sub, st))) { ctx->pack_ops.clear(); return rc; }
+    return mn_pack_flush(ctx, st);
 }
 
 static int64_t slot_capacity(const mn_model* m, int64_t B) {

@@ -18,6 +18,19 @@
 
 #include <vector>
 
+// One element-wise re-layout of a weight tensor (fp32 transposes / sub-matrices / copies, fp16 tensor-core images).  The ~75 of
+// them a sub-module needs are queued by mn_model_set_weights and run as TWO launches (fp32 layouts first, the fp16 images that read
+// them second) instead of one tiny launch each: a training step re-packs every sub-module after the optimiser step.
+enum { PK_COPY = 0, PK_TRANSPOSE, PK_SUBMATRIX, PK_TC_IMAGE, PK_TC_HALF, PK_TC_F32, PK_DGRAD, PK_RGBW };
+struct PackOp {
+    const float* src;
+    void* dst;
+    void* dst2;
+    long long count;
+    int kind;
+    int p[7];
+};
+
 struct mn_ctx {
     int device = 0;
     int sm_count = 148;
@@ -28,7 +41,13 @@ struct mn_ctx {
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
     size_t prof_used = 0;
+    // queued weight re-layouts (see PackOp) and their device-side table
+    std::vector<PackOp> pack_ops;
+    PackOp* pack_ops_d = nullptr;
+    size_t pack_ops_cap = 0;
 };
+void mn_pack_push(mn_ctx* ctx, const PackOp& op);
+int mn_pack_flush(mn_ctx* ctx, cudaStream_t st);
 
 static inline void mn_prof_begin(mn_ctx* ctx, cudaStream_t st) {
     if (!ctx->prof_on) return;

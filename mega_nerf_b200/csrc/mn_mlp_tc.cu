@@ -345,49 +345,9 @@ __device__ __forceinline__ void tc_emit_rgb(const MlpArgs& m, int sub, int64_t r
 // ------------------------------------------------------------------------------------------------
 // weight packing: nn.Linear weight [N_src][K_src] fp32 -> image [K/8][N][8] fp16 (hi) and the residual (lo)
 // ------------------------------------------------------------------------------------------------
-__global__ void tc_pack_kernel(const float* __restrict__ wt /* packed fp32, K-major Wt[k][n_src] */, int n_src, int k_src,
-                               int N, int K, int k_real0, int k_pad0, __half* __restrict__ hi, __half* __restrict__ lo) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)N * K) return;
-    // i enumerates the image linearly: ((k/8)*N + n)*8 + k%8
-    const int k8 = (int)(i % 8);
-    const int n = (int)((i / 8) % N);
-    const int kc = (int)(i / (8 * (int64_t)N));
-    const int k = kc * 8 + k8;
-    int ks;
-    if (k < k_pad0) ks = k < k_real0 ? k : -1;
-    else ks = k_real0 + (k - k_pad0);
-    float v = 0.0f;
-    if (ks >= 0 && ks < k_src && n < n_src) v = wt[(int64_t)ks * n_src + n];
-    const __half h = __float2half_rn(v);
-    hi[i] = h;
-    if (lo) lo[i] = __float2half_rn(v - __half2float(h));
-}
 
 // half-major image for the TS kernel: [N-half][K/8][nw][8] fp16 (nw = min(N,128))
-__global__ void tc_pack_half_kernel(const float* __restrict__ wt, int n_src, int k_src, int N, int K, int nw, int k_real0, int k_pad0,
-                                    __half* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)N * K) return;
-    const int k8 = (int)(i % 8);
-    const int n = (int)((i / 8) % nw);
-    const int64_t rest = i / (8 * (int64_t)nw);
-    const int kc = (int)(rest % (K / 8));
-    const int h = (int)(rest / (K / 8));
-    const int k = kc * 8 + k8;
-    const int ng = h * nw + n;
-    int ks;
-    if (k < k_pad0) ks = k < k_real0 ? k : -1;
-    else ks = k_real0 + (k - k_pad0);
-    float v = 0.0f;
-    if (ks >= 0 && ks < k_src && ng < n_src) v = wt[(int64_t)ks * n_src + ng];
-    out[i] = __float2half_rn(v);
-}
 
-__global__ void tc_pack_f32_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_dst) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_dst) dst[i] = i < n ? src[i] : 0.0f;
-}
 
 // ------------------------------------------------------------------------------------------------
 // feature tiles
@@ -1523,17 +1483,14 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         const int64_t n = (int64_t)g.n * K;
         __half* hi = reinterpret_cast<__half*>(base + g.w_off);
         __half* lo = reinterpret_cast<__half*>(base + P.plane_bytes + g.w_off);
+        // queued: all images of the sub-module are written by ONE launch (mn_pack_flush in mn_model_set_weights)
         if (wide) {
-            tc_pack_half_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, g.n < 256 ? g.n : 256, k_real0, k_pad0, hi);
-            MN_LAUNCH_CHECK(ctx);
-            tc_pack_f32_kernel<<<(unsigned)mn_cdiv(P.bstride, 256), 256, 0, st>>>(bias, n_bias, f32 + g.bias_off, P.bstride);
-            MN_LAUNCH_CHECK(ctx);
+            mn_pack_push(ctx, PackOp{wt, hi, nullptr, (long long)n, PK_TC_HALF, {n_src, k_src, g.n, K, k_real0, k_pad0, g.n < 256 ? g.n : 256}});
+            mn_pack_push(ctx, PackOp{bias, f32 + g.bias_off, nullptr, (long long)P.bstride, PK_TC_F32, {n_bias, 0, 0, 0, 0, 0, 0}});
             return MN_OK;
         }
-        tc_pack_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wt, n_src, k_src, g.n, K, k_real0, k_pad0, hi, lo);
-        MN_LAUNCH_CHECK(ctx);
-        tc_pack_f32_kernel<<<1, 256, 0, st>>>(bias, n_bias, f32 + g.bias_off, 256);
-        MN_LAUNCH_CHECK(ctx);
+        mn_pack_push(ctx, PackOp{wt, hi, lo, (long long)n, PK_TC_IMAGE, {n_src, k_src, g.n, K, k_real0, k_pad0, 0}});
+        mn_pack_push(ctx, PackOp{bias, f32 + g.bias_off, nullptr, 256, PK_TC_F32, {n_bias, 0, 0, 0, 0, 0, 0}});
         return MN_OK;
     };
     int rc, gi = 0;
@@ -1549,10 +1506,8 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
     }
     if ((rc = pack(P.g[gi++], Pk + m->lay.rgb_w, nd.rgb_dim, nd.rgb_in, 0, 0, Pk + m->lay.rgb_b, nd.rgb_dim))) return rc;
     // sigma_w [L] + sigma_b
-    tc_pack_f32_kernel<<<(unsigned)mn_cdiv(nd.L + 4, 256), 256, 0, st>>>(Pk + m->lay.sigma_w, nd.L, f32 + P.sigma_w_off, nd.L);
-    MN_LAUNCH_CHECK(ctx);
-    tc_pack_f32_kernel<<<1, 32, 0, st>>>(Pk + m->lay.sigma_b, 1, f32 + P.sigma_w_off + nd.L, 4);
-    MN_LAUNCH_CHECK(ctx);
+    mn_pack_push(ctx, PackOp{Pk + m->lay.sigma_w, f32 + P.sigma_w_off, nullptr, (long long)nd.L, PK_TC_F32, {nd.L, 0, 0, 0, 0, 0, 0}});
+    mn_pack_push(ctx, PackOp{Pk + m->lay.sigma_b, f32 + P.sigma_w_off + nd.L, nullptr, 4, PK_TC_F32, {1, 0, 0, 0, 0, 0, 0}});
     m->tc_ready = 1;
 
     // ---- data-gradient images of the tensor-core training path (transposed weights, single fp16 plane + fp32 block)
@@ -1567,9 +1522,7 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         unsigned char* db = (unsigned char*)m->tc_dgrad + (size_t)sub * D.sub_bytes;
         const float* Q = m->packed_bwd + (size_t)sub * m->blay.total;
         auto packd = [&](const TcGemm& g, const float* wd, int ld) -> int {
-            const int64_t n = (int64_t)g.n * g.k[0];
-            tc_pack_dgrad_kernel<<<(unsigned)mn_cdiv(n, 256), 256, 0, st>>>(wd, ld, g.n, g.k[0], reinterpret_cast<__half*>(db + g.w_off));
-            MN_LAUNCH_CHECK(ctx);
+            mn_pack_push(ctx, PackOp{wd, db + g.w_off, nullptr, (long long)g.n * g.k[0], PK_DGRAD, {ld, g.n, g.k[0], 0, 0, 0, 0}});
             return MN_OK;
         };
         int di = 0;
@@ -1578,10 +1531,8 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         for (int l = nd.layers - 1; l >= 1; --l)
             if ((rc = packd(D.g[di++], Q + m->blay.w[l], nd.L))) return rc;       // [L][L]: hidden-part columns of layer l
         float* df32 = reinterpret_cast<float*>(db + D.f32_off);
-        tc_pack_f32_kernel<<<(unsigned)mn_cdiv(nd.L, 256), 256, 0, st>>>(Pk + m->lay.sigma_w, nd.L, df32, nd.L);
-        MN_LAUNCH_CHECK(ctx);
-        tc_pack_rgbw_kernel<<<(unsigned)mn_cdiv(3 * (nd.L / 2), 256), 256, 0, st>>>(Pk + m->lay.rgb_w, nd.L / 2, 3, df32 + nd.L);
-        MN_LAUNCH_CHECK(ctx);
+        mn_pack_push(ctx, PackOp{Pk + m->lay.sigma_w, df32, nullptr, (long long)nd.L, PK_TC_F32, {nd.L, 0, 0, 0, 0, 0, 0}});
+        mn_pack_push(ctx, PackOp{Pk + m->lay.rgb_w, df32 + nd.L, nullptr, (long long)3 * (nd.L / 2), PK_RGBW, {nd.L / 2, 3, 0, 0, 0, 0, 0}});
         m->train_tc_ok = 1;
     }
     return MN_OK;

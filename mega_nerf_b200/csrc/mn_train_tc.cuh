@@ -44,19 +44,6 @@ inline bool build_dgrad_plan(const NetDims& nd, TcPlan* p) {
     return true;
 }
 
-// image (n, k) = Wd[k * ld + n]   (Wd = nn.Linear storage [out = k][in = n], BwdLayout), K-major [K/8][N][8] fp16
-__global__ void tc_pack_dgrad_kernel(const float* __restrict__ wd, int ld, int N, int K, __half* __restrict__ img) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)N * K) return;
-    const int k8 = (int)(i % 8), n = (int)((i / 8) % N), kc = (int)(i / (8 * (int64_t)N));
-    img[i] = __float2half_rn(wd[(int64_t)(kc * 8 + k8) * ld + n]);
-}
-// rgb weights: K-major Wt[k][c] (PackedLayout) -> [c][k]
-__global__ void tc_pack_rgbw_kernel(const float* __restrict__ wt, int K, int C, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < K * C) out[(i % C) * K + i / C] = wt[i];
-}
-
 // S = 2^(10 - ceil(log2(max |g|)))  (1 if g == 0 or not finite): the gradient images hold S * dZ in fp16
 __global__ void tc_grad_scale_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ scale) {
     __shared__ float red[32];
