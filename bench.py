@@ -191,6 +191,12 @@ class ClockSampler:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits',
                                           '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            # nvidia-smi needs ~0.1-0.3 s before its first row: wait for it, then drop the idle rows so that a short
+            # timed region (a few 10-ms training steps) is still covered by samples taken under load
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:
+                time.sleep(0.01)
+            self.rows.clear()
         except Exception:  # noqa: BLE001
             self.proc = None
 

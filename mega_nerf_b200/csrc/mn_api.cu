@@ -309,6 +309,8 @@ void mn_model_destroy(mn_model* m) {
     if (m->counters_d) cudaFree(m->counters_d);
     if (m->tc_packed) cudaFree(m->tc_packed);
     if (m->tc_dgrad) cudaFree(m->tc_dgrad);
+    if (m->tc_tp) cudaFree(m->tc_tp);
+    if (m->tp_prog) cudaFree(m->tp_prog);
     delete m;
 }
 

@@ -18,6 +18,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
+#include <vector>
 
 #include "mn_model.cuh"
 
@@ -29,7 +31,7 @@ constexpr int kTileM = 128;
 __device__ unsigned long long g_trace[4 * 4096];
 __device__ unsigned int g_trace_n[2];
 __device__ __forceinline__ void trace_ev(int on, int who, int ev, int sl, int gi) {
-    if (!on || blockIdx.x != 0) return;
+    if (!(on & 1) || blockIdx.x != 0) return;
     const unsigned int i = atomicAdd(&g_trace_n[who], 1u);
     if (i < 2048) {
         unsigned long long t;
@@ -41,7 +43,7 @@ __device__ __forceinline__ void trace_ev(int on, int who, int ev, int sl, int gi
 // SM clock during the kernel (MN_TC_TRACE=1): thread 0 of CTA 0 stamps (clock64, globaltimer) at kernel start and end.
 __device__ unsigned long long g_clk[4];
 __device__ __forceinline__ void clk_stamp(int on, int which) {
-    if (!on || blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (!(on & 1) || blockIdx.x != 0 || threadIdx.x != 0) return;
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_clk[2 * which] = (unsigned long long)clock64();
@@ -659,6 +661,11 @@ struct TcArgs {
     const float* scale;           // PP_DGRAD: device scalar S (power of two): gradient images hold S * dZ
     int64_t act_tile_bytes;       // bytes of one tile's record in tape_act / tape_dz
     int layers;
+    // ---- TMEM ping-pong kernel (mn_mlp_tp.cuh): half-major weight images and the two role tables
+    const unsigned char* tpack;
+    size_t tp_sub_bytes;
+    const uint4* tp_prog;
+    int tp_n[4];
 };
 
 struct SmemLayout {
@@ -1445,6 +1452,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_pp_kernel(const TcArgs A
     }
 }
 
+#include "mn_mlp_tp.cuh"
 #include "mn_mlp_wide.cuh"
 #include "mn_train_tc.cuh"
 
@@ -1476,6 +1484,26 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
     }
     unsigned char* base = (unsigned char*)m->tc_packed + (size_t)sub * sub_bytes;
     const float* Pk = m->packed + (size_t)sub * m->lay.total;
+    // TMEM ping-pong kernel (layer_dim <= 256): its own weight plane and, once per model, the role tables
+    unsigned char* tp_base = nullptr;
+    size_t tp_woff = 0;
+    if (!wide) {
+        size_t tp_bytes = 0;
+        for (int gi2 = 0; gi2 < P.n_gemm; ++gi2) tp_bytes += (size_t)tp_gemm_bytes(P.g[gi2]);
+        tp_bytes = mn_align(tp_bytes, 256);
+        if (!m->tc_tp) {
+            std::vector<uint4> table;
+            if (tp_build_program(P, &table, m->tp_n)) {
+                MN_CUDA(ctx, cudaMalloc(&m->tc_tp, tp_bytes * m->d.n_sub));
+                MN_CUDA(ctx, cudaMemsetAsync(m->tc_tp, 0, tp_bytes * m->d.n_sub, st));
+                MN_CUDA(ctx, cudaMalloc(&m->tp_prog, table.size() * sizeof(uint4)));
+                MN_CUDA(ctx, cudaMemcpyAsync(m->tp_prog, table.data(), table.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+                MN_CUDA(ctx, cudaStreamSynchronize(st));      // `table` is pageable host memory
+                m->tc_tp_sub_bytes = tp_bytes;
+            }
+        }
+        if (m->tc_tp) tp_base = (unsigned char*)m->tc_tp + (size_t)sub * m->tc_tp_sub_bytes;
+    }
     float* f32 = reinterpret_cast<float*>(base + (size_t)P.plane_bytes * 2);
     auto pack = [&](const TcGemm& g, const float* wt, int n_src, int k_src, int k_real0, int k_pad0, const float* bias,
                     int n_bias) -> int {
@@ -1491,6 +1519,11 @@ int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
         }
         mn_pack_push(ctx, PackOp{wt, hi, lo, (long long)n, PK_TC_IMAGE, {n_src, k_src, g.n, K, k_real0, k_pad0, 0}});
         mn_pack_push(ctx, PackOp{bias, f32 + g.bias_off, nullptr, 256, PK_TC_F32, {n_bias, 0, 0, 0, 0, 0, 0}});
+        if (tp_base) {       // half-major image of the TMEM ping-pong kernel: [N-half][K/8][nw][8]
+            const int nw = g.n < 128 ? g.n : 128, nh = (g.n + 127) / 128;
+            mn_pack_push(ctx, PackOp{wt, tp_base + tp_woff, nullptr, (long long)nh * nw * K, PK_TC_HALF, {n_src, k_src, g.n, K, k_real0, k_pad0, nw}});
+            tp_woff += tp_gemm_bytes(g);
+        }
         return MN_OK;
     };
     int rc, gi = 0;
@@ -1559,7 +1592,7 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     static int desc_swap = -1;
     if (desc_swap < 0) {
         const char* e = getenv("MN_TC_TRACE");
-        desc_swap = (e && e[0] == '1') ? 1 : 0;
+        desc_swap = e ? atoi(e) : 0;      // bit 0: timeline; bits 1.. : timing experiments of the TMEM ping-pong kernel (wrong results)
     }
     A.desc_swap = desc_swap;
     A.n_tiles_cap = n_tiles128;
@@ -1577,6 +1610,18 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         const char* e = getenv("MN_TC_PINGPONG");
         use_pp = (e && e[0] == '0') ? 0 : 1;
     }
+    // MN_TC_TP=1: the TMEM ping-pong kernel (mn_mlp_tp.cuh) instead of the shared-memory ping-pong kernel (variants test, A/B runs)
+    static int use_tp = -1;
+    if (use_tp < 0) {
+        const char* e = getenv("MN_TC_TP");
+        use_tp = (e && e[0] == '1') ? 1 : 0;
+    }
+    const TPLayout TL = tp_layout(P);
+    const bool run_tp = !split && P.L <= 256 && use_tp && use_pp && m->tc_tp && TL.stages >= 8;
+    A.tpack = (const unsigned char*)m->tc_tp;
+    A.tp_sub_bytes = m->tc_tp_sub_bytes;
+    A.tp_prog = (const uint4*)m->tp_prog;
+    for (int i = 0; i < 4; ++i) A.tp_n[i] = m->tp_n[i];
     const PPLayout PL = pp_layout(P);
     const bool run_pp = !split && P.L <= 256 && use_pp && PL.total <= kSmemMax && PL.stages >= 3 &&
                         pp_prog_entries(P, P.n_gemm) + 2 <= kPPMaxProg;
@@ -1640,7 +1685,12 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         mn_prof_begin(ctx, st);
         tc_mlp_kernel<true><<<grid, kThreads, total, st>>>(A);
     } else {
-        if (run_pp) {
+        if (run_tp) {
+            const unsigned grid_tp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
+            MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL.total));
+            mn_prof_begin(ctx, st);
+            tc_mlp_tp_kernel<<<grid_tp, kPPThreads, TL.total, st>>>(A);
+        } else if (run_pp) {
             const unsigned grid_pp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<PP_INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));
             mn_prof_begin(ctx, st);

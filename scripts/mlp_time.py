@@ -42,3 +42,18 @@ tot, nl = C.c_double(), C.c_longlong()
 K.check(L.mn_profile_read(h, C.byref(tot), C.byref(nl)), h)
 ms = tot.value / reps
 print(f'width {width} rows {n}: {ms:.3f} ms/launch  {n * flops_per_row(spec) / ms / 1e9:.1f} TFLOP/s   nvidia-smi: {lines[len(lines) // 2] if lines else "-"}')
+# correctness of the timed kernel against the fp32 (CUDA-core) path of the same library: an odd and an even tile count
+prec = os.environ.get('MN_B200_PRECISION', 'tc_f16')
+for rows in (128 * 5 + 17, 128 * 64):
+    xs = x[:rows].contiguous()
+    M.set_precision(prec)
+    got = p(xs).float()
+    so = p(xs[:, :3].contiguous(), sigma_only=True).float()
+    M.set_precision('fp32')
+    ref = p(xs).float()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    msg = f'rows {rows}: max rel err vs fp32 path {err:.3e}'
+    if so is not None:
+        rs = p(xs[:, :3].contiguous(), sigma_only=True).float()
+        msg += f', sigma_only {float((so - rs).abs().max() / rs.abs().max().clamp_min(1e-9)):.3e}'
+    print(msg, 'NaN!' if not torch.isfinite(got).all() else '')

@@ -44,7 +44,8 @@ ev.sort()
 t0 = ev[0][0]
 names = {1: 'mma_start', 2: 'mma_issued', 3: 'epi_accready', 4: 'epi_done'}
 print('counts', list(cnt))
-for t, who, e, sl, gi in ev[:140]:
+W0 = int(os.environ.get('TRACE_SKIP', '0'))
+for t, who, e, sl, gi in ev[W0:W0 + int(os.environ.get('TRACE_SHOW', '140'))]:
     print(f'{t - t0:9d} ns  {names[e]:13s} slot {sl} gemm {gi}')
 # per-GEMM period statistics for slot 0 mma_start events
 st = [t for t, who, e, sl, gi in ev if e == 1 and sl == 0]
