@@ -101,7 +101,45 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+// tcgen05.wait::ld that also pins the 16 destination registers of an earlier tcgen05.ld behind it (register uses are otherwise
+// free to move across an asm statement): lets a second load stay in flight under the arithmetic on the first.
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// One 16-column piece of the epilogue for one accumulator row: + bias -> (ReLU) -> fp16 pairs; returns the partial sigma dot
+// product if kSigma.  (ReLU after the fp16 rounding when no fp32 value is needed: max(round(x), 0) == round(max(x, 0)).)
+template <bool kRelu, bool kSigma>
+__device__ __forceinline__ float tp_piece16(const uint32_t (&v)[16], const float* __restrict__ bias16, const float* __restrict__ sw16,
+                                            uint32_t* hp8) {
+    float sacc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 b = reinterpret_cast<const float4*>(bias16)[i];
+        float f0 = __uint_as_float(v[4 * i + 0]) + b.x, f1 = __uint_as_float(v[4 * i + 1]) + b.y;
+        float f2 = __uint_as_float(v[4 * i + 2]) + b.z, f3 = __uint_as_float(v[4 * i + 3]) + b.w;
+        if (kSigma) {
+            f0 = fmaxf(f0, 0.0f); f1 = fmaxf(f1, 0.0f); f2 = fmaxf(f2, 0.0f); f3 = fmaxf(f3, 0.0f);
+            const float4 s4 = reinterpret_cast<const float4*>(sw16)[i];
+            sacc = fmaf(f0, s4.x, sacc); sacc = fmaf(f1, s4.y, sacc);
+            sacc = fmaf(f2, s4.z, sacc); sacc = fmaf(f3, s4.w, sacc);
+        }
+        uint32_t p0 = pack_h2(f0, f1), p1 = pack_h2(f2, f3);
+        if (kRelu && !kSigma) {
+            const __half2 z = __float2half2_rn(0.0f);
+            __half2 h0 = __hmax2(*reinterpret_cast<__half2*>(&p0), z), h1 = __hmax2(*reinterpret_cast<__half2*>(&p1), z);
+            p0 = *reinterpret_cast<const uint32_t*>(&h0);
+            p1 = *reinterpret_cast<const uint32_t*>(&h1);
+        }
+        hp8[2 * i] = p0;
+        hp8[2 * i + 1] = p1;
+    }
+    return sacc;
+}
 
 // Warps 0..15 epilogue, 16 TMA producer, 17 MMA issuer.
 __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_tp_kernel(const TcArgs A) {
@@ -296,6 +334,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
         const int r = q * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t aphm = 0, fph0 = 0;      // aphm: parity of acc_full[s] in bit s
+        const uint32_t acc_full_a = smem_u32(acc_full);
         int last_sub = -1;
         const int L = P.L;
         for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
@@ -316,122 +355,113 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
             float sigma_[2] = {0.0f, 0.0f}, sacc_[2] = {0.0f, 0.0f};
             uint32_t keep0[16] = {}, keep1[16] = {};      // packed h0 half of the current layer's output, per tile slot
             for (int gi = 0; gi < n_gemm; ++gi) {
-                const TcGemm& g = P.g[gi];
-                const int nh = (g.n + 127) >> 7;
-                const float* bias = F32 + g.bias_off;
-                const bool want_sigma = g.epi == EPI_RELU_SIGMA;
-                const bool publish = g.epi != EPI_RGB && !(want_sigma && A.m.sigma_only);
-                for (int h = 0; h < nh; ++h) {
-                    const int n0 = 128 * h + 32 * part;      // first output channel of this warp's piece
-                    const bool active = n0 < g.n;
-                    const bool last_h = h == nh - 1;
-                    // one tile slot's share of this accumulator half (generic lambda: `sl` is a compile-time constant, so the
-                    // stash arrays keep0 / keep1 stay in registers)
-                    if (g.epi == EPI_RGB) {
-                        // colour head: one code path for both tile slots (nothing is stashed here)
-                        for (int sl = 0; sl < (valid1 ? 2 : 1); ++sl) {
-                            mbar_wait(&acc_full[sl], (aphm >> sl) & 1u);
-                            aphm ^= 1u << sl;
-                            tc_fence_after();
-                            const int64_t slot = (t0 + sl) * kTileM + r;
-                            const int64_t row = slot < n_slots ? (A.m.slot_row ? (int64_t)A.m.slot_row[slot] : slot) : -1;
-                            uint32_t v[32];
-                            tmem_ld32(t_lane + (uint32_t)sl * 256u, v);
-                            tmem_ld_wait();
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&d_free[sl]);
-                            if (part == 0 && row >= 0)
-                                tc_emit_rgb(A.m, A.m.nd.affine ? sub_of(t0 + sl) : 0, row, slot, v, RGBB, sl ? sigma_[1] : sigma_[0], nullptr);
-                        }
-                        continue;
-                    }
-                    auto do_slot = [&](auto slc, uint32_t (&keep)[16]) {
-                        constexpr int sl = decltype(slc)::value;
+                // per-GEMM scalars in registers (the plan lives in the kernel parameters: dynamic constant-bank reads)
+                const int g_n = P.g[gi].n, g_epi = P.g[gi].epi;
+                const int nh = (g_n + 127) >> 7;
+                const float* bias = F32 + P.g[gi].bias_off;
+                const bool want_sigma = g_epi == EPI_RELU_SIGMA;
+                const bool publish = g_epi != EPI_RGB && !(want_sigma && A.m.sigma_only);
+                if (g_epi == EPI_RGB) {
+                    // colour head: one code path for both tile slots (nothing is stashed here)
+                    for (int sl = 0; sl < (valid1 ? 2 : 1); ++sl) {
                         mbar_wait(&acc_full[sl], (aphm >> sl) & 1u);
                         aphm ^= 1u << sl;
                         tc_fence_after();
-                        if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 3, sl, gi * 2 + h);
+                        const int64_t slot = (t0 + sl) * kTileM + r;
+                        const int64_t row = slot < n_slots ? (A.m.slot_row ? (int64_t)A.m.slot_row[slot] : slot) : -1;
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + (uint32_t)sl * 256u, v);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&d_free[sl]);
+                        if (part == 0 && row >= 0)
+                            tc_emit_rgb(A.m, A.m.nd.affine ? sub_of(t0 + sl) : 0, row, slot, v, RGBB, sl ? sigma_[1] : sigma_[0], nullptr);
+                    }
+                    continue;
+                }
+                for (int h = 0; h < nh; ++h) {
+                    const int n0 = 128 * h + 32 * part;      // first output channel of this warp's piece
+                    const bool active = n0 < g_n;
+                    const bool last_h = h == nh - 1;
+                    const int nb = active ? n0 : 0;          // inactive warps (N < 128 halves) run on don't-care columns, no stores
+                    const float* b16 = bias + nb;
+                    const float* s16 = SW + nb;
+                    const uint32_t c_src = (uint32_t)(active ? 32 * part : 0);
+                    const bool stash_out = publish && nh == 2;
+                    // one tile slot's share of this accumulator half.  Generic lambda: the tile slot and the epilogue flavour are
+                    // compile-time constants - the stash arrays stay in registers and the arithmetic is branch-free.
+                    auto do_slot = [&](auto slc, auto reluc, auto sigc, auto lastc, uint32_t (&keep)[16]) {
+                        constexpr int sl = decltype(slc)::value;
+                        constexpr bool kRelu = decltype(reluc)::value, kSigma = decltype(sigc)::value, kLast = decltype(lastc)::value;
+                        mbar_wait_a(acc_full_a + 8u * sl, (aphm >> sl) & 1u);
+                        aphm ^= 1u << sl;
+                        tc_fence_after();
                         const uint32_t t_acc = t_lane + (uint32_t)sl * 256u;
-                        // two 16-column pieces (register budget: the h0 halves of both tile slots stay live across this code).
-                        // Inactive warps (N < 128 halves) run the same code on don't-care columns and skip the stores.
-                        uint32_t hp[16];
-                        float sacc = 0.0f;
-                        const int nb = active ? n0 : 0;
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            uint32_t v[16];
-                            tmem_ld16(t_acc + (uint32_t)((active ? 32 * part : 0) + 16 * c), v);
-                            tmem_ld_wait();
-                            if (c == 1) {
-                                // this warp no longer needs the accumulator
+                        uint32_t v0[16], v1[16];
+                        tmem_ld16(t_acc + c_src, v0);
+                        // last half: every MMA that read this slot's A operand has completed - the stashed h0 half goes out now,
+                        // under the loads, instead of at the tail of the dependent chain
+                        if (kLast && stash_out) tmem_st16(t_acc + 128u + (uint32_t)(16 * part), keep);
+                        tmem_ld_wait16(v0);
+                        tmem_ld16(t_acc + c_src + 16u, v1);      // in flight under the arithmetic on v0
+                        if (kLast) {
+                            uint32_t hp[16];
+                            float sacc = tp_piece16<kRelu, kSigma>(v0, b16, s16, hp);
+                            tmem_ld_wait16(v1);
+                            tc_fence_before();                   // this warp no longer needs the accumulator
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&d_free[sl]);
+                            sacc += tp_piece16<kRelu, kSigma>(v1, b16 + 16, s16 + 16, hp + 8);
+                            if (publish) {
+                                if (active) tmem_st16(t_acc + 128u + (uint32_t)(n0 >> 1), hp);
+                                tmem_st_wait();
                                 tc_fence_before();
                                 __syncwarp();
-                                if (lane == 0) mbar_arrive(&d_free[sl]);
+                                if (lane == 0) mbar_arrive(&a_ready[sl]);
                             }
-                            const float4* b4 = reinterpret_cast<const float4*>(bias + nb + 16 * c);
-                            if (A.desc_swap & 2) {      // timing experiment: no epilogue arithmetic
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) hp[8 * c + i] = v[2 * i] ^ v[2 * i + 1];
-                                continue;
-                            }
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float4 b = b4[i];
-                                float f0 = __uint_as_float(v[4 * i + 0]) + b.x, f1 = __uint_as_float(v[4 * i + 1]) + b.y;
-                                float f2 = __uint_as_float(v[4 * i + 2]) + b.z, f3 = __uint_as_float(v[4 * i + 3]) + b.w;
-                                if (g.epi != EPI_LINEAR) {
-                                    f0 = fmaxf(f0, 0.0f); f1 = fmaxf(f1, 0.0f); f2 = fmaxf(f2, 0.0f); f3 = fmaxf(f3, 0.0f);
+                            if (kSigma) {
+                                SIGP[part * kTileM + r] = sacc_[sl] + (active ? sacc : 0.0f);
+                                sacc_[sl] = 0.0f;
+                                asm volatile("bar.sync 1, 512;" ::: "memory");
+                                if (part == 0) {
+                                    const int64_t slot = (t0 + sl) * kTileM + r;
+                                    const int64_t row = slot < n_slots ? (A.m.slot_row ? (int64_t)A.m.slot_row[slot] : slot) : -1;
+                                    float sv = ((SIGP[r] + SIGP[kTileM + r]) + (SIGP[2 * kTileM + r] + SIGP[3 * kTileM + r])) + SW[L];
+                                    if (A.m.sigma_noise && row >= 0) sv = sv + A.m.sigma_noise[row];
+                                    const float sg = A.m.nd.softplus ? mn_softplus_shifted(sv) : fmaxf(sv, 0.0f);
+                                    sigma_[sl] = sg;
+                                    if (A.m.sigma_only && row >= 0) {
+                                        const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
+                                        A.m.out[o] = A.m.slot_w ? sg * A.m.slot_w[slot] : sg;
+                                    }
                                 }
-                                if (want_sigma) {
-                                    const float4 sw4 = reinterpret_cast<const float4*>(SW + nb + 16 * c)[i];
-                                    sacc = fmaf(f0, sw4.x, sacc); sacc = fmaf(f1, sw4.y, sacc);
-                                    sacc = fmaf(f2, sw4.z, sacc); sacc = fmaf(f3, sw4.w, sacc);
-                                }
-                                hp[8 * c + 2 * i] = pack_h2(f0, f1);
-                                hp[8 * c + 2 * i + 1] = pack_h2(f2, f3);
+                                asm volatile("bar.sync 1, 512;" ::: "memory");   // SIGP is reused by the other tile slot
                             }
-                        }
-                        if (active) sacc_[sl] += sacc;
-                        if (!last_h) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) keep[i] = hp[i];
-                            return;
-                        }
-                        if (publish) {
-                            // all MMAs that read this slot's A operand have completed (acc_full of the last half): overwrite it
-                            const uint32_t a_dst = t_acc + 128u;
-                            if (nh == 2) tmem_st16(a_dst + (uint32_t)(16 * part), keep);
-                            if (active) tmem_st16(a_dst + (uint32_t)(n0 >> 1), hp);
-                            tmem_st_wait();
+                        } else {
+                            // first half of a two-half layer: straight into the stash (all four column pieces are active)
+                            float sacc = tp_piece16<kRelu, kSigma>(v0, b16, s16, keep);
+                            tmem_ld_wait16(v1);
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&a_ready[sl]);
-                        }
-                        if (want_sigma) {
-                            SIGP[part * kTileM + r] = sacc_[sl];
-                            sacc_[sl] = 0.0f;
-                            asm volatile("bar.sync 1, 512;" ::: "memory");
-                            if (part == 0) {
-                                const int64_t slot = (t0 + sl) * kTileM + r;
-                                const int64_t row = slot < n_slots ? (A.m.slot_row ? (int64_t)A.m.slot_row[slot] : slot) : -1;
-                                float s = ((SIGP[r] + SIGP[kTileM + r]) + (SIGP[2 * kTileM + r] + SIGP[3 * kTileM + r])) + SW[L];
-                                if (A.m.sigma_noise && row >= 0) s = s + A.m.sigma_noise[row];
-                                const float sg = A.m.nd.softplus ? mn_softplus_shifted(s) : fmaxf(s, 0.0f);
-                                sigma_[sl] = sg;
-                                if (A.m.sigma_only && row >= 0) {
-                                    const int64_t o = (A.m.scatter ? row : slot) * A.m.out_cols;
-                                    A.m.out[o] = A.m.slot_w ? sg * A.m.slot_w[slot] : sg;
-                                }
-                            }
-                            asm volatile("bar.sync 1, 512;" ::: "memory");   // SIGP is reused by the other tile slot
+                            if (lane == 0) mbar_arrive(&d_free[sl]);
+                            sacc += tp_piece16<kRelu, kSigma>(v1, b16 + 16, s16 + 16, keep + 8);
+                            if (kSigma) sacc_[sl] += sacc;
                         }
                     };
-                    do_slot(std::integral_constant<int, 0>{}, keep0);
-                    if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 4, 0, gi * 2 + h);
-                    if (valid1) {
-                        do_slot(std::integral_constant<int, 1>{}, keep1);
-                        if (warp == 0 && lane == 0) trace_ev(A.desc_swap, 1, 4, 1, gi * 2 + h);
+                    using T = std::true_type;
+                    using F = std::false_type;
+                    using S0 = std::integral_constant<int, 0>;
+                    using S1 = std::integral_constant<int, 1>;
+                    if (g_epi == EPI_RELU) {
+                        if (last_h) { do_slot(S0{}, T{}, F{}, T{}, keep0); if (valid1) do_slot(S1{}, T{}, F{}, T{}, keep1); }
+                        else        { do_slot(S0{}, T{}, F{}, F{}, keep0); if (valid1) do_slot(S1{}, T{}, F{}, F{}, keep1); }
+                    } else if (g_epi == EPI_LINEAR) {
+                        if (last_h) { do_slot(S0{}, F{}, F{}, T{}, keep0); if (valid1) do_slot(S1{}, F{}, F{}, T{}, keep1); }
+                        else        { do_slot(S0{}, F{}, F{}, F{}, keep0); if (valid1) do_slot(S1{}, F{}, F{}, F{}, keep1); }
+                    } else {
+                        if (last_h) { do_slot(S0{}, T{}, T{}, T{}, keep0); if (valid1) do_slot(S1{}, T{}, T{}, T{}, keep1); }
+                        else        { do_slot(S0{}, T{}, T{}, F{}, keep0); if (valid1) do_slot(S1{}, T{}, T{}, F{}, keep1); }
                     }
                 }
             }
