@@ -93,6 +93,72 @@ __device__ __forceinline__ void tp_stage_smem(uint32_t d_tmem, uint64_t ad, uint
         ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(accum), "r"(empty_bar), "r"(release)
         : "memory");
 }
+// A whole activation block in ONE issue sequence: 4 ring stages x 4 K = 16 steps (16 MMAs, A from tensor memory) and, if
+// `release`, the 4 commits that free the stages.  bd0..bd3 = B descriptors of the four stages.  The issuer's instruction count
+// per MMA - not the tensor pipe - paces this kernel, so the common block (K = 256) is straight-line code.
+__device__ __forceinline__ void tp_block_tmem16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bd0, uint64_t bd1, uint64_t bd2, uint64_t bd3,
+                                                uint64_t b_step, uint32_t idesc, uint32_t accum, uint32_t e0, uint32_t e1, uint32_t e2,
+                                                uint32_t e3, uint32_t release) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, rl;\n\t.reg .b64 b<16>;\n\t.reg .b32 a<16>;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %8, 0;\n\t"
+        "setp.ne.and.b32 rl, %13, 0, e;\n\t"
+        "add.u64 b1, %2, %6;\n\tadd.u64 b2, b1, %6;\n\tadd.u64 b3, b2, %6;\n\t"
+        "add.u64 b5, %3, %6;\n\tadd.u64 b6, b5, %6;\n\tadd.u64 b7, b6, %6;\n\t"
+        "add.u64 b9, %4, %6;\n\tadd.u64 b10, b9, %6;\n\tadd.u64 b11, b10, %6;\n\t"
+        "add.u64 b13, %5, %6;\n\tadd.u64 b14, b13, %6;\n\tadd.u64 b15, b14, %6;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\tadd.u32 a4, %1, 32;\n\tadd.u32 a5, %1, 40;\n\t"
+        "add.u32 a6, %1, 48;\n\tadd.u32 a7, %1, 56;\n\tadd.u32 a8, %1, 64;\n\tadd.u32 a9, %1, 72;\n\tadd.u32 a10, %1, 80;\n\t"
+        "add.u32 a11, %1, 88;\n\tadd.u32 a12, %1, 96;\n\tadd.u32 a13, %1, 104;\n\tadd.u32 a14, %1, 112;\n\tadd.u32 a15, %1, 120;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %7, p;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %7, 1;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a4], %3, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a5], b5, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a6], b6, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a7], b7, %7, 1;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a8], %4, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a9], b9, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a10], b10, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a11], b11, %7, 1;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a12], %5, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a13], b13, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a14], b14, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a15], b15, %7, 1;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bd0), "l"(bd1), "l"(bd2), "l"(bd3), "l"(b_step), "r"(idesc), "r"(accum), "r"(e0), "r"(e1),
+          "r"(e2), "r"(e3), "r"(release)
+        : "memory");
+}
+// A whole feature block: 5 ring stages x one K = 16 step, A (this tile slot's feature slice) and B from the same stage.
+__device__ __forceinline__ void tp_block_smem5(uint32_t d_tmem, uint64_t ad0, uint64_t ad1, uint64_t ad2, uint64_t ad3, uint64_t ad4,
+                                               uint64_t b_minus_a, uint32_t idesc, uint32_t accum, uint32_t e0, uint32_t e1, uint32_t e2,
+                                               uint32_t e3, uint32_t e4, uint32_t release) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, rl;\n\t.reg .b64 b<5>;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %8, 0;\n\t"
+        "setp.ne.and.b32 rl, %14, 0, e;\n\t"
+        "add.u64 b0, %1, %6;\n\tadd.u64 b1, %2, %6;\n\tadd.u64 b2, %3, %6;\n\tadd.u64 b3, %4, %6;\n\tadd.u64 b4, %5, %6;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b0, %7, p;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], %2, b1, %7, 1;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], %3, b2, %7, 1;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], %4, b3, %7, 1;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], %5, b4, %7, 1;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t}"
+        ::"r"(d_tmem), "l"(ad0), "l"(ad1), "l"(ad2), "l"(ad3), "l"(ad4), "l"(b_minus_a), "r"(idesc), "r"(accum), "r"(e0), "r"(e1), "r"(e2),
+          "r"(e3), "r"(e4), "r"(release)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -295,7 +361,49 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
                 const uint32_t d_tmem = tmem_base + sl * 256u;
                 const uint64_t bdn = bd_base + ((uint64_t)nw << 16);
                 const uint64_t b_step = (uint64_t)(2u * nw);
-                if (fl & TF_FROM_X) {
+                if (ns == 4u && nk_last == 4u && !(fl & TF_FROM_X)) {
+                    // ---- the common block (K = 256 activations): 16 MMAs in one straight-line issue sequence
+                    uint32_t c0 = stage, c1 = c0 + 1 == nst ? 0u : c0 + 1, c2 = c1 + 1 == nst ? 0u : c1 + 1, c3 = c2 + 1 == nst ? 0u : c2 + 1;
+                    if (!sl) {
+                        const uint32_t p0 = phase, p1 = c1 < c0 ? p0 ^ 1u : p0, p2 = c2 < c0 ? p0 ^ 1u : p0, p3 = c3 < c0 ? p0 ^ 1u : p0;
+                        if (!ahead) mbar_wait_a(full_a + 8u * c0, p0);
+                        mbar_wait_a(full_a + 8u * c1, p1);
+                        mbar_wait_a(full_a + 8u * c2, p2);
+                        mbar_wait_a(full_a + 8u * c3, p3);
+                    }
+                    const uint32_t nx = c3 + 1 == nst ? 0u : c3 + 1;
+                    if (nx < stage) phase ^= 1;
+                    stage = nx;
+                    if (!sl) {
+                        ahead = mbar_test_a(full_a + 8u * stage, phase);
+                        tc_fence_after();
+                    }
+                    tp_block_tmem16(d_tmem, a_t, bdn + (uint64_t)c0 * st_step, bdn + (uint64_t)c1 * st_step, bdn + (uint64_t)c2 * st_step,
+                                    bdn + (uint64_t)c3 * st_step, b_step, idesc, accum, empty_a + 8u * c0, empty_a + 8u * c1, empty_a + 8u * c2,
+                                    empty_a + 8u * c3, release);
+                } else if (ns == 5u && (fl & TF_FROM_X)) {
+                    // ---- the feature block (80 encoding columns): 5 MMAs, A and B of a step in the same stage
+                    uint32_t c[5], ph[5];
+                    c[0] = stage; ph[0] = phase;
+#pragma unroll
+                    for (int i = 1; i < 5; ++i) { c[i] = c[i - 1] + 1 == nst ? 0u : c[i - 1] + 1; ph[i] = c[i] < c[0] ? phase ^ 1u : phase; }
+                    if (!sl) {
+                        if (!ahead) mbar_wait_a(full_a + 8u * c[0], ph[0]);
+#pragma unroll
+                        for (int i = 1; i < 5; ++i) mbar_wait_a(full_a + 8u * c[i], ph[i]);
+                    }
+                    const uint32_t nx = c[4] + 1 == nst ? 0u : c[4] + 1;
+                    if (nx < stage) phase ^= 1;
+                    stage = nx;
+                    if (!sl) {
+                        ahead = mbar_test_a(full_a + 8u * stage, phase);
+                        tc_fence_after();
+                    }
+                    const uint64_t xd = xd0 + (sl ? (uint64_t)(kTPXBytes >> 4) : 0ull);
+                    tp_block_smem5(d_tmem, xd + (uint64_t)c[0] * st_step, xd + (uint64_t)c[1] * st_step, xd + (uint64_t)c[2] * st_step,
+                                   xd + (uint64_t)c[3] * st_step, xd + (uint64_t)c[4] * st_step, bdn - xd, idesc, accum, empty_a + 8u * c[0],
+                                   empty_a + 8u * c[1], empty_a + 8u * c[2], empty_a + 8u * c[3], empty_a + 8u * c[4], release);
+                } else if (fl & TF_FROM_X) {
                     const uint64_t xd = xd0 + (sl ? (uint64_t)(kTPXBytes >> 4) : 0ull);
                     for (uint32_t s2 = 0; s2 < ns; ++s2) {
                         const uint32_t cur = stage;
