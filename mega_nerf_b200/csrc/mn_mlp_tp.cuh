@@ -94,44 +94,51 @@ __device__ __forceinline__ void tp_stage_smem(uint32_t d_tmem, uint64_t ad, uint
         : "memory");
 }
 // A whole activation block in ONE issue sequence: 4 ring stages x 4 K = 16 steps (16 MMAs, A from tensor memory) and, if
-// `release`, the 4 commits that free the stages.  bd0..bd3 = B descriptors of the four stages.  The issuer's instruction count
-// per MMA - not the tensor pipe - paces this kernel, so the common block (K = 256) is straight-line code.
-__device__ __forceinline__ void tp_block_tmem16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bd0, uint64_t bd1, uint64_t bd2, uint64_t bd3,
-                                                uint64_t b_step, uint32_t idesc, uint32_t accum, uint32_t e0, uint32_t e1, uint32_t e2,
-                                                uint32_t e3, uint32_t release) {
+// `release`, the 4 commits that free the stages.  The issuer's instruction count per MMA - not the tensor pipe - paces this
+// kernel (scripts/probes/mma_chain_probe.cu: one thread keeps the pipe at its 64 clk / MMA floor only if it spends well under 64
+// clk per MMA), so the common block (K = 256) is straight-line code on 32-BIT operands: a shared-memory descriptor changes only
+// in its low word (start address >> 4 | LBO << 16; the high word - SBO, version - is constant), b0..b3 = low words of the B
+// descriptors of the four stages, b_step = 2 nw (one K = 16 step).
+__device__ __forceinline__ void tp_block_tmem16(uint32_t d_tmem, uint32_t a_tmem, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
+                                                uint32_t b_step, uint32_t b_hi, uint32_t idesc, uint32_t accum, uint32_t e0, uint32_t e1,
+                                                uint32_t e2, uint32_t e3, uint32_t release) {
     asm volatile(
-        "{\n\t.reg .pred e, p, rl;\n\t.reg .b64 b<16>;\n\t.reg .b32 a<16>;\n\t"
+        "{\n\t.reg .pred e, p, rl;\n\t.reg .b64 q<16>;\n\t.reg .b32 a<16>, l<16>;\n\t"
         "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %8, 0;\n\t"
-        "setp.ne.and.b32 rl, %13, 0, e;\n\t"
-        "add.u64 b1, %2, %6;\n\tadd.u64 b2, b1, %6;\n\tadd.u64 b3, b2, %6;\n\t"
-        "add.u64 b5, %3, %6;\n\tadd.u64 b6, b5, %6;\n\tadd.u64 b7, b6, %6;\n\t"
-        "add.u64 b9, %4, %6;\n\tadd.u64 b10, b9, %6;\n\tadd.u64 b11, b10, %6;\n\t"
-        "add.u64 b13, %5, %6;\n\tadd.u64 b14, b13, %6;\n\tadd.u64 b15, b14, %6;\n\t"
+        "setp.ne.b32 p, %9, 0;\n\t"
+        "setp.ne.and.b32 rl, %14, 0, e;\n\t"
+        "add.u32 l1, %2, %6;\n\tadd.u32 l2, l1, %6;\n\tadd.u32 l3, l2, %6;\n\t"
+        "add.u32 l5, %3, %6;\n\tadd.u32 l6, l5, %6;\n\tadd.u32 l7, l6, %6;\n\t"
+        "add.u32 l9, %4, %6;\n\tadd.u32 l10, l9, %6;\n\tadd.u32 l11, l10, %6;\n\t"
+        "add.u32 l13, %5, %6;\n\tadd.u32 l14, l13, %6;\n\tadd.u32 l15, l14, %6;\n\t"
+        "mov.b64 q0, {%2, %7};\n\tmov.b64 q1, {l1, %7};\n\tmov.b64 q2, {l2, %7};\n\tmov.b64 q3, {l3, %7};\n\t"
+        "mov.b64 q4, {%3, %7};\n\tmov.b64 q5, {l5, %7};\n\tmov.b64 q6, {l6, %7};\n\tmov.b64 q7, {l7, %7};\n\t"
+        "mov.b64 q8, {%4, %7};\n\tmov.b64 q9, {l9, %7};\n\tmov.b64 q10, {l10, %7};\n\tmov.b64 q11, {l11, %7};\n\t"
+        "mov.b64 q12, {%5, %7};\n\tmov.b64 q13, {l13, %7};\n\tmov.b64 q14, {l14, %7};\n\tmov.b64 q15, {l15, %7};\n\t"
         "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\tadd.u32 a4, %1, 32;\n\tadd.u32 a5, %1, 40;\n\t"
         "add.u32 a6, %1, 48;\n\tadd.u32 a7, %1, 56;\n\tadd.u32 a8, %1, 64;\n\tadd.u32 a9, %1, 72;\n\tadd.u32 a10, %1, 80;\n\t"
         "add.u32 a11, %1, 88;\n\tadd.u32 a12, %1, 96;\n\tadd.u32 a13, %1, 104;\n\tadd.u32 a14, %1, 112;\n\tadd.u32 a15, %1, 120;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %7, p;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %7, 1;\n\t"
-        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a4], %3, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a5], b5, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a6], b6, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a7], b7, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], q0, %8, p;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], q1, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], q2, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], q3, %8, 1;\n\t"
         "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a8], %4, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a9], b9, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a10], b10, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a11], b11, %7, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a4], q4, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a5], q5, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a6], q6, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a7], q7, %8, 1;\n\t"
         "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a12], %5, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a13], b13, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a14], b14, %7, 1;\n\t"
-        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a15], b15, %7, 1;\n\t"
-        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(bd0), "l"(bd1), "l"(bd2), "l"(bd3), "l"(b_step), "r"(idesc), "r"(accum), "r"(e0), "r"(e1),
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a8], q8, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a9], q9, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a10], q10, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a11], q11, %8, 1;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a12], q12, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a13], q13, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a14], q14, %8, 1;\n\t"
+        "@e  tcgen05.mma.cta_group::1.kind::f16 [%0], [a15], q15, %8, 1;\n\t"
+        "@rl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "r"(b_step), "r"(b_hi), "r"(idesc), "r"(accum), "r"(e0), "r"(e1),
           "r"(e2), "r"(e3), "r"(release)
         : "memory");
 }
@@ -378,9 +385,9 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
                         ahead = mbar_test_a(full_a + 8u * stage, phase);
                         tc_fence_after();
                     }
-                    tp_block_tmem16(d_tmem, a_t, bdn + (uint64_t)c0 * st_step, bdn + (uint64_t)c1 * st_step, bdn + (uint64_t)c2 * st_step,
-                                    bdn + (uint64_t)c3 * st_step, b_step, idesc, accum, empty_a + 8u * c0, empty_a + 8u * c1, empty_a + 8u * c2,
-                                    empty_a + 8u * c3, release);
+                    const uint32_t bl = (uint32_t)bdn, st32 = (uint32_t)st_step;
+                    tp_block_tmem16(d_tmem, a_t, bl + c0 * st32, bl + c1 * st32, bl + c2 * st32, bl + c3 * st32, 2u * nw, (uint32_t)(bdn >> 32), idesc,
+                                    accum, empty_a + 8u * c0, empty_a + 8u * c1, empty_a + 8u * c2, empty_a + 8u * c3, release);
                 } else if (ns == 5u && (fl & TF_FROM_X)) {
                     // ---- the feature block (80 encoding columns): 5 MMAs, A and B of a step in the same stage
                     uint32_t c[5], ph[5];
