@@ -1689,7 +1689,7 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
             const unsigned grid_tp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL.total));
             mn_prof_begin(ctx, st);
-            tc_mlp_tp_kernel<<<grid_tp, kPPThreads, TL.total, st>>>(A);
+            tc_mlp_tp_kernel<<<grid_tp, kTPThreads, TL.total, st>>>(A);
         } else if (run_pp) {
             const unsigned grid_pp = (unsigned)((n_tiles128 + 1) / 2 < ctx->sm_count ? (n_tiles128 + 1) / 2 : ctx->sm_count);
             MN_CUDA(ctx, cudaFuncSetAttribute(tc_mlp_pp_kernel<PP_INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL.total));

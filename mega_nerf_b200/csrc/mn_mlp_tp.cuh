@@ -29,7 +29,8 @@ constexpr int kTPXBytes = kTPXCols * kTileM * 2;
 constexpr int kTPMaxStages = 12;
 constexpr int kTPMaxProg = 320;       // issuer entries (table is padded by 2)
 constexpr int kTPMaxLoads = 160;      // producer entries
-enum { TF_SLOT1 = 1, TF_FIRST = 2, TF_LAST = 4, TF_FROM_X = 8, TF_WAIT_A = 16 };
+constexpr int kTPThreads = kPPThreads + 32;   // 16 epilogue warps, TMA producer, two MMA issuers (one per tile slot)
+enum { TF_FIRST = 2, TF_LAST = 4, TF_FROM_X = 8, TF_WAIT_A = 16 };
 
 struct TPLayout {
     int ring, f32, f32_stride, sigp, bars, prog, loads, total, stages;
@@ -214,8 +215,8 @@ __device__ __forceinline__ float tp_piece16(const uint32_t (&v)[16], const float
     return sacc;
 }
 
-// Warps 0..15 epilogue, 16 TMA producer, 17 MMA issuer.
-__global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_tp_kernel(const TcArgs A) {
+// Warps 0..15 epilogue, 16 TMA producer, 17 / 18 MMA issuers of tile slot 0 / 1.
+__global__ void __launch_bounds__(kTPThreads, 1) tc_mlp_tp_kernel(const TcArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcPlan& P = A.plan;
     const TPLayout SL = tp_layout(P);
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
     for (int i = threadIdx.x; i < n_prog + 2; i += blockDim.x) PROG[i] = i < n_prog ? A.tp_prog[i] : make_uint4(0u, 0u, 0u, 0u);
     for (int i = threadIdx.x; i < n_loads; i += blockDim.x) LOADS[i] = A.tp_prog[kTPMaxProg + i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kTPMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kTPMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }     // two issuers release a stage
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&d_free[i], kEpiWarps);
@@ -324,122 +325,107 @@ __global__ void __launch_bounds__(kPPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
                 }
             }
         }
-    } else if (warp == kWarpMma) {
-        // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
-        // One table entry per BLOCK = the ring stages of one (GEMM, N-half, segment) for one tile slot: tile slot 0 consumes new
-        // stages, tile slot 1 re-reads them and releases them.  The per-stage inner loop is a handful of instructions; the
-        // issuer's own instruction chain - not the tensor pipe, not the data - is what paces this kernel (ncu: the warp never
-        // spins on a barrier, it is busy ~700 clk per 8 MMAs when every stage pays the full flag decoding).
-        uint32_t stage = 0, phase = 0, blk_stage = 0, blk_phase = 0, ahead = 0;
-        uint32_t dph0 = 0, dph1 = 0, aph0 = 0, aph1 = 0;
+    } else if (warp == kWarpMma || warp == kWarpMma + 1) {
+        // =========================== MMA issuers: one warp per tile slot (one elected lane issues) ===========================
+        // One table entry per BLOCK = the ring stages of one (GEMM, N-half, segment).  Both issuers walk the same table and the
+        // same ring stages, each for its own tile slot (accumulator, A operand, barriers); a stage is free when BOTH have
+        // committed it (`empty` counts 2).  An issuer's own instruction chain - not the tensor pipe, not the data - paces
+        // this kernel (ncu: a single issuer never spins on a barrier, it is busy ~5 clk per instruction, ~250 instructions per
+        // 16-MMA block): two issuers halve that, and the alternation X.h0, Y.h0, X.h1, Y.h1 follows from the data
+        // dependencies (a slot's next block waits for its epilogue; the other slot's MMAs fill the tensor pipe meanwhile).
+        const uint32_t sl = (uint32_t)(warp - kWarpMma);
+        uint32_t stage = 0, phase = 0, ahead = 0, dph = 0, aph = 0;
         const uint32_t ring_base = smem_u32(ring);
         const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
-        const uint32_t acc_full_a = smem_u32(acc_full), d_free_a = smem_u32(d_free), a_ready_a = smem_u32(a_ready);
-        const uint64_t xd0 = make_desc(ring_base + (uint32_t)kTPX0Off, kTileM * 16, 128);
+        const uint32_t acc_full_a = smem_u32(acc_full) + 8u * sl, d_free_a = smem_u32(d_free) + 8u * sl, a_ready_a = smem_u32(a_ready) + 8u * sl;
+        const uint64_t xd = make_desc(ring_base + (uint32_t)kTPX0Off + sl * (uint32_t)kTPXBytes, kTileM * 16, 128);
         const uint64_t bd_base = make_desc(ring_base, 0, 128);                 // LBO (= nw * 16 bytes) is added per entry
         const uint64_t st_step = (uint64_t)(kTPStageBytes >> 4);
+        const uint32_t d_tmem = tmem_base + sl * 256u;
         for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
             const bool valid1 = 2 * pr + 1 < n_tiles;
+            if (sl && !valid1) break;       // odd tile count: the last pair of the launch has no second tile
             uint4 E = PROG[0];
             for (int e = 0; e < n_prog; ++e) {
                 const uint4 En = PROG[e + 1];
                 const uint32_t fl = E.z >> 20;
-                const uint32_t sl = fl & TF_SLOT1;
                 const uint32_t nw = E.z & 0xFFFu, ns = (E.z >> 12) & 0xFu, nk_last = (E.z >> 16) & 0xFu, idesc = E.y;
-                uint32_t a_t = tmem_base + sl * 256u + 128u + E.x;
+                uint32_t a_t = d_tmem + 128u + E.x;
                 E = En;
-                if (sl && !valid1) continue;
-                if (!sl) { blk_stage = stage; blk_phase = phase; }
-                else { stage = blk_stage; phase = blk_phase; }
                 uint32_t accum = 1;
                 if (fl & TF_FIRST) {
                     // the previous contents of this slot's accumulator have been read by the epilogue (fresh barrier: passes)
-                    if (!sl) { mbar_wait_a(d_free_a, dph0 ^ 1); dph0 ^= 1; }
-                    else     { mbar_wait_a(d_free_a + 8, dph1 ^ 1); dph1 ^= 1; }
+                    mbar_wait_a(d_free_a, dph ^ 1);
+                    dph ^= 1;
                     accum = 0;
                 }
                 if (fl & TF_WAIT_A) {
                     // this GEMM's A operand (the previous GEMM's output) is in tensor memory
-                    if (!sl) { mbar_wait_a(a_ready_a, aph0); aph0 ^= 1; }
-                    else     { mbar_wait_a(a_ready_a + 8, aph1); aph1 ^= 1; }
+                    mbar_wait_a(a_ready_a, aph);
+                    aph ^= 1;
                 }
-                tc_fence_after();
-                const uint32_t release = valid1 ? sl : 1u;
-                const uint32_t d_tmem = tmem_base + sl * 256u;
                 const uint64_t bdn = bd_base + ((uint64_t)nw << 16);
                 const uint64_t b_step = (uint64_t)(2u * nw);
+                const uint32_t first = stage;
                 if (ns == 4u && nk_last == 4u && !(fl & TF_FROM_X)) {
                     // ---- the common block (K = 256 activations): 16 MMAs in one straight-line issue sequence
-                    uint32_t c0 = stage, c1 = c0 + 1 == nst ? 0u : c0 + 1, c2 = c1 + 1 == nst ? 0u : c1 + 1, c3 = c2 + 1 == nst ? 0u : c2 + 1;
-                    if (!sl) {
-                        const uint32_t p0 = phase, p1 = c1 < c0 ? p0 ^ 1u : p0, p2 = c2 < c0 ? p0 ^ 1u : p0, p3 = c3 < c0 ? p0 ^ 1u : p0;
-                        if (!ahead) mbar_wait_a(full_a + 8u * c0, p0);
-                        mbar_wait_a(full_a + 8u * c1, p1);
-                        mbar_wait_a(full_a + 8u * c2, p2);
-                        mbar_wait_a(full_a + 8u * c3, p3);
-                    }
+                    const uint32_t c0 = stage, c1 = c0 + 1 == nst ? 0u : c0 + 1, c2 = c1 + 1 == nst ? 0u : c1 + 1, c3 = c2 + 1 == nst ? 0u : c2 + 1;
+                    const uint32_t p0 = phase, p1 = c1 < c0 ? p0 ^ 1u : p0, p2 = c2 < c0 ? p0 ^ 1u : p0, p3 = c3 < c0 ? p0 ^ 1u : p0;
+                    if (!ahead) mbar_wait_a(full_a + 8u * c0, p0);
+                    mbar_wait_a(full_a + 8u * c1, p1);
+                    mbar_wait_a(full_a + 8u * c2, p2);
+                    mbar_wait_a(full_a + 8u * c3, p3);
                     const uint32_t nx = c3 + 1 == nst ? 0u : c3 + 1;
                     if (nx < stage) phase ^= 1;
                     stage = nx;
-                    if (!sl) {
-                        ahead = mbar_test_a(full_a + 8u * stage, phase);
-                        tc_fence_after();
-                    }
+                    ahead = mbar_test_a(full_a + 8u * stage, phase);
+                    tc_fence_after();
                     const uint32_t bl = (uint32_t)bdn, st32 = (uint32_t)st_step;
                     tp_block_tmem16(d_tmem, a_t, bl + c0 * st32, bl + c1 * st32, bl + c2 * st32, bl + c3 * st32, 2u * nw, (uint32_t)(bdn >> 32), idesc,
-                                    accum, empty_a + 8u * c0, empty_a + 8u * c1, empty_a + 8u * c2, empty_a + 8u * c3, release);
+                                    accum, empty_a + 8u * c0, empty_a + 8u * c1, empty_a + 8u * c2, empty_a + 8u * c3, 1u);
                 } else if (ns == 5u && (fl & TF_FROM_X)) {
                     // ---- the feature block (80 encoding columns): 5 MMAs, A and B of a step in the same stage
                     uint32_t c[5], ph[5];
                     c[0] = stage; ph[0] = phase;
 #pragma unroll
                     for (int i = 1; i < 5; ++i) { c[i] = c[i - 1] + 1 == nst ? 0u : c[i - 1] + 1; ph[i] = c[i] < c[0] ? phase ^ 1u : phase; }
-                    if (!sl) {
-                        if (!ahead) mbar_wait_a(full_a + 8u * c[0], ph[0]);
+                    if (!ahead) mbar_wait_a(full_a + 8u * c[0], ph[0]);
 #pragma unroll
-                        for (int i = 1; i < 5; ++i) mbar_wait_a(full_a + 8u * c[i], ph[i]);
-                    }
+                    for (int i = 1; i < 5; ++i) mbar_wait_a(full_a + 8u * c[i], ph[i]);
                     const uint32_t nx = c[4] + 1 == nst ? 0u : c[4] + 1;
                     if (nx < stage) phase ^= 1;
                     stage = nx;
-                    if (!sl) {
-                        ahead = mbar_test_a(full_a + 8u * stage, phase);
-                        tc_fence_after();
-                    }
-                    const uint64_t xd = xd0 + (sl ? (uint64_t)(kTPXBytes >> 4) : 0ull);
+                    ahead = mbar_test_a(full_a + 8u * stage, phase);
+                    tc_fence_after();
                     tp_block_smem5(d_tmem, xd + (uint64_t)c[0] * st_step, xd + (uint64_t)c[1] * st_step, xd + (uint64_t)c[2] * st_step,
                                    xd + (uint64_t)c[3] * st_step, xd + (uint64_t)c[4] * st_step, bdn - xd, idesc, accum, empty_a + 8u * c[0],
-                                   empty_a + 8u * c[1], empty_a + 8u * c[2], empty_a + 8u * c[3], empty_a + 8u * c[4], release);
-                } else if (fl & TF_FROM_X) {
-                    const uint64_t xd = xd0 + (sl ? (uint64_t)(kTPXBytes >> 4) : 0ull);
-                    for (uint32_t s2 = 0; s2 < ns; ++s2) {
-                        const uint32_t cur = stage;
-                        if (!sl) {
-                            if (!ahead) mbar_wait_a(full_a + 8u * cur, phase);
-                            if (++stage == nst) { stage = 0; phase ^= 1; }
-                            ahead = mbar_test_a(full_a + 8u * stage, phase);
-                            tc_fence_after();
-                        } else if (++stage == nst) { stage = 0; phase ^= 1; }
-                        const uint64_t so = (uint64_t)cur * st_step;
-                        tp_stage_smem(d_tmem, xd + so, bdn + so, idesc, accum, empty_a + 8u * cur, release);
-                        accum = 1;
-                    }
+                                   empty_a + 8u * c[1], empty_a + 8u * c[2], empty_a + 8u * c[3], empty_a + 8u * c[4], 1u);
                 } else {
+                    // ---- any other block shape (narrower networks, the colour head): one stage per iteration
                     for (uint32_t s2 = 0; s2 < ns; ++s2) {
                         const uint32_t cur = stage;
-                        if (!sl) {
-                            if (!ahead) mbar_wait_a(full_a + 8u * cur, phase);
-                            if (++stage == nst) { stage = 0; phase ^= 1; }
-                            ahead = mbar_test_a(full_a + 8u * stage, phase);
-                            tc_fence_after();
-                        } else if (++stage == nst) { stage = 0; phase ^= 1; }
-                        tp_stage_tmem(d_tmem, a_t, bdn + (uint64_t)cur * st_step, b_step, idesc, accum, s2 + 1 == ns ? nk_last : 4u,
-                                      empty_a + 8u * cur, release);
-                        a_t += 32u;
+                        if (!ahead) mbar_wait_a(full_a + 8u * cur, phase);
+                        if (++stage == nst) { stage = 0; phase ^= 1; }
+                        ahead = mbar_test_a(full_a + 8u * stage, phase);
+                        tc_fence_after();
+                        const uint64_t so = (uint64_t)cur * st_step;
+                        if (fl & TF_FROM_X) tp_stage_smem(d_tmem, xd + so, bdn + so, idesc, accum, empty_a + 8u * cur, 1u);
+                        else {
+                            tp_stage_tmem(d_tmem, a_t, bdn + so, b_step, idesc, accum, s2 + 1 == ns ? nk_last : 4u, empty_a + 8u * cur, 1u);
+                            a_t += 32u;
+                        }
                         accum = 1;
                     }
                 }
-                if (fl & TF_LAST) commit_elect(acc_full_a + 8u * sl);
+                if (!valid1) {
+                    // no second tile: this issuer also gives the other issuer's release of the block's stages
+                    uint32_t c = first;
+                    for (uint32_t s2 = 0; s2 < ns; ++s2) {
+                        commit_elect(empty_a + 8u * c);
+                        if (++c == nst) c = 0;
+                    }
+                }
+                if (fl & TF_LAST) commit_elect(acc_full_a);
             }
         }
     } else {
@@ -618,10 +604,10 @@ static bool tp_build_program(const TcPlan& P, std::vector<uint4>* table, int cou
                     const unsigned xo = fx ? (unsigned)(((g.src[sgi] == SRC_XAUX ? P.kpe * kTileM * 2 : 0) + k0 * kTileM * 2) >> 4) : 0xFFFFFFFFu;
                     loads.push_back(make_uint4((unsigned)(himg + (kbase + k0) * nw * 2), (unsigned)(kc * nw * 2), xo, 0u));
                 }
-                // one issuer entry per (block, tile slot)
+                // one issuer entry per block (both issuers walk the same table)
                 const int kc_last = kk - (ns - 1) * step;
-                for (int sl = 0; sl < 2; ++sl) {
-                    unsigned fl = (sl ? TF_SLOT1 : 0) | (sgi == 0 ? TF_FIRST : 0) | (sgi == g.nseg - 1 ? TF_LAST : 0) | (fx ? TF_FROM_X : 0);
+                {
+                    unsigned fl = (sgi == 0 ? TF_FIRST : 0) | (sgi == g.nseg - 1 ? TF_LAST : 0) | (fx ? TF_FROM_X : 0);
                     if (!fx && h == 0) fl |= TF_WAIT_A;
                     // kind::f16, D = f32, K-major A and B, N >> 3 at [17,23), M >> 4 at [24,29)  (make_idesc)
                     const unsigned idesc = (1u << 4) | ((unsigned)(nw >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
