@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(kTPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
     uint64_t* a_ready = bars + 28;     // [2] A operand of tile slot s written (next GEMM may start)
     uint64_t* f32_full = bars + 30;
     uint64_t* f32_empty = bars + 31;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+    uint64_t* turn = bars + 32;        // [2] issue token of the two MMA issuers (strict alternation X, Y, X, Y ...)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
     uint4* PROG = reinterpret_cast<uint4*>(smem + SL.prog);
     uint4* LOADS = reinterpret_cast<uint4*>(smem + SL.loads);
 
@@ -255,6 +256,8 @@ __global__ void __launch_bounds__(kTPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
         }
         mbar_init(f32_full, 1);
         mbar_init(f32_empty, kEpiWarps);
+        mbar_init(&turn[0], 1);
+        mbar_init(&turn[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpProd) {
@@ -342,6 +345,12 @@ __global__ void __launch_bounds__(kTPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
         const uint64_t bd_base = make_desc(ring_base, 0, 128);                 // LBO (= nw * 16 bytes) is added per entry
         const uint64_t st_step = (uint64_t)(kTPStageBytes >> 4);
         const uint32_t d_tmem = tmem_base + sl * 256u;
+        // Issue token: the two issuers alternate block by block (X, Y, X, Y ...), i.e. the tensor pipe sees the order of the
+        // one-issuer schedule - one slot's block runs while the other slot's accumulator is drained - but each issuer decodes
+        // its entry, waits for its dependencies and builds its operands while the other one issues.  Free-running issuers
+        // phase-lock instead: both blocks interleave in the pipe, finish together, and both slots wait for the epilogue at once.
+        const uint32_t turn_mine = smem_u32(&turn[sl]), turn_other = smem_u32(&turn[sl ^ 1u]);
+        uint32_t tph = sl ? 0u : 1u;       // issuer 0 starts (fresh barrier: the wait on parity 1 passes)
         for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
             const bool valid1 = 2 * pr + 1 < n_tiles;
             if (sl && !valid1) break;       // odd tile count: the last pair of the launch has no second tile
@@ -381,6 +390,7 @@ __global__ void __launch_bounds__(kTPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
                     ahead = mbar_test_a(full_a + 8u * stage, phase);
                     tc_fence_after();
                     const uint32_t bl = (uint32_t)bdn, st32 = (uint32_t)st_step;
+                    if (valid1) { mbar_wait_a(turn_mine, tph); tph ^= 1; }
                     tp_block_tmem16(d_tmem, a_t, bl + c0 * st32, bl + c1 * st32, bl + c2 * st32, bl + c3 * st32, 2u * nw, (uint32_t)(bdn >> 32), idesc,
                                     accum, empty_a + 8u * c0, empty_a + 8u * c1, empty_a + 8u * c2, empty_a + 8u * c3, 1u);
                 } else if (ns == 5u && (fl & TF_FROM_X)) {
@@ -397,11 +407,13 @@ __global__ void __launch_bounds__(kTPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
                     stage = nx;
                     ahead = mbar_test_a(full_a + 8u * stage, phase);
                     tc_fence_after();
+                    if (valid1) { mbar_wait_a(turn_mine, tph); tph ^= 1; }
                     tp_block_smem5(d_tmem, xd + (uint64_t)c[0] * st_step, xd + (uint64_t)c[1] * st_step, xd + (uint64_t)c[2] * st_step,
                                    xd + (uint64_t)c[3] * st_step, xd + (uint64_t)c[4] * st_step, bdn - xd, idesc, accum, empty_a + 8u * c[0],
                                    empty_a + 8u * c[1], empty_a + 8u * c[2], empty_a + 8u * c[3], empty_a + 8u * c[4], 1u);
                 } else {
                     // ---- any other block shape (narrower networks, the colour head): one stage per iteration
+                    if (valid1) { mbar_wait_a(turn_mine, tph); tph ^= 1; }
                     for (uint32_t s2 = 0; s2 < ns; ++s2) {
                         const uint32_t cur = stage;
                         if (!ahead) mbar_wait_a(full_a + 8u * cur, phase);
@@ -417,7 +429,10 @@ __global__ void __launch_bounds__(kTPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
                         accum = 1;
                     }
                 }
-                if (!valid1) {
+                if (valid1) {
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(turn_other) : "memory");
+                    __syncwarp();
+                } else {
                     // no second tile: this issuer also gives the other issuer's release of the block's stages
                     uint32_t c = first;
                     for (uint32_t s2 = 0; s2 < ns; ++s2) {
