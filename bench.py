@@ -40,14 +40,14 @@ MARGIN = 1.15
 # for diagnostics only (python bench.py --workload c4); their lines carry the same keys.
 WORKLOADS = {
     'c2': dict(desc='BASELINE configs[1]: mega-nerf 8-submodule 256-ch', rays=4096, spec={}, grid=(2, 4), sh_deg=None,
-               kernel='tc_mlp_pp_kernel'),
+               kernel='tc_mlp_tp_kernel'),
     # configs[2]: 65 536 rays per iteration over 8 GPUs = 8192 rays per GPU; the default when N > 1
     'c3': dict(desc='BASELINE configs[2] shard: mega-nerf 8-submodule 256-ch, 65536 rays / 8 GPUs', rays=8192, spec={}, grid=(2, 4),
-               sh_deg=None, kernel='tc_mlp_pp_kernel'),
+               sh_deg=None, kernel='tc_mlp_tp_kernel'),
     'c4': dict(desc='BASELINE configs[3] shape: mega-nerf 25-submodule 512-ch', rays=4096, spec=dict(layer_dim=512), grid=(5, 5),
                sh_deg=None, kernel='tc_mlp_wide_kernel'),
     'c5': dict(desc='BASELINE configs[4]: mega-nerf-sh-3 (SH degree 2 head) 8-submodule 256-ch', rays=8192,
-               spec=dict(pos_dir_dim=0, rgb_dim=27), grid=(2, 4), sh_deg=2, kernel='tc_mlp_pp_kernel'),
+               spec=dict(pos_dir_dim=0, rgb_dim=27), grid=(2, 4), sh_deg=2, kernel='tc_mlp_tp_kernel'),
 }
 WL = WORKLOADS['c2']
 
@@ -708,6 +708,8 @@ def main():
     achieved = flops_step / (kernel_ms_per_step * 1e-3) / 1e12 if kernel_ms_per_step > 0 else 0.0
     passes = {'fp32': 1, 'tc_f16': 1, 'tc_f16x3': 3}[args.precision]
     kernel_name = {'fp32': 'mlp_simt_kernel', 'tc_f16': WL['kernel'], 'tc_f16x3': 'tc_mlp_kernel<split>'}[args.precision]
+    if kernel_name == 'tc_mlp_tp_kernel' and os.environ.get('MN_TC_TP', '1') == '0':
+        kernel_name = 'tc_mlp_pp_kernel'          # A/B switch of libmn_b200.so: the shared-memory ping-pong kernel
     traffic = kernel_traffic(kernel_name, args.workload if world == 1 else 'c3', args.precision)
 
     log(f'mlp kernel: {kernel_ms_per_step:.3f} ms/step, m={mult:.3f}')

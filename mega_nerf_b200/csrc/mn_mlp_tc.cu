@@ -1610,11 +1610,12 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
         const char* e = getenv("MN_TC_PINGPONG");
         use_pp = (e && e[0] == '0') ? 0 : 1;
     }
-    // MN_TC_TP=1: the TMEM ping-pong kernel (mn_mlp_tp.cuh) instead of the shared-memory ping-pong kernel (variants test, A/B runs)
+    // The TMEM ping-pong kernel (mn_mlp_tp.cuh) is the default inference kernel for layer_dim <= 256; MN_TC_TP=0 selects the
+    // shared-memory ping-pong kernel (which also serves the two training modes) - variants test, A/B runs
     static int use_tp = -1;
     if (use_tp < 0) {
         const char* e = getenv("MN_TC_TP");
-        use_tp = (e && e[0] == '1') ? 1 : 0;
+        use_tp = (e && e[0] == '0') ? 0 : 1;
     }
     const TPLayout TL = tp_layout(P);
     const bool run_tp = !split && P.L <= 256 && use_tp && use_pp && m->tc_tp && TL.stages >= 8;

@@ -1,9 +1,8 @@
 // TMEM ping-pong kernel: the inference MLP for layer_dim <= 256 (included inside mn_mlp_tc.cu's anonymous namespace).
 //
-// Shared-memory bandwidth, not the tensor pipe, bounds tc_mlp_pp_kernel: per 128 x 256 x 256 layer of ONE tile it moves
-// 64 KiB (A read) + 128 KiB (B read) + 128 KiB (TMA weight fill) + 64 KiB (epilogue stores) through a 128 B/clk port,
-// i.e. 3072 clk for 2048 clk of MMA (ncu: shared pipe 92 % busy at 0.55-0.6 of the tensor peak).  This kernel removes
-// the two activation terms and halves the fill:
+// Shared-memory bandwidth bounds tc_mlp_pp_kernel: per 128 x 256 x 256 layer of ONE tile it moves 64 KiB (A read) + 128 KiB
+// (B read) + 128 KiB (TMA weight fill) + 64 KiB (epilogue stores) through a 128 B/clk port, i.e. 3072 clk for 2048 clk of
+// MMA (ncu: shared pipe 92 % busy at 0.6 of the tensor peak).  This kernel removes the two activation terms and halves the fill:
 //   * the A operand of every hidden layer lives in TENSOR MEMORY (tcgen05.mma with A from TMEM); the epilogue writes it
 //     there with tcgen05.st (fp16 pairs, one TMEM lane per row) - activations never touch shared memory;
 //   * a CTA works on a PAIR of tiles X, Y of one sub-module and every ring stage (16 KiB: 64 K-columns x one 128-wide
@@ -13,12 +12,32 @@
 //     dependent chain (h1 -> next layer's A) has the other tile's h1 block to hide under.  The h0 half of a layer's
 //     output waits in REGISTERS until the layer's last MMA has read the old A, then both halves are stored.
 //   TMEM columns per tile slot s: [256 s, +128) accumulator (one N-half), [256 s + 128, +128) A operand (K <= 256 fp16).
-//   B read 128 KiB + fill 64 KiB per tile-layer = 1536 clk of the shared pipe for 2048 clk of MMA.
+//   B read 128 KiB + fill 64 KiB per tile-layer = 1536 clk of the shared pipe for 2048 clk of MMA (ncu: LSU 20 % + tensor-core
+//   operand reads 29 % of the pipe; L2 -> SM 3.4 GB per 4736-tile launch against 6.45 GB).
 // The feature segments (PE of the first / skip layer, direction + appearance of the view layer) stay SS-mode MMAs: their
 // 16-column feature slices of both tiles ride in the same ring stage as the matching weight slice.
 //
-// Both single-thread roles (TMA producer, MMA issuer) walk HOST-built tables (tp_build_program): one 16-byte entry per
-// ring stage (producer) / per stage and tile slot (issuer).
+// Roles (608 threads): warps 0..15 epilogue (all 16 drain one accumulator half at a time, 32 columns per warp), warp 16 TMA
+// producer, warps 17 / 18 MMA issuers of tile slot 0 / 1.  What paces the kernel once shared memory is out of the way is the
+// INSTRUCTION CHAIN of the single-thread roles, measured step by step in round 2 (probe: 148 x 32 tiles, TFLOP/s):
+//   719  one issuer, one table entry per ring stage and tile slot (~140 SASS instructions per 4 MMAs)
+//   925  one entry per block (GEMM, N-half, segment, slot), per-stage inner loop
+//  1014  epilogue specialised at compile time (was 3x more control than arithmetic instructions), TMEM loads pipelined
+//  1039  the common blocks as ONE straight-line asm sequence (16 MMAs + 4 commits)
+//  1097  32-bit descriptor arithmetic inside that sequence (a descriptor changes only in its low word): 240 -> 135 instructions
+//  1168  one issuer per tile slot (each decodes, waits and builds operands while the other issues)
+//  1197  issue token between the two issuers (strict X, Y alternation: free-running issuers phase-lock - both blocks
+//        interleave in the pipe, finish together, and both slots wait for the epilogue at once)
+// against 1020 for tc_mlp_pp_kernel on the same box.  scripts/probes/mma_chain_probe.cu: one thread issuing back-to-back reaches
+// the 64 clk / MMA floor (N = 128), dependent accumulation chain or not, A from TMEM or shared memory;
+// scripts/probes/tmem_ld_probe.cu: 16 warps drain tensor memory at ~690 B/clk/SM (a 64 KiB accumulator half in ~100 clk), and a
+// continuous drain halves the MMA rate - neither is the limit here.  What is left (ncu, probe): epilogue warps busy ~70 % of
+// the time (~150 instructions per warp and accumulator half), issuers waiting for the drain of their accumulator.
+// Rejected on hardware: one group of 8 epilogue warps per tile slot (1085: the drain of a half takes longer per warp and
+// both slots stall on it).
+//
+// The TMA producer and the issuers walk HOST-built tables (tp_build_program): one 16-byte entry per ring stage (producer) /
+// per block (issuers).
 #pragma once
 
 constexpr int kTPStageBytes = 16384;
@@ -180,8 +199,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
-                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :: "memory");
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+    // no "memory" clobber: the wait orders tensor-memory -> register traffic only, so the bias loads of the next piece may be
+    // scheduled above it
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

@@ -19,7 +19,7 @@ case "${1:-help}" in
     $G --timeout 900 -- 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_render.csv python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-gpu-incumbent > gpurun_out/l1.log 2>&1;
                          ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_train.csv python bench.py --mode train --steps 1 --warmup 3 > gpurun_out/l2.log 2>&1; tail -3 gpurun_out/l2.log' ;;
   ncu-mlp)      # full capture of the fine-pass launch of the forward MLP kernel
-    $G --timeout 900 -- 'ncu --set full --import-source on --clock-control none -k regex:tc_mlp_pp_kernel -s 5 -c 1 -o gpurun_out/tc_mlp_pp_kernel python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-gpu-incumbent > gpurun_out/n1.log 2>&1; ls -la gpurun_out/*.ncu-rep' ;;
+    $G --timeout 900 -- 'ncu --set full --import-source on --clock-control none -k regex:tc_mlp_tp_kernel -s 5 -c 1 -f -o gpurun_out/tc_mlp_tp_kernel python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-gpu-incumbent > gpurun_out/n1.log 2>&1; ls -la gpurun_out/*.ncu-rep' ;;
   ncu-bwd)      # full capture of the two backward kernels
     $G --timeout 900 -- 'ncu --set full --import-source on --clock-control none -k regex:mlp_bwd -s 4 -c 2 -o gpurun_out/mlp_bwd_kernels python bench.py --mode train --steps 1 --warmup 3 > gpurun_out/n3.log 2>&1; ls -la gpurun_out/*.ncu-rep' ;;
   scale2)       # 2-GPU lines: ray-sharded (graded form) and owner-computes sub-modules

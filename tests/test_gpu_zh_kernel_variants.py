@@ -1,7 +1,7 @@
-"""GPU: the alternatives of the 256-wide tensor-core MLP kernel - the TMEM ping-pong kernel (MN_TC_TP=1: activations in tensor
-memory, weight stages shared by the two tiles of a pair) and the single-tile kernel (MN_TC_PINGPONG=0), environment switches
-libmn_b200.so reads once per process - each in its own subprocess, compared with the default shared-memory ping-pong kernel on
-the same 2048-ray C2 batch and with the reference fixture.  (Round 2 measured and then deleted the other variants: single-tile A-from-TMEM, the cta_group::2 CTA pair
+"""GPU: the alternatives of the default 256-wide tensor-core MLP kernel (the TMEM ping-pong kernel: activations in tensor memory,
+weight stages shared by the two tiles of a pair) - the shared-memory ping-pong kernel (MN_TC_TP=0; it also serves the training
+modes) and the single-tile kernel (MN_TC_PINGPONG=0), environment switches libmn_b200.so reads once per process - each in its
+own subprocess, compared with the default kernel on the same 2048-ray C2 batch and with the reference fixture.  (Round 2 measured and then deleted the other variants: single-tile A-from-TMEM, the cta_group::2 CTA pair
 with three handshakes and shared weight stages, biases folded into the GEMMs - DESIGN.md §7.)
 Every mbarrier wait in these kernels is bounded (a protocol bug traps after ~2 s instead of hanging), and the subprocess has its
 own timeout."""
@@ -56,7 +56,7 @@ def default_out(tmp_path_factory):
     return run_variant(tmp_path_factory.mktemp('variants'), 'default', {})
 
 
-@pytest.mark.parametrize('name,env', [('tmem_pingpong', {'MN_TC_TP': '1'}), ('single_tile', {'MN_TC_PINGPONG': '0'})])
+@pytest.mark.parametrize('name,env', [('smem_pingpong', {'MN_TC_TP': '0'}), ('single_tile', {'MN_TC_PINGPONG': '0'})])
 def test_variant_matches_default_kernel(tmp_path, default_out, name, env):
     got = run_variant(tmp_path, name, env)
     for k, v in default_out.items():
