@@ -1,11 +1,10 @@
 #!/bin/bash
-# one gpurun call: timing of the TMEM ping-pong kernel, A/B against the shared-memory ping-pong kernel, quick parity, ncu
+# one gpurun call: the other BASELINE shapes and the parity-grade tensor mode, each with its full-size parity sample
 mkdir -p gpurun_out
-{
-  echo "== tp"; MN_TC_TP=1 timeout 150 python scripts/mlp_time.py 256 32 2>&1 | grep "TFLOP\|err"
-  echo "== pp"; MN_TC_TP=0 timeout 150 python scripts/mlp_time.py 256 32 2>&1 | grep TFLOP
-} > gpurun_out/tp_check.txt 2>&1
-cat gpurun_out/tp_check.txt
-MN_TC_TP=1 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
-MN_TC_TP=1 timeout 300 ncu --set full --import-source on --clock-control none -k regex:tc_mlp_tp_kernel -s 4 -c 1 -f -o gpurun_out/tc_mlp_tp_kernel python scripts/mlp_time.py 256 32 > gpurun_out/ncu_tp.log 2>&1
-ls -la gpurun_out/*.ncu-rep | tail -2
+for w in c4 c5; do
+  timeout 250 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-incumbent > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
+  tail -1 gpurun_out/bench_$w.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$w', d['ms_per_step'], d['roofline']['kernel'], round(d['roofline']['frac'],4), d['parity']['max_rel_rgb_vs_oracle'], d['parity']['pass'])"
+done
+timeout 250 python bench.py --precision tc_f16x3 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-incumbent > gpurun_out/bench_f16x3.json 2> gpurun_out/bench_f16x3.err
+tail -1 gpurun_out/bench_f16x3.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('f16x3', d['ms_per_step'], d['roofline']['kernel'], round(d['roofline']['frac'],4), d['parity']['max_rel_rgb_vs_oracle'], d['parity']['pass'])"
+echo "== wide kernel probe"; timeout 150 python scripts/mlp_time.py 512 8 2>&1 | grep "TFLOP\|err"
