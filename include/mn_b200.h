@@ -310,6 +310,15 @@ size_t mn_model_backward_workspace_bytes_tc(const mn_model* m, int64_t B);
 int mn_model_backward_tc(mn_ctx* ctx, mn_model* m, int64_t B, int use_coarse, const float* grad_out_d, const void* tape_d,
                          size_t tape_bytes, float* param_grads_d, void* workspace_d, size_t workspace_bytes, void* stream);
 
+/* ---- test hook (host only, no CUDA call) ---------------------------------------------------------------------------
+ * The role tables of the default inference MLP kernel (csrc/mn_mlp_tp.cuh) for one network shape: `desc` as for
+ * mn_model_create (only the per-sub-module fields matter).  table_out receives up to cap_entries 16-byte entries - first the
+ * MMA issuers' block entries, then the TMA producer's stage entries - and info[8] = {issuer entries, issuer entries of a
+ * sigma_only call, producer entries, producer entries of a sigma_only call, bytes of one sub-module's weight image, ring stages,
+ * shared-memory bytes, feature-tile bytes}.  Returns MN_ERR_UNSUPPORTED for shapes this kernel does not run (layer_dim 512,
+ * fp32-only shapes).  Used by tests/test_tp_program.py to check the tables' invariants without a GPU. */
+int mn_debug_tp_program(const mn_model_desc* desc, unsigned int* table_out, int cap_entries, int* info8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1466,6 +1466,29 @@ size_t mn_mlp_tc_workspace(const mn_model* m, int64_t n_tiles128, int precision)
     return mn_align((size_t)n_tiles128 * P.x_tile_bytes * planes, 1024) + 1024;
 }
 
+int mn_mlp_tp_program(const NetDims& nd, unsigned int* table_out, int cap_entries, int* info8) {
+    TcPlan P;
+    if (!build_plan(nd, &P) || nd.L > 256) return MN_ERR_UNSUPPORTED;
+    std::vector<uint4> table;
+    int counts[4];
+    if (!tp_build_program(P, &table, counts)) return MN_ERR_UNSUPPORTED;
+    size_t tp_bytes = 0;
+    for (int gi = 0; gi < P.n_gemm; ++gi) tp_bytes += (size_t)tp_gemm_bytes(P.g[gi]);
+    const TPLayout TL = tp_layout(P);
+    const int info[8] = {counts[0], counts[1], counts[2], counts[3], (int)tp_bytes, TL.stages, TL.total, P.x_tile_bytes};
+    for (int i = 0; i < 8; ++i) info8[i] = info[i];
+    int n = 0;
+    for (int i = 0; i < counts[0] && n < cap_entries; ++i, ++n) {
+        const uint4 e = table[i];
+        table_out[4 * n] = e.x; table_out[4 * n + 1] = e.y; table_out[4 * n + 2] = e.z; table_out[4 * n + 3] = e.w;
+    }
+    for (int i = 0; i < counts[2] && n < cap_entries; ++i, ++n) {
+        const uint4 e = table[kTPMaxProg + i];
+        table_out[4 * n] = e.x; table_out[4 * n + 1] = e.y; table_out[4 * n + 2] = e.z; table_out[4 * n + 3] = e.w;
+    }
+    return MN_OK;
+}
+
 int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st) {
     TcPlan P;
     if (!build_plan(m->nd, &P)) {

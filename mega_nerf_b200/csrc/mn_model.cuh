@@ -136,6 +136,7 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
                      size_t ws_bytes, cudaStream_t st);
 size_t mn_mlp_tc_workspace(const mn_model* m, int64_t n_tiles128, int precision);
 int mn_mlp_tc_pack(mn_ctx* ctx, mn_model* m, int sub, cudaStream_t st);
+int mn_mlp_tp_program(const NetDims& nd, unsigned int* table_out, int cap_entries, int* info8);   // host only (test hook)
 // ---- tensor-core training path (csrc/mn_train_tc.cuh): per-tile tape records and the two passes
 struct TrainTcTape {
     unsigned char* xreg;      // encoder feature tiles        [n_tiles][x_tile_bytes]
