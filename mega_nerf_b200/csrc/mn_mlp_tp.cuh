@@ -28,6 +28,7 @@
 //  1168  one issuer per tile slot (each decodes, waits and builds operands while the other issues)
 //  1197  issue token between the two issuers (strict X, Y alternation: free-running issuers phase-lock - both blocks
 //        interleave in the pipe, finish together, and both slots wait for the epilogue at once)
+//  1220  first-half epilogue: both TMEM loads back to back, `d_free` given before any arithmetic
 // against 1020 for tc_mlp_pp_kernel on the same box.  scripts/probes/mma_chain_probe.cu: one thread issuing back-to-back reaches
 // the 64 clk / MMA floor (N = 128), dependent accumulation chain or not, A from TMEM or shared memory;
 // scripts/probes/tmem_ld_probe.cu: 16 warps drain tensor memory at ~690 B/clk/SM (a 64 KiB accumulator half in ~100 clk), and a
@@ -539,8 +540,19 @@ __global__ void __launch_bounds__(kTPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
                         // last half: every MMA that read this slot's A operand has completed - the stashed h0 half goes out now,
                         // under the loads, instead of at the tail of the dependent chain
                         if (kLast && stash_out) tmem_st16(t_acc + 128u + (uint32_t)(16 * part), keep);
-                        tmem_ld_wait16(v0);
-                        tmem_ld16(t_acc + c_src + 16u, v1);      // in flight under the arithmetic on v0
+                        if (kLast) {
+                            tmem_ld_wait16(v0);
+                            tmem_ld16(t_acc + c_src + 16u, v1);      // in flight under the arithmetic on v0
+                        } else {
+                            // first half: the issuer of this slot waits for the DRAIN of the accumulator (its next block is the
+                            // layer's second half) - both loads go out back to back and `d_free` is given before any arithmetic
+                            tmem_ld16(t_acc + c_src + 16u, v1);
+                            tmem_ld_wait16(v0);
+                            tmem_ld_wait16(v1);
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&d_free[sl]);
+                        }
                         if (kLast) {
                             uint32_t hp[16];
                             float sacc = tp_piece16<kRelu, kSigma>(v0, b16, s16, hp);
@@ -577,10 +589,6 @@ __global__ void __launch_bounds__(kTPThreads, 1) tc_mlp_tp_kernel(const TcArgs A
                         } else {
                             // first half of a two-half layer: straight into the stash (all four column pieces are active)
                             float sacc = tp_piece16<kRelu, kSigma>(v0, b16, s16, keep);
-                            tmem_ld_wait16(v1);
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&d_free[sl]);
                             sacc += tp_piece16<kRelu, kSigma>(v1, b16 + 16, s16 + 16, keep + 8);
                             if (kSigma) sacc_[sl] += sacc;
                         }

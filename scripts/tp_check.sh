@@ -1,10 +1,7 @@
 #!/bin/bash
-# one gpurun call: the other BASELINE shapes and the parity-grade tensor mode, each with its full-size parity sample
+# one gpurun call: probe timing of the default kernel + the parity tests that exercise it
 mkdir -p gpurun_out
-for w in c4 c5; do
-  timeout 250 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-incumbent > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
-  tail -1 gpurun_out/bench_$w.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$w', d['ms_per_step'], d['roofline']['kernel'], round(d['roofline']['frac'],4), d['parity']['max_rel_rgb_vs_oracle'], d['parity']['pass'])"
-done
-timeout 250 python bench.py --precision tc_f16x3 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-incumbent > gpurun_out/bench_f16x3.json 2> gpurun_out/bench_f16x3.err
-tail -1 gpurun_out/bench_f16x3.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('f16x3', d['ms_per_step'], d['roofline']['kernel'], round(d['roofline']['frac'],4), d['parity']['max_rel_rgb_vs_oracle'], d['parity']['pass'])"
-echo "== wide kernel probe"; timeout 150 python scripts/mlp_time.py 512 8 2>&1 | grep "TFLOP\|err"
+{ echo "== tp"; timeout 150 python scripts/mlp_time.py 256 32 2>&1 | grep "TFLOP\|err"; } > gpurun_out/tp_check.txt 2>&1
+cat gpurun_out/tp_check.txt
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_zh_kernel_variants.py tests/test_gpu_ze_properties.py -x -q 2>&1 | tail -3
+timeout 100 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-gpu-incumbent 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['ms_per_step'], d['e2e']['ms_per_step'], round(d['roofline']['frac'],4), d['parity']['max_rel_rgb_vs_oracle'])"
