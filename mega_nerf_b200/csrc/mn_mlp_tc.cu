@@ -1615,7 +1615,7 @@ int mn_mlp_tc_launch(mn_ctx* ctx, mn_model* m, const MlpArgs& a, int64_t n_tiles
     static int desc_swap = -1;
     if (desc_swap < 0) {
         const char* e = getenv("MN_TC_TRACE");
-        desc_swap = e ? atoi(e) : 0;      // bit 0: timeline; bits 1.. : timing experiments of the TMEM ping-pong kernel (wrong results)
+        desc_swap = e ? atoi(e) : 0;      // bit 0: in-kernel timeline + SM-clock stamp
     }
     A.desc_swap = desc_swap;
     A.n_tiles_cap = n_tiles128;

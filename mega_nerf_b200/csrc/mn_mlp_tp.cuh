@@ -642,6 +642,7 @@ static bool tp_build_program(const TcPlan& P, std::vector<uint4>* table, int cou
                 const int step = fx ? kTPXCols : kTPStageCols;
                 const int kk = g.k[sgi];
                 const int ns = (kk + step - 1) / step;
+                if (ns > kTPMaxStages - 4) return false;      // a block must leave ring stages for the next block's prefetch
                 for (int j = 0; j < ns; ++j) {
                     const int k0 = j * step, kc = kk - k0 < step ? kk - k0 : step;
                     const unsigned xo = fx ? (unsigned)(((g.src[sgi] == SRC_XAUX ? P.kpe * kTileM * 2 : 0) + k0 * kTileM * 2) >> 4) : 0xFFFFFFFFu;

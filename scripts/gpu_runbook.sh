@@ -26,5 +26,14 @@ case "${1:-help}" in
     $G --gpus 2 --timeout 900 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -1 gpurun_out/bench_n2.json;
                          python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --parallelism experts --no-cpu-baseline > gpurun_out/bench_n2_experts.json 2> gpurun_out/bench_n2_experts.err; tail -1 gpurun_out/bench_n2_experts.json;
                          python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --gather peer --no-cpu-baseline > gpurun_out/bench_n2_peer.json 2> gpurun_out/bench_n2_peer.err; tail -1 gpurun_out/bench_n2_peer.json' ;;
+  probe)        # the 256-wide kernel alone on a 606k-row batch: default (TMEM ping-pong) vs MN_TC_TP=0 (shared-memory ping-pong), + the three probes
+    $G --timeout 600 -- 'timeout 150 python scripts/mlp_time.py 256 32 2>&1 | grep "TFLOP\|err"; MN_TC_TP=0 timeout 150 python scripts/mlp_time.py 256 32 2>&1 | grep TFLOP;
+                         timeout 150 python scripts/mlp_time.py 512 8 2>&1 | grep TFLOP;
+                         timeout 120 scripts/probes/mma_chain_probe; timeout 120 scripts/probes/tmem_ld_probe; timeout 120 scripts/probes/l2_stream_probe' ;;
+  ncu-probe)    # full capture of the default kernel on the probe batch (source-level stall samples per role: producer / issuers / epilogue)
+    $G --timeout 600 -- 'timeout 300 ncu --set full --import-source on --clock-control none -k regex:tc_mlp_tp_kernel -s 4 -c 1 -f -o gpurun_out/tc_mlp_tp_kernel_probe python scripts/mlp_time.py 256 32 > gpurun_out/ncu_tp.log 2>&1; ls -la gpurun_out/*.ncu-rep' ;;
+  shapes)       # the other BASELINE shapes and the parity-grade tensor mode, each with its full-size parity sample
+    $G --timeout 900 -- 'for w in c4 c5; do timeout 250 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-incumbent > gpurun_out/bench_$w.json 2>/dev/null; tail -c 600 gpurun_out/bench_$w.json; done;
+                         timeout 250 python bench.py --precision tc_f16x3 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-incumbent > gpurun_out/bench_f16x3.json 2>/dev/null; tail -c 600 gpurun_out/bench_f16x3.json' ;;
   *) sed -n 2,6p "$0"; grep -E '^  [a-z0-9-]+\)' "$0" ;;
 esac

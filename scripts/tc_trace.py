@@ -4,6 +4,7 @@ import os
 import sys
 
 os.environ['MN_TC_TRACE'] = '1'
+os.environ.setdefault('MN_TC_TP', '0')      # the issuer / epilogue timeline events live in the shared-memory ping-pong kernel
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))

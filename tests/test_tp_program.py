@@ -12,10 +12,10 @@ from mega_nerf_b200 import _cabi as K
 TF_FIRST, TF_LAST, TF_FROM_X, TF_WAIT_A = 2, 4, 8, 16
 
 
-def desc(layer_dim=256, layers=8, skips=(4,), pos_dir_dim=4, appearance_dim=48, rgb_dim=3, affine=0):
+def desc(layer_dim=256, layers=8, skips=(4,), pos_dir_dim=4, appearance_dim=48, rgb_dim=3, affine=0, pos_xyz_dim=12):
     d = K.ModelDesc()
     d.kind, d.n_sub = 0, 1
-    d.pos_xyz_dim, d.pos_dir_dim = 12, pos_dir_dim
+    d.pos_xyz_dim, d.pos_dir_dim = pos_xyz_dim, pos_dir_dim
     d.layers, d.layer_dim = layers, layer_dim
     d.appearance_dim, d.affine_appearance, d.appearance_count = appearance_dim, affine, 100
     d.rgb_dim, d.xyz_dim, d.shifted_softplus = rgb_dim, 3, 1
@@ -45,6 +45,8 @@ SHAPES = {
     'narrow_128': dict(layer_dim=128, layers=4, skips=()),
     'w192': dict(layer_dim=192, layers=3, skips=(1,)),
     'no_appearance': dict(appearance_dim=0),
+    'pe16': dict(pos_xyz_dim=16),                 # 99 encoding columns -> 7-stage feature blocks
+    'deep_12': dict(layers=12, skips=(4, 8)),
 }
 
 
