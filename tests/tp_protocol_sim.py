@@ -4,7 +4,12 @@ kernel's mbarriers (full / empty per ring stage, acc_full / d_free / a_ready per
 a random time, so many seeds explore many interleavings.  Independent of the barriers, the model tracks WHAT each resource holds
 (which load a ring stage contains, which accumulator half a tile slot's TMEM columns hold and whether it was drained, which
 GEMM's output the A operand is) and asserts that every read sees what the kernel's arithmetic needs.  A deadlock (all actors
-blocked, nothing in flight) or a stale read fails the test.  Test infrastructure only."""
+blocked, nothing in flight) or a stale read fails the test.  Test infrastructure only.
+
+With a `timing` dict (clock cycles, see scripts/tp_pipeline_model.py) the same model runs deterministically with a shared tensor
+pipe and a wake-up latency per barrier hand-off, and reports where the time goes - a what-if tool for the kernel's dependency ring,
+calibrated against the ncu captures under profiles/."""
+import collections
 import heapq
 import random
 
@@ -14,8 +19,8 @@ TF_FIRST, TF_LAST, TF_FROM_X, TF_WAIT_A = 2, 4, 8, 16
 class MBar:
     """mbarrier: `count` arrivals complete a phase; wait(parity) passes once the phase with that parity has completed."""
 
-    def __init__(self, count):
-        self.count, self.pending, self.phase = count, count, 0
+    def __init__(self, count, name=''):
+        self.count, self.pending, self.phase, self.name = count, count, 0, name
 
     def arrive(self, n=1):
         for _ in range(n):
@@ -31,13 +36,17 @@ class Deadlock(AssertionError):
     pass
 
 
-def simulate(prog, loads, n_stages, n_pairs, odd_tail, seed=0, max_events=2_000_000):
+def simulate(prog, loads, n_stages, n_pairs, odd_tail, seed=0, max_events=2_000_000, timing=None, stats=None):
     """prog / loads: the tables (issuer entries (x, idesc, z, code), producer entries).  odd_tail: the last pair has one tile."""
     rnd = random.Random(seed)
-    full = [MBar(1) for _ in range(n_stages)]
-    empty = [MBar(2) for _ in range(n_stages)]
-    acc_full, d_free, a_ready = [MBar(1), MBar(1)], [MBar(16), MBar(16)], [MBar(16), MBar(16)]
-    turn = [MBar(1), MBar(1)]
+    full = [MBar(1, 'full') for _ in range(n_stages)]
+    empty = [MBar(2, 'empty') for _ in range(n_stages)]
+    acc_full, d_free, a_ready = [MBar(1, 'acc_full'), MBar(1, 'acc_full')], [MBar(16, 'd_free'), MBar(16, 'd_free')], [MBar(16, 'a_ready'), MBar(16, 'a_ready')]
+    turn = [MBar(1, 'token'), MBar(1, 'token')]
+    T = timing
+    pipe_free = [0.0]                                # timing mode: the tensor pipe executes blocks in issue order
+    if stats is not None:
+        stats.update(tensor_busy=0.0, wait=collections.defaultdict(float))
     stage_holds = [None] * n_stages                  # (pair, load index) a ring stage contains
     acc = [dict(state='free', what=None), dict(state='free', what=None)]      # accumulator of a tile slot
     a_op = [None, None]                              # (pair, gemm) whose output the A operand of a slot holds
@@ -69,11 +78,11 @@ def simulate(prog, loads, n_stages, n_pairs, odd_tail, seed=0, max_events=2_000_
                     assert stage_readers[s] == 0, f'TMA overwrites ring stage {s} under {stage_readers[s]} unfinished block(s)'
                     stage_holds[s] = (pr, li)
                     full[s].arrive()
-                later(rnd.uniform(0.2, 3.0), land)           # TMA in flight
+                later(T['tma'] if T else rnd.uniform(0.2, 3.0), land)           # TMA in flight
                 stage += 1
                 if stage == n_stages:
                     stage, phase = 0, phase ^ 1
-                yield ('sleep', rnd.uniform(0.05, 0.3))
+                yield ('sleep', T['prod_stage'] if T else rnd.uniform(0.05, 0.3))
 
     def issuer(sl):
         stage, phase, dph, aph = 0, 0, 0, 0
@@ -87,6 +96,9 @@ def simulate(prog, loads, n_stages, n_pairs, odd_tail, seed=0, max_events=2_000_
             for x, idesc, z, code in prog:
                 ns, fl = (z >> 12) & 0xF, z >> 20
                 gi, h = code // 2, code % 2
+                n_mma = ns if (fl & TF_FROM_X) else 4 * (ns - 1) + ((z >> 16) & 0xF)
+                if T:
+                    yield ('sleep', T['decode'])            # table entry, flags, operand arithmetic
                 if fl & TF_FIRST:
                     yield ('wait', d_free[sl], dph ^ 1)
                     dph ^= 1
@@ -118,8 +130,17 @@ def simulate(prog, loads, n_stages, n_pairs, odd_tail, seed=0, max_events=2_000_
                 for s in blk:
                     stage_readers[s] += 1
                 a_readers[sl] += reads_a_op
-                yield ('sleep', rnd.uniform(0.1, 0.6))          # the issue sequence itself
-                done_at[0] = max(done_at[0], now[0]) + rnd.uniform(0.5, 2.0) * ns     # the tensor pipe executes the block
+                t_issue0 = now[0]
+                yield ('sleep', T['issue_fixed'] + T['issue_mma'] * n_mma if T else rnd.uniform(0.1, 0.6))          # the issue sequence itself
+                if T:
+                    # the pipe starts on the block's first MMA soon after the sequence begins and cannot finish before it ends
+                    start = max(pipe_free[0], t_issue0 + T['first_mma'])
+                    pipe_free[0] = max(start + n_mma * T['mma'], now[0])
+                    done_at[0] = pipe_free[0] + T['commit']
+                    if stats is not None:
+                        stats['tensor_busy'] += n_mma * T['mma']
+                else:
+                    done_at[0] = max(done_at[0], now[0]) + rnd.uniform(0.5, 2.0) * ns     # the tensor pipe executes the block
 
                 def complete(blk=tuple(blk), last=bool(fl & TF_LAST), sl=sl, what=(pr, gi, h), twice=not v1, reads_a_op=reads_a_op):
                     a_readers[sl] -= reads_a_op
@@ -144,10 +165,18 @@ def simulate(prog, loads, n_stages, n_pairs, odd_tail, seed=0, max_events=2_000_
                         yield ('wait', acc_full[sl], aph[sl])
                         aph[sl] ^= 1
                         assert acc[sl] == dict(state='complete', what=(pr, gi, h)), f'epilogue pair {pr} gemm {gi}.{h} slot {sl}: {acc[sl]}'
-                        yield ('sleep', rnd.uniform(0.1, 0.5))      # tcgen05.ld
+                        last_h = h == halves[gi] - 1
+                        yield ('sleep', T['ld'] if T else rnd.uniform(0.1, 0.5))      # tcgen05.ld
+                        if T and (last_h or T.get('d_free_late')):
+                            yield ('sleep', T['math'] / 2)          # the second load completes under the first piece's arithmetic
                         acc[sl].update(state='free', what=None)
                         d_free[sl].arrive(16)
-                        yield ('sleep', rnd.uniform(0.1, 1.0))      # arithmetic
+                        if T:
+                            yield ('sleep', T['math'] / 2 if (last_h or T.get('d_free_late')) else T['math'])
+                            if last_h and gi in _publishers:
+                                yield ('sleep', T['st'])            # tcgen05.st + wait::st + fence
+                        else:
+                            yield ('sleep', rnd.uniform(0.1, 1.0))      # arithmetic
                         if h == halves[gi] - 1 and gi in _publishers:
                             assert a_readers[sl] == 0, f'epilogue overwrites the A operand of slot {sl} under unfinished MMAs'
                             a_op[sl] = (pr, gi)
@@ -173,7 +202,7 @@ def simulate(prog, loads, n_stages, n_pairs, odd_tail, seed=0, max_events=2_000_
                 return
             _, bar, parity = req
             if not bar.passed(parity):
-                blocked[name] = (bar, parity)
+                blocked[name] = (bar, parity, now[0])
                 return
 
     for name in list(actors):
@@ -182,10 +211,16 @@ def simulate(prog, loads, n_stages, n_pairs, odd_tail, seed=0, max_events=2_000_
     while actors:
         # wake whoever can proceed
         progressed = False
-        for name, (bar, parity) in list(blocked.items()):
+        for name, (bar, parity, t0) in list(blocked.items()):
             if bar.passed(parity):
                 del blocked[name]
-                step(name)
+                hop = (T.get('hop_' + name.rstrip('01'), T['hop']) if T else 0.0)      # per-role override: hop_issuer / hop_epilogue / hop_producer
+                if stats is not None:
+                    stats['wait'][(name, bar.name)] += now[0] - t0 + hop
+                if T:
+                    later(hop, lambda name=name: step(name))        # wake-up latency of a barrier hand-off
+                else:
+                    step(name)
                 progressed = True
         if progressed:
             continue
