@@ -318,6 +318,12 @@ int mn_model_backward_tc(mn_ctx* ctx, mn_model* m, int64_t B, int use_coarse, co
  * shared-memory bytes, feature-tile bytes}.  Returns MN_ERR_UNSUPPORTED for shapes this kernel does not run (layer_dim 512,
  * fp32-only shapes).  Used by tests/test_tp_program.py to check the tables' invariants without a GPU. */
 int mn_debug_tp_program(const mn_model_desc* desc, unsigned int* table_out, int cap_entries, int* info8);
+/* In-kernel timeline of CTA 0 of the shared-memory ping-pong MLP kernel and the SM clock during the last MLP launch; recorded
+ * only when the process runs with MN_TC_TRACE=1 (scripts/tc_trace.py).  out: [2][2048] (tag, globaltimer ns) pairs of the MMA
+ * issuer / epilogue warp 0, counts[2] their numbers, reset != 0 clears them; out4 = {clock64, globaltimer} at kernel start and
+ * end.  Both synchronise the device. */
+int mn_debug_read_trace(unsigned long long* out, unsigned int* counts, int reset);
+int mn_debug_read_clock(unsigned long long* out4);
 
 #ifdef __cplusplus
 }
